@@ -1,0 +1,117 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (/root/reference, CPU fp32, via
+tools/ref_shim.py) on the seeded synthetic weights/inputs of mug_diffusion_b200.synth.
+
+Run in the build container only (the GPU box has no /root/reference):
+    python tools/make_goldens.py [--only blocks|unet|ddim]
+"""
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import golden_cases as gc  # noqa: E402
+import ref_shim  # noqa: E402
+from mug_diffusion_b200 import synth  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def get_module(model, path):
+    m = model
+    for part in path.split("."):
+        m = m[int(part)] if part.isdigit() else getattr(m, part)
+    return m
+
+
+def fresh_model(z_length):
+    """A new reference model per config (S4 mutates its state on first use of a length)."""
+    model, _ = ref_shim.load_reference_model(z_length=z_length)
+    sd = synth.synthetic_state_dict(z_length)
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    bad = [k for k in missing if k.startswith("model.unet_model.") or k.startswith("model.first_stage_model.decoder.")]
+    assert not bad and not unexpected, (bad[:5], unexpected[:5])
+    return model, sd
+
+
+def save(name, **arrs):
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **{k: np.asarray(v, dtype=np.float32) for k, v in arrs.items()})
+    print("wrote", name, {k: tuple(np.shape(v)) for k, v in arrs.items()})
+
+
+@torch.no_grad()
+def make_blocks():
+    model, _ = fresh_model(gc.BLOCK_L)
+    out = {}
+    for name, case in gc.BLOCK_CASES.items():
+        mod = get_module(model, case["path"])
+        x = gc.block_input(name, case)
+        if case["kind"] == "res":
+            y = mod(x, gc.block_emb(name))
+        elif case["kind"] == "attn":
+            y = mod(x, gc.block_context(name))
+        else:
+            y = mod(x)
+        out[name] = y.numpy()
+        if case["kind"] == "s4":
+            k, _ = mod.s4_model.kernel(L=x.shape[-1])
+            out[name + ".K"] = k[0].numpy()
+    for name, case in gc.ATTN_CORE_CASES.items():
+        mod = get_module(model, case["path"])
+        x, ctx = gc.attn_core_inputs(name, case)
+        out["core." + name] = mod(x, context=ctx).numpy()
+    save("blocks_L96", **out)
+
+
+@torch.no_grad()
+def make_unet():
+    for name, case in gc.UNET_CASES.items():
+        model, _ = fresh_model(case["L"])
+        inp = synth.synthetic_inputs(case["B"], case["L"])
+        t = torch.tensor(case["t"], dtype=torch.long)
+        t0 = time.time()
+        eps = model.model.forward(inp["x_T"], t, inp["c"], synth.wave_list(inp["w"]))
+        print(name, "ref eval %.2fs" % (time.time() - t0))
+        save(name, eps=eps.numpy())
+
+
+@torch.no_grad()
+def make_ddim():
+    from mug.diffusion.ddim import DDIMSampler
+
+    for name, case in gc.DDIM_CASES.items():
+        model, _ = fresh_model(case["L"])
+        model.z_length = case["L"]
+        inp = synth.synthetic_inputs(case["B"], case["L"])
+        sampler = DDIMSampler(model)
+        pred = []
+        t0 = time.time()
+        z, inter = sampler.sample(S=case["S"], c=inp["c"], w=synth.wave_list(inp["w"]), batch_size=case["B"],
+                                  shape=None, verbose=False, x_T=inp["x_T"], eta=0.0,
+                                  unconditional_guidance_scale=case["scale"],
+                                  unconditional_conditioning=inp["uc"],
+                                  img_callback=lambda p, i: pred.append(p.clone()))
+        logits = model.model.decode(z)
+        print(name, "ref sample+decode %.2fs" % (time.time() - t0))
+        save(name, z=z.numpy(), logits=logits.numpy(), pred_x0_first=pred[0].numpy(), pred_x0_last=pred[-1].numpy())
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default=None)
+    a = ap.parse_args()
+    torch.set_num_threads(os.cpu_count())
+    os.makedirs(GOLD, exist_ok=True)
+    if a.only in (None, "blocks"):
+        make_blocks()
+    if a.only in (None, "unet"):
+        make_unet()
+    if a.only in (None, "ddim"):
+        make_ddim()
