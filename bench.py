@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""Benchmark of the denoising hot path (BASELINE.json metric: denoising-steps/sec).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload NAME]
+
+One "step" = one DDIM step of the workload's whole per-GPU batch: Beff U-Net evaluations (2B with
+classifier-free guidance) + the CFG/DDIM update.  Default workload = BASELINE.json configs[1]:
+3-min audio (z_length 512), 4 charts, webui-default CFG scale 5 (effective U-Net batch 8), 50-step schedule.
+Multi-GPU: every rank runs the same per-GPU batch on different samples after one NCCL weight broadcast
+(weak scaling, no per-step collective); value = N*K / max-over-ranks time.
+
+Prints ONE JSON line (rank 0).  --impl reference times the CPU oracle port of the reference path
+(oracle/mug_oracle.py: torch CPU fp32, all host threads) on the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: z_length, per-GPU batch, CFG scale, schedule length S
+    "L512_B4_cfg5_S50": dict(L=512, B=4, scale=5.0, S=50),
+    "L512_B4_nocfg_S50": dict(L=512, B=4, scale=1.0, S=50),
+    "L512_B32_cfg5_S50": dict(L=512, B=32, scale=5.0, S=50),
+    "L992_B8_cfg5_S100": dict(L=992, B=8, scale=5.0, S=100),
+    "L96_B1_cfg5_S10": dict(L=96, B=1, scale=5.0, S=10),
+}
+GFLOP_PER_EVAL = {96: 4.19, 512: 22.46, 992: 44.37}        # BASELINE.md §3, per sample-eval
+METRIC = "denoising-steps/sec"
+UNIT = "DDIM steps/s (whole per-GPU batch per step, summed over GPUs)"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(tflops=float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1590.0))), hbm=float(d.get("hbm_gbs", 6650.0)),
+                    src="measured (MEASURED_PEAKS.json bf16_tflops_sustained)")
+    return dict(tflops=1400.0, hbm=6650.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def make_inputs(wl, rank):
+    from mug_diffusion_b200 import synth
+
+    return synth.synthetic_inputs(wl["B"], wl["L"], seed=1234 + rank)
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline : the oracle port of the reference path on the host cores
+# ---------------------------------------------------------------------------------------------------
+def time_oracle_steps(wl, steps, warmup, sd=None):
+    """DDIM steps of the CPU oracle (full workload batch, CFG as configured); returns (steps/s, threads)."""
+    from mug_diffusion_b200 import synth
+    from oracle import mug_oracle as orc
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = sd or synth.synthetic_state_dict(wl["L"], decoder=False)
+    inp = make_inputs(wl, 0)
+    sch = orc.make_schedule(wl["S"])
+    ts = np.flip(sch["timesteps"])
+    x = inp["x_T"]
+    B = wl["B"]
+    cfg = wl["scale"] != 1.0
+
+    def one(i, x):
+        t = torch.full((B,), int(ts[i % len(ts)]), dtype=torch.long)
+        with torch.no_grad():
+            if cfg:
+                e = orc.unet_forward(sd, torch.cat([x, x]), torch.cat([t, t]), torch.cat([inp["uc"], inp["c"]]),
+                                     [torch.cat([w, w]) for w in inp["w"]])
+                eu, ec = e.chunk(2)
+                e = eu + wl["scale"] * (ec - eu)
+            else:
+                e = orc.unet_forward(sd, x, t, inp["c"], inp["w"])
+        idx = len(ts) - 1 - (i % len(ts))
+        a_t, a_prev = float(sch["alphas"][idx]), float(sch["alphas_prev"][idx])
+        pred = (x - float(sch["sqrt_one_minus_alphas"][idx]) * e) / a_t ** 0.5
+        return a_prev ** 0.5 * pred + (1 - a_prev) ** 0.5 * e
+
+    for i in range(warmup):
+        x = one(i, x)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        x = one(warmup + i, x)
+    dt = time.perf_counter() - t0
+    return steps / dt, torch.get_num_threads(), dt
+
+
+def run_reference(args, wl, name):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    v, threads, dt = time_oracle_steps(wl, args.steps, args.warmup)
+    line = dict(metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=1000.0 / v, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                impl="reference",
+                config=dict(workload=name, z_length=wl["L"], per_gpu_batch=wl["B"], cfg_scale=wl["scale"], schedule_S=wl["S"],
+                            note="CPU oracle port of the reference PyTorch path (oracle/mug_oracle.py, bit-identical to the "
+                                 "reference on tests/golden); S4 kernels regenerated every eval like the reference"),
+                cpu_baseline=dict(value=v, unit=UNIT, cores=threads, kind="port", sample=f"{args.steps} full DDIM steps of the workload"),
+                e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="L512_B4_cfg5_S50", choices=list(WORKLOADS))
+    ap.add_argument("--gemm", default=os.environ.get("MUGD_GEMM", "auto"), choices=["auto", "simt", "tc"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return run_reference(args, wl, args.workload)
+
+    import torch.distributed as dist
+
+    from mug_diffusion_b200 import lib as L_
+    from mug_diffusion_b200 import synth
+    from mug_diffusion_b200.config import ModelConfig
+    from mug_diffusion_b200.dist import broadcast_blob
+    from mug_diffusion_b200.engine import OpList
+    from mug_diffusion_b200.sampler import DDIMSampler, MugDiffusionB200, _ptr
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun"
+    dev = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(dev)
+    cfg = ModelConfig()
+    L, B, S = wl["L"], wl["B"], wl["S"]
+    cfg_on = wl["scale"] != 1.0
+    Beff = 2 * B if cfg_on else B
+
+    # ---- weights: rank 0 builds + packs, one NCCL broadcast ---------------------------------------
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        sd = synth.synthetic_state_dict(L) if rank == 0 else None
+        blob = broadcast_blob(sd, cfg, dev)
+        model = MugDiffusionB200(None, cfg, z_length=L, device=dev, gemm_impl=args.gemm, blob=blob)
+    else:
+        sd = synth.synthetic_state_dict(L)
+        model = MugDiffusionB200(sd, cfg, z_length=L, device=dev, gemm_impl=args.gemm)
+    eng = model.engine
+    inp = make_inputs(wl, rank)
+    sampler = DDIMSampler(model)
+
+    # ---- device-resident timed loop ("value") -----------------------------------------------------
+    # Set the request up exactly as sample() does, then drive K steps of (graph replay + update) by hand.
+    sampler.make_schedule(S, verbose=False)
+    sess = eng.session(Beff, L, per_sample_t=False)
+    ts = np.flip(sampler.ddim_timesteps)
+    reps = (args.steps + args.warmup) // len(ts) + 1
+    sess.set_timestep_table(np.tile(ts, reps)[:min(1000, len(ts) * reps)])
+    ctx = torch.cat([inp["uc"], inp["c"]]).to(dev) if cfg_on else inp["c"].to(dev)
+    aud = [torch.cat([w, w]).to(dev) if cfg_on else w.to(dev) for w in inp["w"]]
+    sess.set_context(ctx)
+    sess.set_audio(aud)
+    coef = np.stack([np.asarray(a, dtype=np.float32) for a in (sampler.ddim_alphas, sampler.ddim_alphas_prev, sampler.ddim_sigmas,
+                                                               sampler.ddim_sqrt_one_minus_alphas)], axis=1)
+    # the step counter runs 0..K+W-1 monotonically; replicate the coefficient table so row (S'-1-i) is valid
+    total_rows = min(1000, len(ts) * reps)
+    coef_rep = np.ascontiguousarray(np.tile(coef, (reps, 1))[:total_rows])
+    sess.coef[:total_rows].copy_(torch.from_numpy(coef_rep).to(dev))
+    sess.load_x(inp["x_T"].to(dev), dup=cfg_on)
+    sess.set_step(0)
+    n = B * L * 16
+    upd = L_.DdimUpdate()
+    upd.x = sess.xin.ptr
+    upd.x_dup = sess.xin.r(B * L, 2 * B * L).ptr if cfg_on else None
+    upd.eps, upd.coef, upd.step = sess.eps.ptr, _ptr(sess.coef), _ptr(sess.step)
+    upd.S, upd.n, upd.cfg, upd.scale, upd.temperature = total_rows, n, int(cfg_on), float(wl["scale"]), 1.0
+    adv = L_.StepAdvance()
+    adv.step = _ptr(sess.step)
+    tail = OpList()
+    tail.add(L_.OP_DDIM_UPDATE, upd)
+    tail.add(L_.OP_STEP_ADVANCE, adv)
+    assert args.steps + args.warmup <= total_rows, "steps+warmup exceeds the 1000-row step tables"
+
+    def step():
+        sess.eval(graph=True)
+        eng.run_ops(tail)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    clock_info = clocks.stop() if rank == 0 else None
+    launches_per_step = sess.plan.launches + 2
+    value = world * args.steps / (ms / 1000.0)
+    finite = bool(torch.isfinite(sess.read_rows(sess.eps, Beff, 16, L)).all())
+
+    # ---- roofline of the dominant kernel family (GEMM): per-op CUDA-event timing of one eager eval ------
+    roof = None
+    if rank == 0:
+        import ctypes as C
+        ops = sess.plan._arr
+        st = torch.cuda.current_stream().cuda_stream
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(sess.plan.n_ops + 1)]
+        for rep in range(2):        # second pass is the measured one
+            evs[0].record()
+            for i in range(sess.plan.n_ops):
+                L_.check(eng.lib.mugd_op_run(eng.handle, C.byref(ops[i]), st), "op")
+                evs[i + 1].record()
+            torch.cuda.synchronize()
+        by_kind = {}
+        gemm_flops = gemm_ms = 0.0
+        gemm_n = 0
+        for i in range(sess.plan.n_ops):
+            dt = evs[i].elapsed_time(evs[i + 1])
+            k = ops[i].kind
+            by_kind[k] = by_kind.get(k, 0.0) + dt
+            if k == L_.OP_GEMM:
+                g = ops[i].u.gemm
+                gemm_flops += 2.0 * g.M * g.N * g.K * g.taps
+                gemm_ms += dt
+                gemm_n += 1
+        pk = measured_peaks()
+        ach = gemm_flops / (gemm_ms * 1e-3) / 1e12
+        names = {1: "gemm", 2: "groupnorm", 3: "layernorm", 4: "attention", 5: "s4conv", 7: "transpose", 8: "copy2d"}
+        roof = dict(bound="tensor", kernel=f"gemm ({eng.gemm_impl})", achieved=ach, peak=pk["tflops"], unit="TFLOP/s",
+                    frac=ach / pk["tflops"], traffic=None, peak_source=pk["src"], launches=gemm_n,
+                    avg_launch_us=1000.0 * gemm_ms / max(gemm_n, 1), algorithmic_gflop_per_eval_batch=gemm_flops / 1e9,
+                    eager_ms_by_kernel={names.get(k, str(k)): round(v, 4) for k, v in sorted(by_kind.items())})
+
+    # ---- end to end through the public API with HOST (pinned) inputs ----------------------------------
+    e2e = None
+    host = dict(x_T=inp["x_T"].pin_memory(), c=inp["c"].pin_memory(), uc=inp["uc"].pin_memory(), w=[w.pin_memory() for w in inp["w"]])
+    h2d = sum(t.numel() * 4 for t in [host["x_T"], host["c"], host["uc"]] + host["w"])
+    K = min(args.steps, 1000)
+
+    def request():
+        c = host["c"].to(dev, non_blocking=True)
+        uc = host["uc"].to(dev, non_blocking=True)
+        w = [t.to(dev, non_blocking=True) for t in host["w"]]
+        xT = host["x_T"].to(dev, non_blocking=True)
+        z, _ = sampler.sample(S=K, c=c, w=w, batch_size=B, shape=(16, L), verbose=False, x_T=xT, eta=0.0,
+                              unconditional_guidance_scale=wl["scale"], unconditional_conditioning=uc, tqdm_class=_NoBar)
+        logits = model.model.decode(z)
+        return logits.to("cpu", non_blocking=False)
+
+    request()                                   # warm (decoder plan, graph already captured)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    out = request()
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    n_steps_e2e = len(sampler.ddim_timesteps)
+    e2e = dict(value=world * n_steps_e2e / float(dt.item()), unit=UNIT, h2d_bytes_per_step=h2d / n_steps_e2e,
+               d2h_bytes_per_step=out.numel() * 4 / n_steps_e2e,
+               note=f"one sampler.sample(S={K}) + decode request per GPU from pinned host inputs to host logits; "
+                    f"{n_steps_e2e} DDIM steps; per-step bytes = request bytes / steps")
+
+    # ---- CPU baseline (rank 0, N=1 only, bounded sample) ------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, threads, dtc = time_oracle_steps(wl, args.cpu_steps, 1, sd={k: v for k, v in sd.items() if k.startswith("model.unet_model.")})
+        cpu = dict(value=v, unit=UNIT, cores=threads, kind="port",
+                   sample=f"{args.cpu_steps} full DDIM steps (+1 warm-up) of the same workload on the CPU oracle port, {dtc:.1f} s")
+
+    if rank == 0:
+        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+                    ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                    config=dict(workload=args.workload, z_length=L, per_gpu_batch=B, global_batch=B * world, unet_batch_per_gpu=Beff,
+                                cfg_scale=wl["scale"], schedule_S=S, gemm_impl=eng.gemm_impl, parallelism=f"replica-sharded batch x{world}",
+                                l2="working set exceeds L2: 421 MB of fp32 weights are streamed every step",
+                                gflop_per_step=Beff * GFLOP_PER_EVAL.get(L, 0.0), outputs_finite=finite),
+                    roofline=roof, cpu_baseline=cpu, e2e=e2e, gpu_launches=launches_per_step * args.steps,
+                    launches_per_step=launches_per_step, clocks=clock_info)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+class _NoBar:
+    def __init__(self, it, **kw):
+        self.it = it
+
+    def __iter__(self):
+        return iter(self.it)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,189 @@
+/*
+ * mugd.h -- C ABI of libmugd.so, the sm_100a (B200) denoising engine for Mug-Diffusion.
+ *
+ * The reference (Keytoyze/Mug-Diffusion) has no FFI: its hot path is Python calling ATen.  The boundary
+ * this library replaces is therefore the set of Python call sites
+ *     DDIMSampler.sample / ddim_sampling / p_sample_ddim   mug/diffusion/ddim.py:56-196
+ *     MugDiffusionWrapper.forward -> UNetModel.forward       mug/diffusion/diffusion.py:52-54, unet.py:511-550
+ *     MugDiffusionWrapper.decode  -> Decoder.forward         mug/diffusion/diffusion.py:49-50, autoencoder.py:329-354
+ * and the entry points below are what a ctypes binding on the reference side would call
+ * (INTEGRATION.md shows that binding).  Plain pointers and sizes only: every pointer is a DEVICE pointer
+ * into memory the caller owns (torch allocations in the Python host), `stream` is a cudaStream_t passed
+ * as void*.  No CPU fallback exists: mugd_create fails on anything that is not compute capability 10.x.
+ *
+ * Execution model: the host "compiles" a network evaluation into a flat launch plan (array of mugd_op,
+ * pointers fully resolved), the library validates it, optionally captures it into a CUDA graph, and
+ * replays it once per DDIM step with zero host synchronisation.  Step-dependent data (time-embedding
+ * rows, DDIM coefficients) is indexed on the device through a step counter, so one graph serves all steps.
+ *
+ * Activation layout: channels-last  [B * L, C]  fp32 row-major with explicit leading dimension, so a
+ * channel concat is a column range of a wider buffer (unet.py:114-118,545 torch.cat -> zero copies).
+ */
+#ifndef MUGD_H
+#define MUGD_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MUGD_ABI_VERSION 3
+
+typedef struct mugd_handle mugd_handle;   /* one device + scratch state            */
+typedef struct mugd_plan mugd_plan;       /* validated launch plan (+ CUDA graph)  */
+
+enum mugd_status {
+    MUGD_OK = 0,
+    MUGD_ERR_INVALID = 1,      /* bad argument / unsupported shape            */
+    MUGD_ERR_CUDA = 2,         /* CUDA runtime error (see mugd_last_error)    */
+    MUGD_ERR_NO_DEVICE = 3,    /* not an sm_100 device; there is no fallback  */
+    MUGD_ERR_OOM = 4
+};
+
+enum mugd_op_kind {
+    MUGD_OP_GEMM = 1,          /* Linear / 1x1 conv / conv3 / strided conv / upsample+conv, fused epilogue */
+    MUGD_OP_GROUPNORM = 2,     /* GroupNorm(eps) [+ SiLU]                                                    */
+    MUGD_OP_LAYERNORM = 3,
+    MUGD_OP_ATTENTION = 4,     /* rel-pos-biased softmax attention with post-softmax gain                   */
+    MUGD_OP_S4CONV = 5,        /* causal long convolution + D*u + GELU                                       */
+    MUGD_OP_DDIM_UPDATE = 6,   /* CFG combine + x_{t-1} update                                              */
+    MUGD_OP_TRANSPOSE = 7,     /* [B,C,L] <-> [B,L,C] with leading dimensions                                */
+    MUGD_OP_COPY2D = 8,        /* strided row copy                                                           */
+    MUGD_OP_STEP_ADVANCE = 9   /* *step += 1                                                                 */
+};
+
+/* A-operand row addressing of MUGD_OP_GEMM (rows are tokens of B samples, Lout output rows each) */
+enum mugd_conv_mode {
+    MUGD_CONV_NONE = 0,        /* taps=1: Linear / 1x1 conv (unet.py skip_connection, attention.py proj_in)  */
+    MUGD_CONV_SAME = 1,        /* taps=3, pad 1: nn.Conv1d(k=3,padding=1)                                    */
+    MUGD_CONV_DOWN = 2,        /* taps=3, right-pad 1, stride 2: models.py:84-91 Downsample                  */
+    MUGD_CONV_UP = 3           /* nearest x2 then taps=3 pad 1: models.py:66-70 Upsample                     */
+};
+enum mugd_act { MUGD_ACT_NONE = 0, MUGD_ACT_SILU = 1, MUGD_ACT_GELU = 2 };
+/* gated epilogues: weight rows are interleaved (value_j, gate_j) by the packer; output has N/2 columns */
+enum mugd_gate { MUGD_GATE_NONE = 0, MUGD_GATE_GEGLU = 1 /* a*gelu(g), attention.py:38-45 */,
+                 MUGD_GATE_GLU = 2 /* a*sigmoid(g), s4.py:191-192,1536 */ };
+enum mugd_gemm_impl { MUGD_GEMM_AUTO = 0, MUGD_GEMM_SIMT = 1 /* exact fp32 FMA */,
+                      MUGD_GEMM_TC = 2 /* tcgen05 3xTF32 split, fp32 accumulate in TMEM */ };
+
+typedef struct mugd_gemm {
+    const float* A;  int64_t lda;          /* [B*Lin, K] activations                                       */
+    const float* W;                        /* [N][taps*K], K-major per tap (conv weight [Cout][k][Cin])    */
+    const float* W_lo;                     /* optional fp32 residual of the TF32 split (tensor-core path)  */
+    const float* bias;                     /* [N] or NULL                                                  */
+    const float* rowvec;                   /* per-sample row vector added before act: time embedding       */
+    int64_t rowvec_b_stride;               /*   rowvec[step*step_stride + b*b_stride + n]                  */
+    int64_t rowvec_step_stride;
+    const int32_t* step;                   /* device step counter or NULL (=0)                             */
+    const float* residual; int64_t ldr;    /* added after act/gate, or NULL                                */
+    float* C;        int64_t ldc;          /* [B*Lout, N] (N/2 when gated)                                 */
+    int32_t M, N, K;                       /* M = B*Lout rows, N weight rows, K channels per tap           */
+    int32_t taps, conv_mode, Lin, Lout;
+    int32_t act, gate, impl;
+} mugd_gemm;
+
+typedef struct mugd_groupnorm {
+    const float* x; int64_t ldx; float* y; int64_t ldy;
+    const float* gamma; const float* beta;
+    int32_t B, L, C, G; float eps; int32_t silu;
+} mugd_groupnorm;
+
+typedef struct mugd_layernorm {
+    const float* x; int64_t ldx; float* y; int64_t ldy;
+    const float* gamma; const float* beta;
+    int32_t rows, C; float eps;
+} mugd_layernorm;
+
+typedef struct mugd_attention {
+    const float* q; int64_t ldq;           /* [B*Lq, H*D] head h at columns h*D..                          */
+    const float* k; int64_t ldk;           /* [B*Lk, H*D]                                                  */
+    const float* v; int64_t ldv;
+    float* o; int64_t ldo;
+    const float* relpos;                   /* [2*pos_max+1][H] additive, inside the scale (attention.py:113) */
+    const float* cgain;                    /* [2*pos_max+1][H] post-softmax multiplier (attention.py:122)   */
+    int32_t B, H, D, Lq, Lk, pos_max; float scale;
+} mugd_attention;
+
+typedef struct mugd_s4conv {
+    const float* u; int64_t ldu;           /* [B*L, H]                                                     */
+    const float* Kt;                       /* [L][H] kernel taps, tap-major (from mugd_s4_kernel_gen)      */
+    const float* D;                        /* [H]                                                          */
+    float* y; int64_t ldy;                 /* gelu(conv + D*u)                                             */
+    int32_t B, L, H;
+} mugd_s4conv;
+
+typedef struct mugd_ddim_update {
+    float* x;                              /* [B*L, C] in place -> x_{t-1}                                  */
+    float* x_dup;                          /* optional second copy of x_{t-1} (the cfg half of the 2B batch) */
+    const float* eps;                      /* [Beff*L, C]; Beff = 2B when cfg (uncond first, ddim.py:173)   */
+    const float* noise;                    /* [B*L, C] or NULL (sigma = 0)                                  */
+    float* pred_x0;                        /* [B*L, C] or NULL                                              */
+    const float* coef;                     /* [S][4] = a_t, a_prev, sigma_t, sqrt(1-a_t) per DDIM index     */
+    const int32_t* step;                   /* device step counter i; row used = S-1-i (ddim.py:138)         */
+    int32_t S; int32_t n;                  /* n = B*L*C elements                                            */
+    int32_t cfg; float scale; float temperature;
+} mugd_ddim_update;
+
+typedef struct mugd_transpose {            /* to_nlc=1: in [B,C,L] (contiguous) -> out [B*L, ldo] cols 0..C  */
+    const float* in; float* out;           /* to_nlc=0: in [B*L, ldi] -> out [B,C,L]                          */
+    int64_t ldi, ldo; int32_t B, C, L, to_nlc;
+} mugd_transpose;
+
+typedef struct mugd_copy2d {
+    const float* src; int64_t lds; float* dst; int64_t ldd; int32_t rows, cols;
+} mugd_copy2d;
+
+typedef struct mugd_step_advance { int32_t* step; } mugd_step_advance;
+
+typedef struct mugd_op {
+    int32_t kind;
+    int32_t tag;                           /* free for the host (profiling labels)                          */
+    union {
+        mugd_gemm gemm; mugd_groupnorm gn; mugd_layernorm ln; mugd_attention attn; mugd_s4conv s4;
+        mugd_ddim_update ddim; mugd_transpose tr; mugd_copy2d cp; mugd_step_advance adv;
+    } u;
+} mugd_op;
+
+/* ---- lifecycle -------------------------------------------------------------------------------- */
+int  mugd_abi_version(void);
+const char* mugd_last_error(void);                         /* thread-local message of the last failure */
+int  mugd_create(int device, mugd_handle** out);           /* MUGD_ERR_NO_DEVICE unless sm_100          */
+void mugd_destroy(mugd_handle* h);
+int  mugd_device_info(mugd_handle* h, int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
+int  mugd_set_gemm_impl(mugd_handle* h, int impl);         /* default for ops with impl == AUTO         */
+
+/* ---- single op (parity tests call every kernel through this) ---------------------------------- */
+int  mugd_op_run(mugd_handle* h, const mugd_op* op, void* stream);
+
+/* ---- plans ------------------------------------------------------------------------------------ */
+int  mugd_plan_create(mugd_handle* h, const mugd_op* ops, int32_t n_ops, mugd_plan** out);
+int  mugd_plan_run(mugd_plan* p, void* stream);            /* eager launches                            */
+int  mugd_plan_capture(mugd_plan* p, void* stream);        /* build + instantiate a CUDA graph          */
+int  mugd_plan_replay(mugd_plan* p, int32_t times, void* stream); /* launch the graph `times` times     */
+int  mugd_plan_launch_count(mugd_plan* p);                 /* kernels launched by one run of the plan   */
+void mugd_plan_destroy(mugd_plan* p);
+
+/* ---- S4 kernel generation: SSKernelNPLR.forward, s4.py:706-832 (once per model and length) ----- */
+int  mugd_s4_kernel_gen(mugd_handle* h,
+                        const float* log_dt,      /* [H]        */
+                        const float* Bri,         /* [H][N][2]  */
+                        const float* Cri,         /* [H][N][2]  */
+                        const float* Pri,         /* [H][N][2]  */
+                        const float* inv_w_real,  /* [H][N]     */
+                        const float* w_imag,      /* [H][N]     */
+                        int32_t H, int32_t N, int32_t L_internal, int32_t L_out,
+                        float* Kt,                /* [L_out][H] */
+                        void* workspace, int64_t workspace_bytes, /* >= 16*H*(L_internal/2+1) bytes */
+                        void* stream);
+
+/* ---- utility ---------------------------------------------------------------------------------- */
+int  mugd_fill_i32(int32_t* dst, int32_t value, void* stream);
+/* sizeof() of {mugd_op, mugd_gemm, mugd_groupnorm, mugd_layernorm, mugd_attention, mugd_s4conv,
+ * mugd_ddim_update, mugd_transpose, mugd_copy2d} so a foreign-language mirror can verify its layout */
+int  mugd_abi_sizes(int32_t* out, int32_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MUGD_H */

@@ -1,0 +1,139 @@
+// Small fused elementwise kernels of the sampler loop:
+//   ddim_update : classifier-free-guidance combine + DDIM x_{t-1} update   mug/diffusion/ddim.py:170-195
+//   transpose   : [B,C,L] <-> channels-last [B*L, ld] at the Python boundary (reference tensors are NCL)
+//   copy2d      : strided row copy (the 4 per-level tensors that live in two concat buffers)
+//   step_advance: device-side step counter so one CUDA graph serves every DDIM step
+#include "common.cuh"
+
+namespace mugd {
+
+// x_prev = sqrt(a_prev) * (x - sqrt(1-a_t) e)/sqrt(a_t) + sqrt(1 - a_prev - sigma^2) e + sigma*noise*T
+// written with explicit _rn intrinsics: same operation order and roundings as the reference's separate
+// ATen ops (no FMA contraction), so given identical eps the update is bit-identical.
+__global__ void __launch_bounds__(256)
+ddim_update_kernel(const mugd_ddim_update d) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.n) return;
+    const int step = d.step ? *d.step : 0;
+    const int index = d.S - 1 - step;                     // ddim.py:138
+    const float* cf = d.coef + 4 * index;
+    const float a_t = cf[0], a_prev = cf[1], sigma = cf[2], s1m = cf[3];
+    float e;
+    if (d.cfg) {
+        const float eu = d.eps[i], ec = d.eps[(int64_t)d.n + i];
+        e = __fadd_rn(eu, __fmul_rn(d.scale, __fsub_rn(ec, eu)));   // ddim.py:175
+    } else {
+        e = d.eps[i];
+    }
+    const float x = d.x[i];
+    const float pred = __fdiv_rn(__fsub_rn(x, __fmul_rn(s1m, e)), __fsqrt_rn(a_t));            // :189
+    const float dir = __fmul_rn(__fsqrt_rn(__fsub_rn(__fsub_rn(1.0f, a_prev), __fmul_rn(sigma, sigma))), e);  // :191
+    float xp = __fadd_rn(__fmul_rn(__fsqrt_rn(a_prev), pred), dir);
+    const float nz = d.noise ? __fmul_rn(__fmul_rn(sigma, d.noise[i]), d.temperature) : 0.0f;  // :192
+    xp = __fadd_rn(xp, nz);                                                                     // :195
+    d.x[i] = xp;
+    if (d.x_dup) d.x_dup[i] = xp;
+    if (d.pred_x0) d.pred_x0[i] = pred;
+}
+
+int launch_ddim_update(const DeviceInfo&, const mugd_ddim_update& d, cudaStream_t st, int* launches) {
+    MUGD_REQUIRE(d.n > 0 && d.S > 0 && d.x && d.eps && d.coef, "ddim_update: bad arguments");
+    ddim_update_kernel<<<(d.n + 255) / 256, 256, 0, st>>>(d);
+    MUGD_CHECK_CUDA(cudaGetLastError());
+    if (launches) *launches += 1;
+    return MUGD_OK;
+}
+
+// 32x32 smem-tiled transpose, coalesced on both sides.
+__global__ void __launch_bounds__(256)
+transpose_kernel(const mugd_transpose t) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    const int c0 = blockIdx.y * 32, l0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    if (t.to_nlc) {
+        const float* in = t.in + (int64_t)b * t.C * t.L;
+#pragma unroll
+        for (int r = ty; r < 32; r += 8) {
+            const int c = c0 + r, l = l0 + tx;
+            tile[r][tx] = (c < t.C && l < t.L) ? in[(int64_t)c * t.L + l] : 0.f;
+        }
+        __syncthreads();
+        float* out = t.out + (int64_t)b * t.L * t.ldo;
+#pragma unroll
+        for (int r = ty; r < 32; r += 8) {
+            const int l = l0 + r, c = c0 + tx;
+            if (c < t.C && l < t.L) out[(int64_t)l * t.ldo + c] = tile[tx][r];
+        }
+    } else {
+        const float* in = t.in + (int64_t)b * t.L * t.ldi;
+#pragma unroll
+        for (int r = ty; r < 32; r += 8) {
+            const int l = l0 + r, c = c0 + tx;
+            tile[r][tx] = (c < t.C && l < t.L) ? in[(int64_t)l * t.ldi + c] : 0.f;
+        }
+        __syncthreads();
+        float* out = t.out + (int64_t)b * t.C * t.L;
+#pragma unroll
+        for (int r = ty; r < 32; r += 8) {
+            const int c = c0 + r, l = l0 + tx;
+            if (c < t.C && l < t.L) out[(int64_t)c * t.L + l] = tile[tx][r];
+        }
+    }
+}
+
+int launch_transpose(const DeviceInfo&, const mugd_transpose& t, cudaStream_t st, int* launches) {
+    MUGD_REQUIRE(t.B > 0 && t.C > 0 && t.L > 0 && t.in && t.out, "transpose: bad arguments");
+    MUGD_REQUIRE(t.B <= 65535 && (t.C + 31) / 32 <= 65535, "transpose: grid too large");
+    if (t.to_nlc) MUGD_REQUIRE(t.ldo >= t.C, "transpose: ldo < C");
+    else MUGD_REQUIRE(t.ldi >= t.C, "transpose: ldi < C");
+    dim3 grid((t.L + 31) / 32, (t.C + 31) / 32, t.B);
+    transpose_kernel<<<grid, 256, 0, st>>>(t);
+    MUGD_CHECK_CUDA(cudaGetLastError());
+    if (launches) *launches += 1;
+    return MUGD_OK;
+}
+
+__global__ void __launch_bounds__(256)
+copy2d_kernel(const mugd_copy2d c) {
+    const int q = c.cols >> 2;
+    const int64_t total = (int64_t)c.rows * q;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / q;
+        const int cc = (int)(i - r * q) * 4;
+        st_f4(c.dst + r * c.ldd + cc, ld_f4(c.src + r * c.lds + cc));
+    }
+}
+
+int launch_copy2d(const DeviceInfo& dev, const mugd_copy2d& c, cudaStream_t st, int* launches) {
+    MUGD_REQUIRE(c.rows > 0 && c.cols > 0 && c.cols % 4 == 0 && c.lds % 4 == 0 && c.ldd % 4 == 0 && aligned16(c.src) && aligned16(c.dst),
+                 "copy2d: shape/alignment");
+    const int64_t total = (int64_t)c.rows * (c.cols / 4);
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > dev.sm_count * 8) blocks = dev.sm_count * 8;
+    copy2d_kernel<<<blocks, 256, 0, st>>>(c);
+    MUGD_CHECK_CUDA(cudaGetLastError());
+    if (launches) *launches += 1;
+    return MUGD_OK;
+}
+
+__global__ void step_advance_kernel(int32_t* step) { *step += 1; }
+__global__ void fill_i32_kernel(int32_t* p, int32_t v) { *p = v; }
+
+int launch_step_advance(const DeviceInfo&, const mugd_step_advance& a, cudaStream_t st, int* launches) {
+    MUGD_REQUIRE(a.step, "step_advance: null counter");
+    step_advance_kernel<<<1, 1, 0, st>>>(a.step);
+    MUGD_CHECK_CUDA(cudaGetLastError());
+    if (launches) *launches += 1;
+    return MUGD_OK;
+}
+
+}  // namespace mugd
+
+extern "C" int mugd_fill_i32(int32_t* dst, int32_t value, void* stream) {
+    using namespace mugd;
+    MUGD_REQUIRE(dst, "fill_i32: null");
+    fill_i32_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(dst, value);
+    MUGD_CHECK_CUDA(cudaGetLastError());
+    return MUGD_OK;
+}

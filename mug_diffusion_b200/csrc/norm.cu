@@ -1,0 +1,147 @@
+// GroupNorm(+SiLU) and LayerNorm on channels-last activations.  HBM/L2-bandwidth kernels:
+// 128-bit vector loads, per-thread fp64 partial moments, warp-shuffle + one smem hop block reduction.
+//
+// Reference semantics:
+//   Normalize = GroupNorm(num_groups, C, eps=1e-6, affine)      mug/model/models.py:10-13
+//   followed by SiLU in TimestepResBlock / ResnetBlock / out     mug/diffusion/unet.py:153-157,174-181,489-491
+//   nn.LayerNorm(dim) eps=1e-5                                   mug/model/attention.py:136-138
+#include "common.cuh"
+
+namespace mugd {
+
+// One CTA per (group, sample).  The (L x cg) slab of a group is read twice (moments, then apply);
+// the second read is served by L1/L2.  cg is a multiple of 4 so every float4 belongs to one group.
+constexpr int GN_THREADS = 256;
+
+__global__ void __launch_bounds__(GN_THREADS)
+groupnorm_silu_kernel(const float* __restrict__ x, int64_t ldx, float* __restrict__ y, int64_t ldy,
+                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                      int L, int C, int G, float eps, int silu) {
+    const int g = blockIdx.x, b = blockIdx.y;
+    const int cg = C / G;
+    const int q = cg >> 2;                 // float4 per row of this group
+    const int total = L * q;
+    const float* xb = x + (int64_t)b * L * ldx + (int64_t)g * cg;
+    float* yb = y + (int64_t)b * L * ldy + (int64_t)g * cg;
+
+    double s = 0.0, ss = 0.0;
+    for (int i = threadIdx.x; i < total; i += GN_THREADS) {
+        const int row = i / q, qq = i - row * q;
+        const float4 v = ld_f4(xb + (int64_t)row * ldx + qq * 4);
+        s += (double)v.x + (double)v.y + (double)v.z + (double)v.w;
+        ss += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+    }
+    __shared__ double red[2][GN_THREADS / 32];
+    __shared__ float stats[2];
+    s = warp_sum(s);
+    ss = warp_sum(ss);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { red[0][warp] = s; red[1][warp] = ss; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double ts = 0.0, tss = 0.0;
+#pragma unroll
+        for (int w = 0; w < GN_THREADS / 32; ++w) { ts += red[0][w]; tss += red[1][w]; }
+        const double n = (double)L * cg;
+        const double mean = ts / n;
+        double var = tss / n - mean * mean;
+        if (var < 0.0) var = 0.0;
+        stats[0] = (float)mean;
+        stats[1] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+    __syncthreads();
+    const float mean = stats[0], rstd = stats[1];
+    const float* gm = gamma + g * cg;
+    const float* bt = beta + g * cg;
+    for (int i = threadIdx.x; i < total; i += GN_THREADS) {
+        const int row = i / q, qq = i - row * q;
+        const float4 v = ld_f4(xb + (int64_t)row * ldx + qq * 4);
+        const float4 ga = ld_f4(gm + qq * 4);
+        const float4 be = ld_f4(bt + qq * 4);
+        float4 o;
+        o.x = (v.x - mean) * rstd * ga.x + be.x;
+        o.y = (v.y - mean) * rstd * ga.y + be.y;
+        o.z = (v.z - mean) * rstd * ga.z + be.z;
+        o.w = (v.w - mean) * rstd * ga.w + be.w;
+        if (silu) { o.x = silu_f(o.x); o.y = silu_f(o.y); o.z = silu_f(o.z); o.w = silu_f(o.w); }
+        st_f4(yb + (int64_t)row * ldy + qq * 4, o);
+    }
+}
+
+int launch_groupnorm(const DeviceInfo&, const mugd_groupnorm& g, cudaStream_t st, int* launches) {
+    MUGD_REQUIRE(g.B > 0 && g.L > 0 && g.C > 0 && g.G > 0, "groupnorm: empty shape B=%d L=%d C=%d G=%d", g.B, g.L, g.C, g.G);
+    MUGD_REQUIRE(g.C % g.G == 0 && (g.C / g.G) % 4 == 0, "groupnorm: C/G must be a multiple of 4 (C=%d G=%d)", g.C, g.G);
+    MUGD_REQUIRE(g.ldx % 4 == 0 && g.ldy % 4 == 0 && aligned16(g.x) && aligned16(g.y) && aligned16(g.gamma) && aligned16(g.beta),
+                 "groupnorm: operands must be 16-byte aligned with ld %% 4 == 0");
+    MUGD_REQUIRE(g.ldx >= g.C && g.ldy >= g.C, "groupnorm: leading dimension smaller than C");
+    dim3 grid(g.G, g.B);
+    groupnorm_silu_kernel<<<grid, GN_THREADS, 0, st>>>(g.x, g.ldx, g.y, g.ldy, g.gamma, g.beta, g.L, g.C, g.G, g.eps, g.silu);
+    MUGD_CHECK_CUDA(cudaGetLastError());
+    if (launches) *launches += 1;
+    return MUGD_OK;
+}
+
+// ---- LayerNorm: one warp per row, row held in registers (C <= 1024) --------------------------------
+constexpr int LN_WARPS = 8;
+constexpr int LN_MAXQ = 8;   // float4 per lane
+
+__global__ void __launch_bounds__(LN_WARPS * 32)
+layernorm_kernel(const float* __restrict__ x, int64_t ldx, float* __restrict__ y, int64_t ldy,
+                 const float* __restrict__ gamma, const float* __restrict__ beta, int rows, int C, float eps) {
+    const int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const int nq = C >> 2;
+    const float* xr = x + (int64_t)row * ldx;
+    float4 v[LN_MAXQ];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXQ; ++i) {
+        const int qi = lane + i * 32;
+        if (qi < nq) {
+            v[i] = ld_f4(xr + qi * 4);
+            s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        } else {
+            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    const float mean = warp_sum(s) / (float)C;
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXQ; ++i) {
+        const int qi = lane + i * 32;
+        if (qi < nq) {
+            const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+            ss += (a * a + b * b) + (c * c + d * d);
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(ss) / (float)C + eps);
+    float* yr = y + (int64_t)row * ldy;
+#pragma unroll
+    for (int i = 0; i < LN_MAXQ; ++i) {
+        const int qi = lane + i * 32;
+        if (qi < nq) {
+            const float4 ga = ld_f4(gamma + qi * 4), be = ld_f4(beta + qi * 4);
+            float4 o;
+            o.x = (v[i].x - mean) * rstd * ga.x + be.x;
+            o.y = (v[i].y - mean) * rstd * ga.y + be.y;
+            o.z = (v[i].z - mean) * rstd * ga.z + be.z;
+            o.w = (v[i].w - mean) * rstd * ga.w + be.w;
+            st_f4(yr + qi * 4, o);
+        }
+    }
+}
+
+int launch_layernorm(const DeviceInfo&, const mugd_layernorm& g, cudaStream_t st, int* launches) {
+    MUGD_REQUIRE(g.rows > 0 && g.C > 0, "layernorm: empty shape");
+    MUGD_REQUIRE(g.C % 4 == 0 && g.C <= LN_MAXQ * 128, "layernorm: C=%d must be a multiple of 4 and <= %d", g.C, LN_MAXQ * 128);
+    MUGD_REQUIRE(g.ldx % 4 == 0 && g.ldy % 4 == 0 && aligned16(g.x) && aligned16(g.y) && aligned16(g.gamma) && aligned16(g.beta),
+                 "layernorm: operands must be 16-byte aligned with ld %% 4 == 0");
+    const int blocks = (g.rows + LN_WARPS - 1) / LN_WARPS;
+    layernorm_kernel<<<blocks, LN_WARPS * 32, 0, st>>>(g.x, g.ldx, g.y, g.ldy, g.gamma, g.beta, g.rows, g.C, g.eps);
+    MUGD_CHECK_CUDA(cudaGetLastError());
+    if (launches) *launches += 1;
+    return MUGD_OK;
+}
+
+}  // namespace mugd

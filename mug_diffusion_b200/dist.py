@@ -1,0 +1,61 @@
+"""Multi-GPU plumbing (one process per GPU, torch.distributed).
+
+The sampler path shards embarrassingly: every (audio, prompt, noise) sample is independent through the whole
+DDIM loop and the decode (no cross-sample op exists in the U-Net).  So the only collective is
+the one-time broadcast of the packed weight blob from rank 0 over NCCL/NVLink; after that each rank runs
+its contiguous slice of the batch with zero per-step traffic.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+from .config import ModelConfig
+from .packer import WeightBlob, pack_model
+
+
+def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous, balanced slice [lo, hi) of ``total`` samples for ``rank`` (first ranks get the remainder)."""
+    base, rem = divmod(total, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_batch(tensors: Sequence[torch.Tensor], rank: int, world: int) -> List[torch.Tensor]:
+    lo, hi = shard_range(tensors[0].shape[0], rank, world)
+    return [t[lo:hi] for t in tensors]
+
+
+def broadcast_blob(state_dict: Optional[Dict[str, torch.Tensor]], cfg: ModelConfig, device: torch.device, src: int = 0) -> WeightBlob:
+    """Rank ``src`` packs the state_dict; everybody receives the flat fp32 blob (one broadcast) plus the
+    small layout table (broadcast_object_list).  Works with NCCL (device tensors) and gloo (CPU)."""
+    rank = dist.get_rank()
+    blob = pack_model(state_dict, cfg.unet, cfg.decoder) if rank == src else None
+    meta = [(blob.entries, blob.meta, blob.numel) if rank == src else None]
+    dist.broadcast_object_list(meta, src=src)
+    entries, bmeta, numel = meta[0]
+    use_cuda = dist.get_backend() == "nccl"
+    if rank == src:
+        flat = blob.data.to(device) if use_cuda else blob.data
+    else:
+        flat = torch.empty(numel, dtype=torch.float32, device=device if use_cuda else "cpu")
+    dist.broadcast(flat, src=src)
+    if rank != src:
+        blob = WeightBlob()
+        blob.entries, blob.meta, blob._size = entries, bmeta, numel
+    blob.data = flat
+    return blob
+
+
+def gather_batch(local: torch.Tensor, sizes: Sequence[int], dst: int = 0) -> Optional[torch.Tensor]:
+    """Optional final gather of per-rank results (e.g. logits [b_r,16,8L]) onto ``dst``."""
+    world = dist.get_world_size()
+    rank = dist.get_rank()
+    if rank == dst:
+        bufs = [torch.empty((sizes[r],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device) for r in range(world)]
+        dist.gather(local.contiguous(), bufs, dst=dst)
+        return torch.cat(bufs, dim=0)
+    dist.gather(local.contiguous(), None, dst=dst)
+    return None

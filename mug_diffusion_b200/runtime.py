@@ -1,0 +1,332 @@
+"""Runtime: ``MugEngine`` (handle + weights on one GPU) and ``Session`` (compiled state for one shape)."""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import lib as L_
+from .config import ModelConfig
+from .engine import (Arena, CTX_TOKENS_MAX, DecoderCompiler, MAX_STEPS, OpList, UNetCompiler, View)
+from .netspec import s4_blocks
+from .packer import WeightBlob, pack_model
+
+
+def _ptr(t: torch.Tensor) -> int:
+    return t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class Plan:
+    def __init__(self, engine: "MugEngine", ops: OpList):
+        self.engine = engine
+        self.n_ops = len(ops.ops)
+        self._arr = ops.array()
+        self.handle = C.c_void_p()
+        L_.check(engine.lib.mugd_plan_create(engine.handle, self._arr, self.n_ops, C.byref(self.handle)), "plan_create")
+        self.captured = False
+        self.launches = 0
+
+    def run(self):
+        L_.check(self.engine.lib.mugd_plan_run(self.handle, _stream()), "plan_run")
+        self.launches = self.engine.lib.mugd_plan_launch_count(self.handle)
+
+    def capture(self):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            L_.check(self.engine.lib.mugd_plan_capture(self.handle, side.cuda_stream), "plan_capture")
+        torch.cuda.current_stream().wait_stream(side)
+        self.launches = self.engine.lib.mugd_plan_launch_count(self.handle)
+        self.captured = True
+
+    def replay(self, times: int = 1):
+        L_.check(self.engine.lib.mugd_plan_replay(self.handle, times, _stream()), "plan_replay")
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.engine.lib.mugd_plan_destroy(self.handle)
+        except Exception:
+            pass
+
+
+class MugEngine:
+    """One GPU: libmugd handle + packed weights.  Thread-safe through a single lock (the reference is not
+    re-entrant either: webui.py:355-356 mutates model.z_length per request)."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], cfg: Optional[ModelConfig] = None,
+                 device: Optional[torch.device] = None, gemm_impl: str = "auto", blob: Optional[WeightBlob] = None):
+        if not torch.cuda.is_available():
+            raise L_.MugdError("mug_diffusion_b200 needs an sm_100 (B200) GPU; there is no CPU fallback")
+        self.cfg = cfg or ModelConfig()
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        torch.cuda.set_device(self.device)
+        self.lib = L_.load()
+        self.handle = C.c_void_p()
+        L_.check(self.lib.mugd_create(self.device.index or 0, C.byref(self.handle)), "mugd_create")
+        self.blob = blob if blob is not None else pack_model(state_dict, self.cfg.unet, self.cfg.decoder)
+        self.weights = self.blob.data.to(self.device)          # the ~420 MB HBM-resident blob
+        self.wbase = self.weights.data_ptr()
+        self.lock = threading.RLock()
+        self.sessions: Dict[tuple, "Session"] = {}
+        self.dec_sessions: Dict[tuple, "DecoderSession"] = {}
+        self.set_gemm_impl(gemm_impl)
+
+    def set_gemm_impl(self, impl: str):
+        code = {"auto": L_.GEMM_SIMT, "simt": L_.GEMM_SIMT, "tc": L_.GEMM_TC}[impl]
+        L_.check(self.lib.mugd_set_gemm_impl(self.handle, code), "set_gemm_impl")
+        self.gemm_impl = impl
+        self.sessions.clear()
+        self.dec_sessions.clear()
+
+    def run_ops(self, ops: OpList):
+        st = _stream()
+        for op in ops.ops:
+            L_.check(self.lib.mugd_op_run(self.handle, C.byref(op), st), f"op kind {op.kind}")
+
+    def session(self, Beff: int, Lz: int, per_sample_t: bool = False) -> "Session":
+        key = (Beff, Lz, per_sample_t)
+        s = self.sessions.get(key)
+        if s is None:
+            s = Session(self, Beff, Lz, per_sample_t)
+            self.sessions[key] = s
+        return s
+
+    def decoder_session(self, B: int, Lz: int) -> "DecoderSession":
+        key = (B, Lz)
+        s = self.dec_sessions.get(key)
+        if s is None:
+            s = DecoderSession(self, B, Lz)
+            self.dec_sessions[key] = s
+        return s
+
+    def __del__(self):
+        try:
+            self.sessions.clear()
+            self.dec_sessions.clear()
+            if self.handle:
+                self.lib.mugd_destroy(self.handle)
+        except Exception:
+            pass
+
+
+class Session:
+    """Compiled U-Net evaluation for Beff samples of length Lz (Beff = 2B under classifier-free guidance)."""
+
+    def __init__(self, engine: MugEngine, Beff: int, Lz: int, per_sample_t: bool):
+        self.engine, self.Beff, self.Lz, self.per_sample_t = engine, Beff, Lz, per_sample_t
+        cfg = engine.cfg.unet
+        dev = engine.device
+        comp = UNetCompiler(cfg, engine.blob, engine.wbase)
+        self.comp = comp
+        emb_total = engine.blob.meta["emb_total"]
+        n_attn = sum(1 for b in _all_blocks(comp) if b.kind == "attn")
+        attn_blocks = [b for b in _all_blocks(comp) if b.kind == "attn"]
+        s4b = [b for b in _all_blocks(comp) if b.kind == "s4"]
+
+        # ---- side buffers (owned torch tensors) ----------------------------------------------
+        emb_rows = Beff if per_sample_t else MAX_STEPS
+        self.emb_table = torch.zeros(emb_rows, emb_total, device=dev)
+        self.temb = torch.zeros(emb_rows, cfg.model_channels, device=dev)
+        self.emb_h1 = torch.zeros(emb_rows, cfg.time_embed_dim, device=dev)
+        self.emb_h2 = torch.zeros(emb_rows, cfg.time_embed_dim, device=dev)
+        self.step = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.coef = torch.zeros(MAX_STEPS, 4, device=dev)
+        self.ctx = torch.zeros(Beff * CTX_TOKENS_MAX, cfg.context_dim, device=dev)
+        self.ctx_kv = [torch.zeros(Beff * CTX_TOKENS_MAX, 2 * b.cin, device=dev) for b in attn_blocks]
+        self.ctx_tokens = 21
+        self.s4_kt = {b.prefix: torch.zeros(Lz // b.ds, b.cin, device=dev) for b in s4b}
+        self._gen_s4_kernels(s4b)
+        self._build(comp)
+
+    # S4 convolution kernels for this length: SSKernelNPLR.forward once per (model, L)  (s4.py:706-832)
+    def _gen_s4_kernels(self, s4b):
+        eng = self.engine
+        N = eng.cfg.unet.s4_state // 2
+        ws = None
+        for b in s4b:
+            k = b.prefix + "s4_model.kernel.kernel."
+            L_int = int(eng.blob.meta[k + "L"])
+            L_req = self.Lz // b.ds
+            if L_req > L_int:
+                raise L_.MugdError(
+                    f"S4 layer {b.prefix}: requested length {L_req} exceeds the checkpoint's internal kernel length "
+                    f"{L_int}; lengthen C~ with mug_diffusion_b200.s4_setup.double_length() before packing (s4.py:557-584)")
+            need = 16 * b.cin * (L_int // 2 + 1)
+            if ws is None or ws.numel() * 8 < need:
+                ws = torch.empty(need // 8 + 2, dtype=torch.float64, device=eng.device)
+
+            def w(n):
+                return eng.wbase + 4 * eng.blob.offset(k + n)
+
+            L_.check(eng.lib.mugd_s4_kernel_gen(eng.handle, w("log_dt"), w("B"), w("C"), w("P"), w("inv_w_real"), w("w_imag"),
+                                                b.cin, N, L_int, L_req, _ptr(self.s4_kt[b.prefix]), _ptr(ws), ws.numel() * 8,
+                                                _stream()), "s4_kernel_gen")
+        torch.cuda.current_stream().synchronize()
+
+    def _ext(self, base_ctx_tokens: int) -> dict:
+        return dict(
+            emb_table=_ptr(self.emb_table), step=_ptr(self.step), ctx_tokens=base_ctx_tokens,
+            ctx_kv=[View(_ptr(t), t.shape[1], self.Beff * base_ctx_tokens, t.shape[1]) for t in self.ctx_kv],
+            s4_kt={p: View(_ptr(t), t.shape[1], t.shape[0], t.shape[1]) for p, t in self.s4_kt.items()},
+        )
+
+    def _build(self, comp: UNetCompiler):
+        dry = Arena(0)
+        comp.compile(dry, self.Beff, self.Lz, self._ext(self.ctx_tokens), self.per_sample_t)
+        nbytes = dry.high + 1024
+        self.arena_t = torch.zeros(nbytes // 4 + 64, device=self.engine.device)
+        base = (self.arena_t.data_ptr() + 255) // 256 * 256
+        arena = Arena(base, nbytes)
+        res = comp.compile(arena, self.Beff, self.Lz, self._ext(self.ctx_tokens), self.per_sample_t)
+        self.xin: View = res["xin"]
+        self.eps: View = res["eps"]
+        self.audio_slots = res["audio_slots"]
+        self.plan = Plan(self.engine, res["ops"])
+        self.arena_bytes = nbytes
+        self._captured_for = None
+
+    # ---- per-request preparation ---------------------------------------------------------------
+    def set_timestep_table(self, timesteps: Sequence[int]):
+        """Time-embedding MLP + all ResBlock emb projections for the given timesteps, one row each
+        (unet.py:335-339, 166-172; model/util.py:156-176).  The sinusoid is evaluated on the host exactly
+        as the reference does; the three GEMMs run on the GPU."""
+        cfg = self.engine.cfg.unet
+        eng = self.engine
+        t = torch.as_tensor(np.asarray(timesteps), dtype=torch.long)
+        R = t.shape[0]
+        assert R <= self.temb.shape[0]
+        half = cfg.model_channels // 2
+        import math
+        freqs = torch.exp(-math.log(10000.0) * torch.arange(0, half, dtype=torch.float32) / half)
+        args = t[:, None].float() * freqs[None]
+        emb = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
+        self.temb[:R].copy_(emb.to(eng.device))
+        ops = OpList()
+        up = self.comp.prefix
+        tv = View(_ptr(self.temb), cfg.model_channels, R, cfg.model_channels)
+        h1 = View(_ptr(self.emb_h1), cfg.time_embed_dim, R, cfg.time_embed_dim)
+        h2 = View(_ptr(self.emb_h2), cfg.time_embed_dim, R, cfg.time_embed_dim)
+        et = View(_ptr(self.emb_table), self.emb_table.shape[1], R, self.emb_table.shape[1])
+        w = self.comp.w
+        ops.gemm(tv, w(up + "time_embed.0.weight"), cfg.time_embed_dim, cfg.model_channels, h1, bias=w(up + "time_embed.0.bias"),
+                 act=L_.ACT_SILU)
+        # emb is only ever consumed through emb_layers = SiLU -> Linear, so SiLU(emb) is stored
+        ops.gemm(h1, w(up + "time_embed.2.weight"), cfg.time_embed_dim, cfg.time_embed_dim, h2, bias=w(up + "time_embed.2.bias"),
+                 act=L_.ACT_SILU)
+        ops.gemm(h2, w(up + "emb_all.weight"), self.emb_table.shape[1], cfg.time_embed_dim, et, bias=w(up + "emb_all.bias"))
+        eng.run_ops(ops)
+
+    def set_context(self, context: torch.Tensor):
+        """context [Beff, ctx_dim, T] (reference layout) -> per-layer cross-attention K|V projections
+        (attention.py:97-98), constant over the DDIM steps."""
+        eng = self.engine
+        cfg = eng.cfg.unet
+        Bc, Cd, T = context.shape
+        assert Bc == self.Beff and Cd == cfg.context_dim and T <= CTX_TOKENS_MAX
+        if T != self.ctx_tokens:
+            self.ctx_tokens = T
+            self._build(self.comp)            # Lk is baked into the attention ops
+        context = context.to(eng.device, torch.float32).contiguous()
+        ops = OpList()
+        ops.transpose(_ptr(context), _ptr(self.ctx), 0, cfg.context_dim, Bc, Cd, T, True)
+        cv = View(_ptr(self.ctx), cfg.context_dim, Bc * T, cfg.context_dim)
+        blocks = [b for b in _all_blocks(self.comp) if b.kind == "attn"]
+        for b, kv in zip(blocks, self.ctx_kv):
+            o = View(_ptr(kv), kv.shape[1], Bc * T, kv.shape[1])
+            ops.gemm(cv, self.comp.w(b.prefix + "transformer_blocks.0.attn2.kv.weight"), 2 * b.cin, cfg.context_dim, o, Lout=T)
+        eng.run_ops(ops)
+        self._keep = context
+
+    def set_audio(self, audios: Sequence[torch.Tensor]):
+        """The last ``levels`` entries of the wave-encoder output list (unet.py:527-543), NCL layout, written
+        (transposed) into every concat slot that holds them."""
+        cfg = self.engine.cfg.unet
+        w4 = list(audios)[-cfg.levels:]
+        keep = []
+        ops = OpList()
+        for lvl, view in self.audio_slots:
+            a = w4[lvl].to(self.engine.device, torch.float32).contiguous()
+            keep.append(a)
+            assert a.shape == (self.Beff, cfg.audio_channels[lvl], self.Lz >> lvl), (a.shape, lvl)
+            ops.transpose(_ptr(a), view.ptr, 0, view.ld, self.Beff, a.shape[1], a.shape[2], True)
+        self.engine.run_ops(ops)
+        self._keep_audio = keep
+
+    def load_x(self, x: torch.Tensor, dup: bool):
+        """x [B,C,L] -> xin rows (both halves when dup)."""
+        x = x.to(self.engine.device, torch.float32).contiguous()
+        B, Cc, Lr = x.shape
+        ops = OpList()
+        ops.transpose(_ptr(x), self.xin.ptr, 0, self.xin.ld, B, Cc, Lr, True)
+        if dup:
+            ops.transpose(_ptr(x), self.xin.r(B * Lr, 2 * B * Lr).ptr, 0, self.xin.ld, B, Cc, Lr, True)
+        self.engine.run_ops(ops)
+        self._keep_x = x
+
+    def read_rows(self, view: View, B: int, Cc: int, Lr: int) -> torch.Tensor:
+        out = torch.empty(B, Cc, Lr, device=self.engine.device)
+        ops = OpList()
+        ops.transpose(view.ptr, _ptr(out), view.ld, 0, B, Cc, Lr, False)
+        self.engine.run_ops(ops)
+        return out
+
+    def eval(self, graph: bool = True):
+        if graph:
+            if not self.plan.captured:
+                self.plan.run()               # warm-up (lazy module load, cudaFuncSetAttribute) outside capture
+                self.plan.capture()
+            self.plan.replay(1)
+        else:
+            self.plan.run()
+
+    def set_step(self, value: int):
+        L_.check(self.engine.lib.mugd_fill_i32(_ptr(self.step), value, _stream()), "fill_i32")
+
+
+class DecoderSession:
+    def __init__(self, engine: MugEngine, B: int, Lz: int):
+        self.engine, self.B, self.Lz = engine, B, Lz
+        comp = DecoderCompiler(engine.cfg.decoder, engine.blob, engine.wbase)
+        dry = Arena(0)
+        comp.compile(dry, B, Lz)
+        nbytes = dry.high + 1024
+        self.arena_t = torch.zeros(nbytes // 4 + 64, device=engine.device)
+        base = (self.arena_t.data_ptr() + 255) // 256 * 256
+        res = comp.compile(Arena(base, nbytes), B, Lz)
+        self.zin, self.logits, self.Lout = res["zin"], res["logits"], res["Lout"]
+        self.plan = Plan(engine, res["ops"])
+        self.arena_bytes = nbytes
+
+    def decode(self, z: torch.Tensor) -> torch.Tensor:
+        eng = self.engine
+        cfg = eng.cfg.decoder
+        z = z.to(eng.device, torch.float32)
+        if cfg.scale != 1.0:
+            z = z / cfg.scale                 # autoencoder.py:76
+        z = z.contiguous()
+        ops = OpList()
+        ops.transpose(_ptr(z), self.zin.ptr, 0, self.zin.ld, self.B, cfg.z_channels, self.Lz, True)
+        eng.run_ops(ops)
+        self.plan.run()
+        out = torch.empty(self.B, cfg.x_channels, self.Lout, device=eng.device)
+        ops = OpList()
+        ops.transpose(self.logits.ptr, _ptr(out), self.logits.ld, 0, self.B, cfg.x_channels, self.Lout, False)
+        eng.run_ops(ops)
+        return out
+
+
+def _all_blocks(comp: UNetCompiler):
+    lay = comp.lay
+    for entry in lay.input + [lay.middle] + lay.output:
+        if isinstance(entry, tuple):
+            continue
+        for b in entry:
+            yield b
