@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MUGD_ABI_VERSION 3
+#define MUGD_ABI_VERSION 4
 
 typedef struct mugd_handle mugd_handle;   /* one device + scratch state            */
 typedef struct mugd_plan mugd_plan;       /* validated launch plan (+ CUDA graph)  */
@@ -172,6 +172,8 @@ int  mugd_s4_kernel_gen(mugd_handle* h,
                         const float* Pri,         /* [H][N][2]  */
                         const float* inv_w_real,  /* [H][N]     */
                         const float* w_imag,      /* [H][N]     */
+                        const float* omega_ri,    /* [L_internal/2+1][2] FFT nodes as the reference computes them
+                                                     (complex64 omega**arange, s4.py:595-598) or NULL = exact */
                         int32_t H, int32_t N, int32_t L_internal, int32_t L_out,
                         float* Kt,                /* [L_out][H] */
                         void* workspace, int64_t workspace_bytes, /* >= 16*H*(L_internal/2+1) bytes */

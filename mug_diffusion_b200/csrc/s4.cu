@@ -105,8 +105,9 @@ int launch_s4conv(const DeviceInfo& dev, const mugd_s4conv& s, cudaStream_t st, 
 // (2) kernel generation (fp64).  With w' = w*dt, omega_f = exp(-2 pi i f / L):
 //   reference:  z = 2(1-omega)/(1+omega);  r_xy = dt * sum_n v_xy[n] / (z - w'_n)
 //               k_f = (r00 - r01 r10 / (1 + r11)) * 2 / (1 + omega);   K = irfft(k_f, L)[:L_out]
-//   Multiplying numerator and denominator by (1+omega) removes the 0/0 at the Nyquist node (where the
-//   reference relies on rounding noise of its complex64 omega^f):
+//   Multiplying numerator and denominator by (1+omega) -- an identity for ANY omega, exact or not --
+//   removes the 0/0 at the Nyquist node (where the reference relies on rounding noise of its complex64
+//   omega^f):
 //               s_xy = dt * sum_n v_xy[n] / (2(1-omega) - w'_n (1+omega)),     r_xy = (1+omega) s_xy
 //               k_f  = 2 * ( s00 - (1+omega) s01 s10 / (1 + (1+omega) s11) )
 //   v00 = B*C, v01 = B*conj(P), v10 = P*C, v11 = P*conj(P)              (s4.py:771-778)
@@ -123,15 +124,22 @@ __device__ __forceinline__ cd cdiv(cd a, cd b) {
 __global__ void s4_kf_kernel(const float* __restrict__ log_dt, const float* __restrict__ Bri,
                              const float* __restrict__ Cri, const float* __restrict__ Pri,
                              const float* __restrict__ inv_w_real, const float* __restrict__ w_imag,
-                             int H, int N, int Lint, double2* __restrict__ kf) {
+                             const float* __restrict__ omega_ri, int H, int N, int Lint, double2* __restrict__ kf) {
     const int nf = Lint / 2 + 1;
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     const int h = blockIdx.y;
     if (f >= nf) return;
     const double dt = exp((double)log_dt[h]);
-    double sn, cs;
-    sincospi(-2.0 * (double)f / (double)Lint, &sn, &cs);
-    const cd om = {cs, sn};
+    // FFT nodes: the caller's table (the reference evaluates omega^f as a complex64 power, s4.py:595-598,
+    // which is off by up to ~5e-6 at f = L/2; using the same nodes reproduces its kernel to ~2e-6) or exact.
+    cd om;
+    if (omega_ri) {
+        om = {(double)omega_ri[2 * f], (double)omega_ri[2 * f + 1]};
+    } else {
+        double sn, cs;
+        sincospi(-2.0 * (double)f / (double)Lint, &sn, &cs);
+        om = {cs, sn};
+    }
     const cd one_m = {2.0 * (1.0 - om.re), -2.0 * om.im};     // 2(1-omega)
     const cd one_p = {1.0 + om.re, om.im};                    // 1+omega
     cd s00 = {0, 0}, s01 = {0, 0}, s10 = {0, 0}, s11 = {0, 0};
@@ -190,9 +198,9 @@ __global__ void s4_irfft_kernel(const double2* __restrict__ kf, int H, int Lint,
 }  // namespace mugd
 
 extern "C" int mugd_s4_kernel_gen(mugd_handle*, const float* log_dt, const float* Bri, const float* Cri,
-                                  const float* Pri, const float* inv_w_real, const float* w_imag, int32_t H,
-                                  int32_t N, int32_t L_internal, int32_t L_out, float* Kt, void* workspace,
-                                  int64_t workspace_bytes, void* stream) {
+                                  const float* Pri, const float* inv_w_real, const float* w_imag,
+                                  const float* omega_ri, int32_t H, int32_t N, int32_t L_internal, int32_t L_out,
+                                  float* Kt, void* workspace, int64_t workspace_bytes, void* stream) {
     using namespace mugd;
     MUGD_REQUIRE(H > 0 && N > 0 && L_internal > 0 && L_out > 0 && L_out <= L_internal,
                  "s4_kernel_gen: bad shape H=%d N=%d L_internal=%d L_out=%d (L_out must be <= L_internal; lengthen C~ with "
@@ -203,7 +211,7 @@ extern "C" int mugd_s4_kernel_gen(mugd_handle*, const float* log_dt, const float
     cudaStream_t st = (cudaStream_t)stream;
     double2* kf = (double2*)workspace;
     dim3 g1((nf + 127) / 128, H);
-    s4_kf_kernel<<<g1, 128, 0, st>>>(log_dt, Bri, Cri, Pri, inv_w_real, w_imag, H, N, L_internal, kf);
+    s4_kf_kernel<<<g1, 128, 0, st>>>(log_dt, Bri, Cri, Pri, inv_w_real, w_imag, omega_ri, H, N, L_internal, kf);
     MUGD_CHECK_CUDA(cudaGetLastError());
     const size_t smem = sizeof(double2) * (size_t)(nf + L_internal);
     MUGD_REQUIRE(smem <= 200 * 1024, "s4_kernel_gen: L_internal=%d too long for the one-shot DFT", L_internal);

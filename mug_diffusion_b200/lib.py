@@ -18,7 +18,7 @@ CONV_NONE, CONV_SAME, CONV_DOWN, CONV_UP = range(4)
 ACT_NONE, ACT_SILU, ACT_GELU = range(3)
 GATE_NONE, GATE_GEGLU, GATE_GLU = range(3)
 GEMM_AUTO, GEMM_SIMT, GEMM_TC = range(3)
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 _f = C.c_void_p  # device pointers travel as integers
 
@@ -127,7 +127,7 @@ def load() -> C.CDLL:
     lib.mugd_plan_launch_count.argtypes = [C.c_void_p]
     lib.mugd_plan_destroy.argtypes = [C.c_void_p]
     lib.mugd_plan_destroy.restype = None
-    lib.mugd_s4_kernel_gen.argtypes = [C.c_void_p] + [C.c_void_p] * 6 + [C.c_int32] * 4 + [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    lib.mugd_s4_kernel_gen.argtypes = [C.c_void_p] + [C.c_void_p] * 7 + [C.c_int32] * 4 + [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     lib.mugd_fill_i32.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
     lib.mugd_abi_sizes.argtypes = [C.POINTER(C.c_int32), C.c_int32]
     if lib.mugd_abi_version() != ABI_VERSION:

@@ -166,8 +166,9 @@ class Session:
             def w(n):
                 return eng.wbase + 4 * eng.blob.offset(k + n)
 
+            om = s4_fft_nodes(L_int).to(eng.device)
             L_.check(eng.lib.mugd_s4_kernel_gen(eng.handle, w("log_dt"), w("B"), w("C"), w("P"), w("inv_w_real"), w("w_imag"),
-                                                b.cin, N, L_int, L_req, _ptr(self.s4_kt[b.prefix]), _ptr(ws), ws.numel() * 8,
+                                                _ptr(om), b.cin, N, L_int, L_req, _ptr(self.s4_kt[b.prefix]), _ptr(ws), ws.numel() * 8,
                                                 _stream()), "s4_kernel_gen")
         torch.cuda.current_stream().synchronize()
 
@@ -321,6 +322,22 @@ class DecoderSession:
         ops.transpose(self.logits.ptr, _ptr(out), self.logits.ld, 0, self.B, cfg.x_channels, self.Lout, False)
         eng.run_ops(ops)
         return out
+
+
+_NODE_CACHE: Dict[int, torch.Tensor] = {}
+
+
+def s4_fft_nodes(L_int: int) -> torch.Tensor:
+    """omega_f for f = 0..L/2 evaluated the way the reference does (SSKernelNPLR._omega, s4.py:586-604):
+    a complex64 base raised to integer powers on the host.  This is a parameter-free constant table like the
+    timestep sinusoid; feeding the same nodes to the fp64 kernel generator reproduces the reference's kernel
+    to ~2e-6 instead of ~1e-4 (the complex64 power drifts by up to 5e-6 at f = L/2).  Returns [L/2+1, 2] fp32."""
+    t = _NODE_CACHE.get(L_int)
+    if t is None:
+        base = torch.tensor(np.exp(-2j * np.pi / L_int), dtype=torch.complex64)
+        t = torch.view_as_real(base ** torch.arange(0, L_int // 2 + 1)).contiguous()
+        _NODE_CACHE[L_int] = t
+    return t
 
 
 def _all_blocks(comp: UNetCompiler):

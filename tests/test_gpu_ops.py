@@ -236,7 +236,8 @@ def test_s4conv(R, B, L, H):
     assert rel_err(ncl(out.cpu(), B), ref) < 2e-5
 
 
-@pytest.mark.parametrize("L_int,L_out,H", [(96, 96, 128), (24, 24, 384), (512, 512, 128), (124, 124, 512), (128, 100, 64), (63, 63, 32)])
+@pytest.mark.parametrize("L_int,L_out,H", [(96, 96, 128), (24, 24, 384), (512, 512, 128), (124, 124, 512), (128, 100, 64), (63, 63, 32),
+                                           (992, 992, 128)])
 def test_s4_kernel_gen_vs_oracle(R, L_int, L_out, H):
     import ctypes as C
     N = 32
@@ -249,11 +250,18 @@ def test_s4_kernel_gen_vs_oracle(R, L_int, L_out, H):
     dev = {k: v.cuda() for k, v in sd.items() if k != pre + "L"}
     kt = torch.zeros(L_out, H).cuda()
     ws = torch.zeros(2 * H * (L_int // 2 + 1) + 8, dtype=torch.float64).cuda()
-    L_.check(R.lib.mugd_s4_kernel_gen(R.handle, ptr(dev[pre + "log_dt"]), ptr(dev[pre + "B"]), ptr(dev[pre + "C"]), ptr(dev[pre + "P"]),
-                                      ptr(dev[pre + "inv_w_real"]), ptr(dev[pre + "w_imag"]), H, N, L_int, L_out, ptr(kt), ptr(ws),
-                                      ws.numel() * 8, torch.cuda.current_stream().cuda_stream), "s4_kernel_gen")
+    from mug_diffusion_b200.runtime import s4_fft_nodes
+    st = torch.cuda.current_stream().cuda_stream
+    args = [ptr(dev[pre + n]) for n in ("log_dt", "B", "C", "P", "inv_w_real", "w_imag")]
+    om = s4_fft_nodes(L_int).cuda()
+    L_.check(R.lib.mugd_s4_kernel_gen(R.handle, *args, ptr(om), H, N, L_int, L_out, ptr(kt), ptr(ws), ws.numel() * 8, st), "s4_kernel_gen")
     torch.cuda.synchronize()
-    assert rel_err(kt.t(), ref) < 2e-5
+    # with the reference's own FFT nodes the fp64 generator reproduces the reference's fp32 kernel to its rounding noise
+    assert rel_err(kt.t(), ref) < 1e-5
+    # with exact nodes (omega = NULL) it differs by the drift of the reference's complex64 omega**f: ~4e-5 @96 .. 4e-4 @992
+    L_.check(R.lib.mugd_s4_kernel_gen(R.handle, *args, None, H, N, L_int, L_out, ptr(kt), ptr(ws), ws.numel() * 8, st), "s4_kernel_gen")
+    torch.cuda.synchronize()
+    assert rel_err(kt.t(), ref) < 1e-3
 
 
 def test_s4_kernel_gen_vs_reference_golden(R, golden_dir):
@@ -267,11 +275,13 @@ def test_s4_kernel_gen_vs_reference_golden(R, golden_dir):
         dev = {n: sd[k + n].cuda() for n in ("log_dt", "B", "C", "P", "inv_w_real", "w_imag")}
         kt = torch.zeros(Lr, H).cuda()
         ws = torch.zeros(2 * H * (Lr // 2 + 1) + 8, dtype=torch.float64).cuda()
+        from mug_diffusion_b200.runtime import s4_fft_nodes
+        om = s4_fft_nodes(Lr).cuda()
         L_.check(R.lib.mugd_s4_kernel_gen(R.handle, ptr(dev["log_dt"]), ptr(dev["B"]), ptr(dev["C"]), ptr(dev["P"]), ptr(dev["inv_w_real"]),
-                                          ptr(dev["w_imag"]), H, 32, Lr, Lr, ptr(kt), ptr(ws), ws.numel() * 8,
+                                          ptr(dev["w_imag"]), ptr(om), H, 32, Lr, Lr, ptr(kt), ptr(ws), ws.numel() * 8,
                                           torch.cuda.current_stream().cuda_stream), "s4_kernel_gen")
         torch.cuda.synchronize()
-        assert rel_err(kt.t(), gold[name + ".K"]) < 2e-5
+        assert rel_err(kt.t(), gold[name + ".K"]) < 1e-5
 
 
 # ---------------------------------------------------------------------------------------------------
