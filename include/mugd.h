@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MUGD_ABI_VERSION 4
+#define MUGD_ABI_VERSION 5
 
 typedef struct mugd_handle mugd_handle;   /* one device + scratch state            */
 typedef struct mugd_plan mugd_plan;       /* validated launch plan (+ CUDA graph)  */
@@ -70,7 +70,8 @@ enum mugd_gemm_impl { MUGD_GEMM_AUTO = 0, MUGD_GEMM_SIMT = 1 /* exact fp32 FMA *
 typedef struct mugd_gemm {
     const float* A;  int64_t lda;          /* [B*Lin, K] activations                                       */
     const float* W;                        /* [N][taps*K], K-major per tap (conv weight [Cout][k][Cin])    */
-    const float* W_lo;                     /* optional fp32 residual of the TF32 split (tensor-core path)  */
+    const float* W_hi;                     /* optional: W rounded to TF32 (rna)            } tensor-core path, */
+    const float* W_lo;                     /* optional: rna_tf32(W - W_hi)                 } same layout as W  */
     const float* bias;                     /* [N] or NULL                                                  */
     const float* rowvec;                   /* per-sample row vector added before act: time embedding       */
     int64_t rowvec_b_stride;               /*   rowvec[step*step_stride + b*b_stride + n]                  */
@@ -81,6 +82,11 @@ typedef struct mugd_gemm {
     int32_t M, N, K;                       /* M = B*Lout rows, N weight rows, K channels per tap           */
     int32_t taps, conv_mode, Lin, Lout;
     int32_t act, gate, impl;
+    int32_t split_k;                       /* tensor-core path: 0 = auto, >0 forces the K split            */
+    int32_t n_counters;                    /* entries available in `counters`                              */
+    int32_t reserved0;
+    void* workspace; int64_t workspace_bytes; /* split-K partial tiles (see mugd_gemm_tc_query)            */
+    int32_t* counters;                     /* zero-initialised tile tickets, left zero by every launch     */
 } mugd_gemm;
 
 typedef struct mugd_groupnorm {
@@ -178,6 +184,11 @@ int  mugd_s4_kernel_gen(mugd_handle* h,
                         float* Kt,                /* [L_out][H] */
                         void* workspace, int64_t workspace_bytes, /* >= 16*H*(L_internal/2+1) bytes */
                         void* stream);
+
+/* ---- tensor-core GEMM planning: is this GEMM taken by the tcgen05 kernel, with which K split, and how much
+ * split-K workspace / how many tile counters does it need (the host allocates them once per plan) ------ */
+int  mugd_gemm_tc_query(mugd_handle* h, const mugd_gemm* g, int32_t sm_count, int32_t* supported, int32_t* splits,
+                        int64_t* workspace_bytes, int32_t* n_tiles);
 
 /* ---- utility ---------------------------------------------------------------------------------- */
 int  mugd_fill_i32(int32_t* dst, int32_t value, void* stream);

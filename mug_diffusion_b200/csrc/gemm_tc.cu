@@ -1,14 +1,521 @@
-// tcgen05 (5th-gen tensor core) GEMM path -- placeholder until the 3xTF32 kernel lands; reports
-// "unsupported" so MUGD_GEMM_AUTO falls through to the exact-fp32 FFMA kernel in gemm_simt.cu.
+// tcgen05 (5th-generation tensor core) implicit GEMM for the conv/linear contractions of the U-Net,
+// fp32 in / fp32 out with the 3xTF32 split so results stay at fp32 accuracy (DESIGN.md §4 "Precision"):
+//
+//     a = a_hi + a_lo (both exactly representable in TF32, round-to-nearest),   w = w_hi + w_lo
+//     acc += a_lo*w_hi + a_hi*w_lo + a_hi*w_hi          (fp32 accumulation in TMEM, dropped term ~2^-22)
+//
+// Structure (one 128 x BN output tile per CTA, optional split-K over blockIdx.z):
+//   warp 0      TMA producer : per k-step (32 fp32 = one 128-byte swizzle row) loads the raw A tile through a
+//                              3-D tensor map (k, l, b) -- the conv k=3 halo is the TMA out-of-bounds zero fill
+//                              on the l axis, so no im2col / padding copy exists -- plus the pre-split W_hi / W_lo
+//                              tiles; completion on an mbarrier (complete_tx).
+//   warps 4-7   converter    : split the raw A tile into a_hi (in place) and a_lo (cvt.rna.tf32), then
+//                              fence.proxy.async and signal the MMA warp.  Elementwise on smem addresses, so it is
+//                              independent of the 128B swizzle pattern.
+//   warp 1      MMA issuer   : one elected thread issues 12 tcgen05.mma.kind::tf32 (M128 x BN x K8) per k-step
+//                              from shared-memory descriptors (K-major, SWIZZLE_128B); tcgen05.commit releases the
+//                              stage to the producer and, after the last k-step, hands the accumulator to the epilogue.
+//   warp 2      TMEM allocator (BN fp32 columns x 128 lanes).
+//   warps 4-7   epilogue     : tcgen05.ld 32x32b (thread = one output row, 32 columns at a time) -> bias /
+//                              time-embedding row / SiLU / GELU / GEGLU / GLU / residual -> 128-byte row stores.
+//                              With split-K the partial tile goes to a workspace and the last CTA of the tile
+//                              (atomic ticket) reduces the splits in fixed order (deterministic) and runs the epilogue.
+//
+// Reference call sites are the same as gemm_simt.cu (which remains the exact-fp32 referee and the fallback for
+// shapes this kernel does not take: K % 32 != 0, N < 64, strided / upsampling convs).
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace mugd {
 
-bool gemm_tc_supported(const mugd_gemm&) { return false; }
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 32;                 // fp32 elements per k-step = 128 bytes = one swizzle row
+constexpr int TC_THREADS = 256;
+constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
 
-int launch_gemm_tc(const DeviceInfo&, const mugd_gemm&, cudaStream_t, int*) {
-    set_error("gemm_tc: not built");
-    return MUGD_ERR_INVALID;
+struct TcParams {
+    mugd_gemm g;
+    float* ws;                // split-K partial tiles [tile][split][128][BN]
+    int32_t* counters;        // one ticket per output tile, zero at rest
+    int32_t splits;
+    int32_t total_it;         // taps * K / 32
+    int32_t kblocks;          // K / 32
+    int32_t Lrows, Bs;        // row structure of the A tensor map (Lrows = rows per sample, Bs samples)
+    int32_t box_l, box_b;     // TMA box: box_l rows of box_b consecutive samples (box_l*box_b <= 128)
+    int32_t tiles_per_sample; // when Lrows >= 128
+};
+
+// ---- raw PTX helpers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// bounded wait: a protocol bug traps (CUDA error) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    const long long t0 = clock64();
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) break;
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// start>>4 [0,14) | LBO>>4 [16,30) (unused for swizzled K-major, 1) | SBO>>4 [32,46) = 1024 B between 8-row
+// groups | version=1 [46,48) | layout_type=SWIZZLE_128B(2) [61,64)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+template <int BN>
+struct TcSmem {
+    static constexpr uint32_t B_BYTES = BN * TC_BK * 4;
+    static constexpr uint32_t STAGE_BYTES = 2 * TC_A_BYTES + 2 * B_BYTES;
+    static constexpr int STAGES = (BN == 256) ? 2 : (BN == 128 ? 3 : 4);
+    static constexpr uint32_t TILE_BYTES = STAGES * STAGE_BYTES;
+    static constexpr uint32_t TOTAL = TILE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__device__ __forceinline__ void tc_epilogue_store(const mugd_gemm& g, const float* v, int m, int n, const float* rowvec) {
+    // v: 32 consecutive accumulator columns n..n+31 of output row m (N % 4 == 0 guaranteed)
+    const int bidx = m / g.Lout;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int nn = n + q * 4;
+        if (nn >= g.N) break;
+        float x[4] = {v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]};
+        if (g.bias) {
+            const float4 bb = ld_f4(g.bias + nn);
+            x[0] += bb.x; x[1] += bb.y; x[2] += bb.z; x[3] += bb.w;
+        }
+        if (rowvec) {
+            const float4 rv = ld_f4(rowvec + (int64_t)bidx * g.rowvec_b_stride + nn);
+            x[0] += rv.x; x[1] += rv.y; x[2] += rv.z; x[3] += rv.w;
+        }
+        if (g.act == MUGD_ACT_SILU) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) x[j] = silu_f(x[j]);
+        } else if (g.act == MUGD_ACT_GELU) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) x[j] = gelu_f(x[j]);
+        }
+        if (g.gate == MUGD_GATE_NONE) {
+            if (g.residual) {
+                const float4 rr = ld_f4(g.residual + (int64_t)m * g.ldr + nn);
+                x[0] += rr.x; x[1] += rr.y; x[2] += rr.z; x[3] += rr.w;
+            }
+            st_f4(g.C + (int64_t)m * g.ldc + nn, make_float4(x[0], x[1], x[2], x[3]));
+        } else {
+            float o0, o1;
+            if (g.gate == MUGD_GATE_GEGLU) { o0 = x[0] * gelu_f(x[1]); o1 = x[2] * gelu_f(x[3]); }
+            else { o0 = x[0] * sigmoid_f(x[1]); o1 = x[2] * sigmoid_f(x[3]); }
+            const int no = nn >> 1;
+            if (g.residual) {
+                const float2 rr = *reinterpret_cast<const float2*>(g.residual + (int64_t)m * g.ldr + no);
+                o0 += rr.x; o1 += rr.y;
+            }
+            *reinterpret_cast<float2*>(g.C + (int64_t)m * g.ldc + no) = make_float2(o0, o1);
+        }
+    }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWhi,
+               const __grid_constant__ CUtensorMap tmWlo, const TcParams p) {
+    using S = TcSmem<BN>;
+    constexpr int STAGES = S::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // SWIZZLE_128B needs 1024-B alignment
+    const uint32_t bars = base + S::TILE_BYTES;                          // barrier block (8-byte aligned)
+    // barrier addresses: full[s], conv[s], empty[s], accum ; tmem ptr slot after them
+    auto bar_full = [&](int s) { return bars + 8u * s; };
+    auto bar_conv = [&](int s) { return bars + 8u * (STAGES + s); };
+    auto bar_empty = [&](int s) { return bars + 8u * (2 * STAGES + s); };
+    const uint32_t bar_accum = bars + 8u * (3 * STAGES);
+    const uint32_t tmem_slot = bars + 8u * (3 * STAGES + 1);
+    auto a_hi = [&](int s) { return base + s * S::STAGE_BYTES; };
+    auto a_lo = [&](int s) { return base + s * S::STAGE_BYTES + TC_A_BYTES; };
+    auto b_hi = [&](int s) { return base + s * S::STAGE_BYTES + 2 * TC_A_BYTES; };
+    auto b_lo = [&](int s) { return base + s * S::STAGE_BYTES + 2 * TC_A_BYTES + S::B_BYTES; };
+
+    const mugd_gemm& g = p.g;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * BN;
+    // ---- tile -> rows -------------------------------------------------------------------------------
+    int b_base, l_base, rows_valid;
+    if (p.Lrows >= TC_BM) {
+        b_base = blockIdx.y / p.tiles_per_sample;
+        l_base = (blockIdx.y % p.tiles_per_sample) * TC_BM;
+        rows_valid = min(TC_BM, p.Lrows - l_base);
+    } else {
+        b_base = blockIdx.y * p.box_b;
+        l_base = 0;
+        rows_valid = min(p.box_b, p.Bs - b_base) * p.Lrows;
+    }
+    const int m_base = b_base * p.Lrows + l_base;
+    const int it_begin = (int)(((long long)p.total_it * blockIdx.z) / p.splits);
+    const int it_end = (int)(((long long)p.total_it * (blockIdx.z + 1)) / p.splits);
+    const int nit = it_end - it_begin;
+
+    // ---- one-time setup ------------------------------------------------------------------------------
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bar_full(s), 1);
+            mbar_init(bar_conv(s), 4);        // one arrival per converter warp
+            mbar_init(bar_empty(s), 1);
+        }
+        mbar_init(bar_accum, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        // ===================================== TMA producer =====================================
+        if (lane == 0) {
+            const uint32_t a_tx = (uint32_t)(p.box_l * p.box_b) * TC_BK * 4;
+            for (int i = 0; i < nit; ++i) {
+                const int s = i % STAGES;
+                const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+                mbar_wait(bar_empty(s), ph ^ 1u);
+                const int it = it_begin + i;
+                const int t = it / p.kblocks;
+                const int kb = it - t * p.kblocks;
+                mbar_expect_tx(bar_full(s), a_tx + 2 * S::B_BYTES);
+                const int lshift = (g.conv_mode == MUGD_CONV_SAME) ? (t - 1) : 0;
+                tma_load_3d(a_hi(s), &tmA, bar_full(s), kb * TC_BK, l_base + lshift, b_base);
+                tma_load_2d(b_hi(s), &tmWhi, bar_full(s), t * g.K + kb * TC_BK, n0);
+                tma_load_2d(b_lo(s), &tmWlo, bar_full(s), t * g.K + kb * TC_BK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================== MMA issuer =======================================
+        if (lane == 0) {
+            // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A=TF32 [7,10)=2, B=TF32 [10,13)=2,
+            // A/B K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            for (int i = 0; i < nit; ++i) {
+                const int s = i % STAGES;
+                const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+                mbar_wait(bar_conv(s), ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint64_t dah = umma_desc(a_hi(s)), dal = umma_desc(a_lo(s));
+                const uint64_t dbh = umma_desc(b_hi(s)), dbl = umma_desc(b_lo(s));
+#pragma unroll
+                for (int kk = 0; kk < TC_BK / 8; ++kk) {
+                    const uint64_t ko = (uint64_t)(kk * 2);         // 8 fp32 = 32 bytes = 2 x 16-byte units
+                    umma_tf32(tmem_base, dal + ko, dbh + ko, idesc, (i > 0 || kk > 0) ? 1u : 0u);
+                    umma_tf32(tmem_base, dah + ko, dbl + ko, idesc, 1u);
+                    umma_tf32(tmem_base, dah + ko, dbh + ko, idesc, 1u);
+                }
+                umma_commit(bar_empty(s));                            // stage reusable once these MMAs retire
+            }
+            umma_commit(bar_accum);
+        }
+    } else if (warp >= 4) {
+        // ===================================== converter ========================================
+        const int ct = threadIdx.x - 128;                             // 0..127
+        for (int i = 0; i < nit; ++i) {
+            const int s = i % STAGES;
+            const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+            mbar_wait(bar_full(s), ph);
+            const uint32_t hi_addr = a_hi(s), lo_addr = a_lo(s);
+#pragma unroll
+            for (int j = 0; j < (int)(TC_A_BYTES / 16 / 128); ++j) {   // 8 x 16 bytes per thread
+                const uint32_t off = (uint32_t)(ct + j * 128) * 16u;
+                float4 x;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(hi_addr + off));
+                float4 h, l;
+                h.x = to_tf32(x.x); h.y = to_tf32(x.y); h.z = to_tf32(x.z); h.w = to_tf32(x.w);
+                l.x = to_tf32(x.x - h.x); l.y = to_tf32(x.y - h.y); l.z = to_tf32(x.z - h.z); l.w = to_tf32(x.w - h.w);
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(hi_addr + off), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(lo_addr + off), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA (async proxy)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_conv(s));
+        }
+        // ===================================== epilogue =========================================
+        mbar_wait(bar_accum, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int q = warp & 3;                                        // TMEM lane quarter this warp may read
+        const int r = q * 32 + lane;                                   // tile row == TMEM lane
+        const int m = m_base + r;
+        const bool row_ok = (r < rows_valid) && (m < g.M);
+        const int step = g.step ? *g.step : 0;
+        const float* rowvec = g.rowvec ? g.rowvec + (int64_t)step * g.rowvec_step_stride : nullptr;
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+        float v[32];
+        if (p.splits == 1) {
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                tmem_ld32(trow + (uint32_t)c0, v);
+                if (row_ok && n0 + c0 < g.N) tc_epilogue_store<BN>(g, v, m, n0 + c0, rowvec);
+            }
+        } else {
+            const int tile_lin = blockIdx.y * gridDim.x + blockIdx.x;
+            float* wst = p.ws + ((int64_t)tile_lin * p.splits) * (TC_BM * BN);
+            float* mine = wst + (int64_t)blockIdx.z * (TC_BM * BN) + (int64_t)r * BN;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                tmem_ld32(trow + (uint32_t)c0, v);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) st_f4(mine + c0 + j * 4, make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]));
+            }
+            __threadfence();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            __shared__ int s_last;
+            if (ct == 0) {
+                const int prev = atomicAdd(p.counters + tile_lin, 1);
+                s_last = (prev == p.splits - 1) ? 1 : 0;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (s_last) {
+                __threadfence();
+                if (row_ok) {
+#pragma unroll 1
+                    for (int c0 = 0; c0 < BN; c0 += 32) {
+                        if (n0 + c0 >= g.N) break;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+                        for (int z = 0; z < p.splits; ++z) {               // fixed order -> deterministic
+                            const float* src = wst + (int64_t)z * (TC_BM * BN) + (int64_t)r * BN + c0;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float4 t4 = __ldcg(reinterpret_cast<const float4*>(src + j * 4));
+                                v[j * 4] += t4.x; v[j * 4 + 1] += t4.y; v[j * 4 + 2] += t4.z; v[j * 4 + 3] += t4.w;
+                            }
+                        }
+                        tc_epilogue_store<BN>(g, v, m, n0 + c0, rowvec);
+                    }
+                }
+                if (ct == 0) p.counters[tile_lin] = 0;                      // ready for the next launch / graph replay
+            }
+        }
+    }
+    // ---- teardown -------------------------------------------------------------------------------------
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+    }
+}
+
+// =====================================================================================================
+// host side
+// =====================================================================================================
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+struct TcGeometry {
+    int BN, splits, gx, gy, Lrows, Bs, box_l, box_b, tiles_per_sample, total_it;
+    int64_t ws_floats;
+};
+
+bool gemm_tc_supported(const mugd_gemm& g) {
+    if (!(g.conv_mode == MUGD_CONV_NONE || g.conv_mode == MUGD_CONV_SAME)) return false;
+    if (g.K % TC_BK != 0 || g.N < 64 || g.N % 4 != 0) return false;
+    if (!g.W_hi || !g.W_lo) return false;
+    if (g.lda % 4 != 0 || !aligned16(g.A) || !aligned16(g.W_hi) || !aligned16(g.W_lo)) return false;
+    return true;
+}
+
+static TcGeometry tc_geometry(const mugd_gemm& g, int sm_count, int forced_split) {
+    TcGeometry t;
+    t.BN = (g.N >= 128) ? 128 : 64;
+    if (g.conv_mode == MUGD_CONV_NONE) { t.Lrows = g.M; t.Bs = 1; }
+    else { t.Lrows = g.Lout; t.Bs = g.M / g.Lout; }
+    if (t.Lrows >= TC_BM) {
+        t.box_l = TC_BM; t.box_b = 1;
+        t.tiles_per_sample = (t.Lrows + TC_BM - 1) / TC_BM;
+        t.gy = t.tiles_per_sample * t.Bs;
+    } else {
+        t.box_l = t.Lrows;
+        t.box_b = TC_BM / t.Lrows;
+        if (t.box_b > t.Bs) t.box_b = t.Bs;
+        t.tiles_per_sample = 1;
+        t.gy = (t.Bs + t.box_b - 1) / t.box_b;
+    }
+    t.gx = (g.N + t.BN - 1) / t.BN;
+    t.total_it = g.taps * (g.K / TC_BK);
+    int splits = 1;
+    const int tiles = t.gx * t.gy;
+    if (forced_split > 0) splits = forced_split;
+    else if (tiles < sm_count) {
+        splits = (sm_count + tiles - 1) / tiles;
+        const int max_by_k = t.total_it / 4 > 0 ? t.total_it / 4 : 1;     // keep >= 4 k-steps per split
+        if (splits > max_by_k) splits = max_by_k;
+        if (splits > 16) splits = 16;
+    }
+    if (splits > t.total_it) splits = t.total_it;
+    if (splits < 1) splits = 1;
+    t.splits = splits;
+    t.ws_floats = splits > 1 ? (int64_t)tiles * splits * TC_BM * t.BN : 0;
+    return t;
+}
+
+template <int BN>
+static int tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmWhi, const CUtensorMap& tmWlo, const TcParams& p,
+                     const TcGeometry& t, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        MUGD_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcSmem<BN>::TOTAL));
+        configured = true;
+    }
+    dim3 grid(t.gx, t.gy, t.splits);
+    gemm_tc_kernel<BN><<<grid, TC_THREADS, TcSmem<BN>::TOTAL, st>>>(tmA, tmWhi, tmWlo, p);
+    MUGD_CHECK_CUDA(cudaGetLastError());
+    return MUGD_OK;
+}
+
+int launch_gemm_tc(const DeviceInfo& dev, const mugd_gemm& g, cudaStream_t st, int* launches) {
+    MUGD_REQUIRE(gemm_tc_supported(g), "gemm_tc: unsupported shape/operands");
+    EncodeTiledFn enc = get_encode();
+    MUGD_REQUIRE(enc != nullptr, "gemm_tc: cuTensorMapEncodeTiled not available from the driver");
+    const TcGeometry t = tc_geometry(g, dev.sm_count, g.split_k);
+    if (t.splits > 1) {
+        MUGD_REQUIRE(g.workspace && g.counters, "gemm_tc: split-K needs workspace and counters");
+        MUGD_REQUIRE(g.workspace_bytes >= t.ws_floats * 4, "gemm_tc: workspace too small (%lld < %lld)", (long long)g.workspace_bytes,
+                     (long long)t.ws_floats * 4);
+        MUGD_REQUIRE(g.n_counters >= t.gx * t.gy, "gemm_tc: need %d tile counters, have %d", t.gx * t.gy, g.n_counters);
+    }
+    CUtensorMap tmA, tmWhi, tmWlo;
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)g.K, (cuuint64_t)t.Lrows, (cuuint64_t)t.Bs};
+        cuuint64_t strides[2] = {(cuuint64_t)g.lda * 4, (cuuint64_t)t.Lrows * (cuuint64_t)g.lda * 4};
+        cuuint32_t box[3] = {(cuuint32_t)TC_BK, (cuuint32_t)t.box_l, (cuuint32_t)t.box_b};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(g.A), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        MUGD_REQUIRE(r == CUDA_SUCCESS, "gemm_tc: cuTensorMapEncodeTiled(A) failed with %d (K=%d L=%d B=%d lda=%lld)", (int)r, g.K,
+                     t.Lrows, t.Bs, (long long)g.lda);
+    }
+    for (int w = 0; w < 2; ++w) {
+        const cuuint64_t ktot = (cuuint64_t)g.taps * g.K;
+        cuuint64_t dims[2] = {ktot, (cuuint64_t)g.N};
+        cuuint64_t strides[1] = {ktot * 4};
+        cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)t.BN};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = enc(w == 0 ? &tmWhi : &tmWlo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(w == 0 ? g.W_hi : g.W_lo), dims,
+                         strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        MUGD_REQUIRE(r == CUDA_SUCCESS, "gemm_tc: cuTensorMapEncodeTiled(W) failed with %d", (int)r);
+    }
+    TcParams p;
+    p.g = g;
+    p.ws = (float*)g.workspace;
+    p.counters = g.counters;
+    p.splits = t.splits;
+    p.total_it = t.total_it;
+    p.kblocks = g.K / TC_BK;
+    p.Lrows = t.Lrows;
+    p.Bs = t.Bs;
+    p.box_l = t.box_l;
+    p.box_b = t.box_b;
+    p.tiles_per_sample = t.tiles_per_sample;
+    int rc = (t.BN == 128) ? tc_launch<128>(tmA, tmWhi, tmWlo, p, t, st) : tc_launch<64>(tmA, tmWhi, tmWlo, p, t, st);
+    if (rc != MUGD_OK) return rc;
+    if (launches) *launches += 1;
+    return MUGD_OK;
 }
 
 }  // namespace mugd
+
+extern "C" int mugd_gemm_tc_query(mugd_handle*, const mugd_gemm* g, int32_t sm_count, int32_t* supported, int32_t* splits,
+                                  int64_t* workspace_bytes, int32_t* n_tiles) {
+    using namespace mugd;
+    MUGD_REQUIRE(g, "gemm_tc_query: null");
+    const bool ok = (g->conv_mode == MUGD_CONV_NONE || g->conv_mode == MUGD_CONV_SAME) && g->K % TC_BK == 0 && g->N >= 64 && g->N % 4 == 0;
+    if (supported) *supported = ok ? 1 : 0;
+    if (!ok) {
+        if (splits) *splits = 0;
+        if (workspace_bytes) *workspace_bytes = 0;
+        if (n_tiles) *n_tiles = 0;
+        return MUGD_OK;
+    }
+    const TcGeometry t = tc_geometry(*g, sm_count > 0 ? sm_count : 148, g->split_k);
+    if (splits) *splits = t.splits;
+    if (workspace_bytes) *workspace_bytes = t.ws_floats * 4;
+    if (n_tiles) *n_tiles = t.gx * t.gy;
+    return MUGD_OK;
+}

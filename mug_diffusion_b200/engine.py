@@ -74,8 +74,9 @@ class Arena:
 
 
 class OpList:
-    def __init__(self):
+    def __init__(self, tc_map: Optional[Dict[int, Tuple[int, int]]] = None):
         self.ops: List[L_.Op] = []
+        self.tc_map = tc_map or {}         # W pointer -> (W_hi, W_lo) pointers of the TF32 split
 
     def add(self, kind: int, desc, tag: int = 0):
         self.ops.append(L_.make_op(kind, desc, tag))
@@ -89,11 +90,14 @@ class OpList:
              mode: int = L_.CONV_NONE, Lin: int = 0, Lout: int = 0, act: int = L_.ACT_NONE,
              gate: int = L_.GATE_NONE, residual: Optional[View] = None, rowvec: int = 0,
              rowvec_b_stride: int = 0, rowvec_step_stride: int = 0, step: int = 0, impl: int = L_.GEMM_AUTO,
-             W_lo: int = 0, tag: int = 0):
+             W_hi: int = 0, W_lo: int = 0, split_k: int = 0, tag: int = 0):
         g = L_.Gemm()
         M = out.rows
         g.A, g.lda = A.ptr, A.ld
-        g.W, g.W_lo, g.bias = W, W_lo or None, bias or None
+        if not W_hi and W in self.tc_map:
+            W_hi, W_lo = self.tc_map[W]
+        g.W, g.W_hi, g.W_lo, g.bias = W, W_hi or None, W_lo or None, bias or None
+        g.split_k = split_k
         g.rowvec, g.rowvec_b_stride, g.rowvec_step_stride = rowvec or None, rowvec_b_stride, rowvec_step_stride
         g.step = step or None
         if residual is not None:
@@ -154,6 +158,20 @@ class OpList:
         self.add(L_.OP_COPY2D, d, tag)
 
 
+def tc_weight_map(blob: WeightBlob, wbase: int) -> Dict[int, Tuple[int, int]]:
+    """address of every GEMM weight that has a TF32 hi/lo split in the blob -> (hi address, lo address)"""
+    cached = getattr(blob, "_tc_map", None)
+    if cached is not None and cached[0] == wbase:
+        return cached[1]
+    m = {}
+    for name, e in blob.entries.items():
+        if name.endswith("#hi"):
+            base = name[:-3]
+            m[wbase + 4 * blob.offset(base)] = (wbase + 4 * e.offset, wbase + 4 * blob.offset(base + "#lo"))
+    blob._tc_map = (wbase, m)
+    return m
+
+
 # tags (profiling labels carried in mugd_op.tag)
 TAG_RES, TAG_ATTN, TAG_S4, TAG_UPDOWN, TAG_IO = 1, 2, 3, 4, 5
 
@@ -170,7 +188,7 @@ class UNetCompiler:
 
     def compile(self, arena: Arena, Beff: int, Lz: int, ext: Dict[str, int], per_sample_t: bool) -> dict:
         cfg = self.cfg
-        ops = OpList()
+        ops = OpList(tc_weight_map(self.blob, self.wbase))
         nlev = cfg.levels
         assert Lz % (1 << (nlev - 1)) == 0 and (Lz >> (nlev - 1)) % 4 == 0, "z_length must be a multiple of 32"
         rows = [Beff * (Lz >> l) for l in range(nlev)]
@@ -410,7 +428,7 @@ class DecoderCompiler:
 
     def compile(self, arena: Arena, B: int, Lz: int) -> dict:
         cfg = self.cfg
-        ops = OpList()
+        ops = OpList(tc_weight_map(self.blob, self.wbase))
         G = cfg.num_groups
         zin = arena.alloc(B * Lz, cfg.z_channels)
         cur = zin

@@ -18,18 +18,20 @@ CONV_NONE, CONV_SAME, CONV_DOWN, CONV_UP = range(4)
 ACT_NONE, ACT_SILU, ACT_GELU = range(3)
 GATE_NONE, GATE_GEGLU, GATE_GLU = range(3)
 GEMM_AUTO, GEMM_SIMT, GEMM_TC = range(3)
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 _f = C.c_void_p  # device pointers travel as integers
 
 
 class Gemm(C.Structure):
-    _fields_ = [("A", _f), ("lda", C.c_int64), ("W", _f), ("W_lo", _f), ("bias", _f), ("rowvec", _f),
+    _fields_ = [("A", _f), ("lda", C.c_int64), ("W", _f), ("W_hi", _f), ("W_lo", _f), ("bias", _f), ("rowvec", _f),
                 ("rowvec_b_stride", C.c_int64), ("rowvec_step_stride", C.c_int64), ("step", _f),
                 ("residual", _f), ("ldr", C.c_int64), ("C", _f), ("ldc", C.c_int64),
                 ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
                 ("taps", C.c_int32), ("conv_mode", C.c_int32), ("Lin", C.c_int32), ("Lout", C.c_int32),
-                ("act", C.c_int32), ("gate", C.c_int32), ("impl", C.c_int32)]
+                ("act", C.c_int32), ("gate", C.c_int32), ("impl", C.c_int32),
+                ("split_k", C.c_int32), ("n_counters", C.c_int32), ("reserved0", C.c_int32),
+                ("workspace", _f), ("workspace_bytes", C.c_int64), ("counters", _f)]
 
 
 class GroupNorm(C.Structure):
@@ -128,6 +130,8 @@ def load() -> C.CDLL:
     lib.mugd_plan_destroy.argtypes = [C.c_void_p]
     lib.mugd_plan_destroy.restype = None
     lib.mugd_s4_kernel_gen.argtypes = [C.c_void_p] + [C.c_void_p] * 7 + [C.c_int32] * 4 + [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    lib.mugd_gemm_tc_query.argtypes = [C.c_void_p, C.POINTER(Gemm), C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                       C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
     lib.mugd_fill_i32.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
     lib.mugd_abi_sizes.argtypes = [C.POINTER(C.c_int32), C.c_int32]
     if lib.mugd_abi_version() != ABI_VERSION:
@@ -153,5 +157,5 @@ def check(rc: int, what: str = ""):
 EXPORTED_SYMBOLS = [
     "mugd_abi_version", "mugd_last_error", "mugd_create", "mugd_destroy", "mugd_device_info", "mugd_set_gemm_impl",
     "mugd_op_run", "mugd_plan_create", "mugd_plan_run", "mugd_plan_capture", "mugd_plan_replay",
-    "mugd_plan_launch_count", "mugd_plan_destroy", "mugd_s4_kernel_gen", "mugd_fill_i32", "mugd_abi_sizes",
+    "mugd_plan_launch_count", "mugd_plan_destroy", "mugd_s4_kernel_gen", "mugd_fill_i32", "mugd_abi_sizes", "mugd_gemm_tc_query",
 ]

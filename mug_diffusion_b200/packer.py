@@ -76,6 +76,19 @@ class WeightBlob:
         return self.data[e.offset:e.offset + n].view(e.shape)
 
 
+def tf32_rna(x: torch.Tensor) -> torch.Tensor:
+    """fp32 -> nearest TF32 value (10-bit mantissa, ties away from zero) = PTX cvt.rna.tf32.f32, as fp32."""
+    u = x.contiguous().view(torch.int32)
+    return ((u + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def tf32_split(w: torch.Tensor):
+    """w ~= hi + lo with both parts exactly representable in TF32 (the B operand of the 3xTF32 tensor-core GEMM)."""
+    hi = tf32_rna(w)
+    lo = tf32_rna(w - hi)
+    return hi, lo
+
+
 def _conv3(w: torch.Tensor) -> torch.Tensor:
     return w.permute(0, 2, 1).contiguous().reshape(w.shape[0], -1)
 
@@ -180,7 +193,8 @@ def all_unet_blocks(cfg: UNetConfig, prefix: str) -> List[Block]:
 
 
 def pack_model(sd: Dict[str, torch.Tensor], ucfg: UNetConfig, dcfg: DecoderConfig,
-               unet_prefix: str = "model.unet_model.", dec_prefix: str = "model.first_stage_model.decoder.") -> WeightBlob:
+               unet_prefix: str = "model.unet_model.", dec_prefix: str = "model.first_stage_model.decoder.",
+               tensor_core_split: bool = True) -> WeightBlob:
     blob = WeightBlob()
     up = unet_prefix
     for n in ("time_embed.0.", "time_embed.2."):
@@ -202,5 +216,25 @@ def pack_model(sd: Dict[str, torch.Tensor], ucfg: UNetConfig, dcfg: DecoderConfi
         _pack_block(blob, sd, b)
     for b in decoder_layout(dcfg, dec_prefix):
         _pack_block(blob, sd, b)
+    if tensor_core_split:
+        # pre-split every GEMM weight the tcgen05 kernel can take (K per tap % 32 == 0, N >= 64) into TF32 hi/lo
+        for name in list(blob.entries):
+            e = blob.entries[name]
+            if name.endswith("weight") and len(e.shape) == 2 and e.shape[0] >= 64 and e.shape[1] % 32 == 0:
+                w = _chunk_of(blob, name).view(e.shape)
+                hi, lo = tf32_split(w)
+                blob.add_shaped(name + "#hi", hi)
+                blob.add_shaped(name + "#lo", lo)
     blob.finalize()
     return blob
+
+
+def _chunk_of(blob: WeightBlob, name: str) -> torch.Tensor:
+    """the (not yet concatenated) flat tensor of an entry"""
+    off = 0
+    target = blob.entries[name].offset
+    for c in blob._chunks:
+        if off == target and c.numel() == int(torch.tensor(blob.entries[name].shape).prod()):
+            return c
+        off += c.numel()
+    raise KeyError(name)

@@ -10,7 +10,7 @@ import torch
 
 from . import lib as L_
 from .config import ModelConfig
-from .engine import (Arena, CTX_TOKENS_MAX, DecoderCompiler, MAX_STEPS, OpList, UNetCompiler, View)
+from .engine import (Arena, CTX_TOKENS_MAX, DecoderCompiler, MAX_STEPS, OpList, UNetCompiler, View, tc_weight_map)
 from .netspec import s4_blocks
 from .packer import WeightBlob, pack_model
 
@@ -27,6 +27,7 @@ class Plan:
     def __init__(self, engine: "MugEngine", ops: OpList):
         self.engine = engine
         self.n_ops = len(ops.ops)
+        engine.attach_workspace(ops)
         self._arr = ops.array()
         self.handle = C.c_void_p()
         L_.check(engine.lib.mugd_plan_create(engine.handle, self._arr, self.n_ops, C.byref(self.handle)), "plan_create")
@@ -75,18 +76,30 @@ class MugEngine:
         self.weights = self.blob.data.to(self.device)          # the ~420 MB HBM-resident blob
         self.wbase = self.weights.data_ptr()
         self.lock = threading.RLock()
+        # split-K scratch of the tensor-core GEMM: all ops run in stream order, so one buffer serves every plan
+        # (bound: tiles*splits < 2*SMs tiles of 128x128 fp32)
+        self.tc_ws = torch.zeros(8 * 1024 * 1024, device=self.device)          # 32 MB
+        self.tc_counters = torch.zeros(4096, dtype=torch.int32, device=self.device)
         self.sessions: Dict[tuple, "Session"] = {}
         self.dec_sessions: Dict[tuple, "DecoderSession"] = {}
         self.set_gemm_impl(gemm_impl)
 
     def set_gemm_impl(self, impl: str):
-        code = {"auto": L_.GEMM_SIMT, "simt": L_.GEMM_SIMT, "tc": L_.GEMM_TC}[impl]
+        code = {"auto": L_.GEMM_TC, "simt": L_.GEMM_SIMT, "tc": L_.GEMM_TC}[impl]
         L_.check(self.lib.mugd_set_gemm_impl(self.handle, code), "set_gemm_impl")
         self.gemm_impl = impl
         self.sessions.clear()
         self.dec_sessions.clear()
 
+    def attach_workspace(self, ops: OpList):
+        for op in ops.ops:
+            if op.kind == L_.OP_GEMM:
+                g = op.u.gemm
+                g.workspace, g.workspace_bytes = self.tc_ws.data_ptr(), self.tc_ws.numel() * 4
+                g.counters, g.n_counters = self.tc_counters.data_ptr(), self.tc_counters.numel()
+
     def run_ops(self, ops: OpList):
+        self.attach_workspace(ops)
         st = _stream()
         for op in ops.ops:
             L_.check(self.lib.mugd_op_run(self.handle, C.byref(op), st), f"op kind {op.kind}")
@@ -210,7 +223,7 @@ class Session:
         args = t[:, None].float() * freqs[None]
         emb = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
         self.temb[:R].copy_(emb.to(eng.device))
-        ops = OpList()
+        ops = OpList(tc_weight_map(eng.blob, eng.wbase))
         up = self.comp.prefix
         tv = View(_ptr(self.temb), cfg.model_channels, R, cfg.model_channels)
         h1 = View(_ptr(self.emb_h1), cfg.time_embed_dim, R, cfg.time_embed_dim)
@@ -236,7 +249,7 @@ class Session:
             self.ctx_tokens = T
             self._build(self.comp)            # Lk is baked into the attention ops
         context = context.to(eng.device, torch.float32).contiguous()
-        ops = OpList()
+        ops = OpList(tc_weight_map(eng.blob, eng.wbase))
         ops.transpose(_ptr(context), _ptr(self.ctx), 0, cfg.context_dim, Bc, Cd, T, True)
         cv = View(_ptr(self.ctx), cfg.context_dim, Bc * T, cfg.context_dim)
         blocks = [b for b in _all_blocks(self.comp) if b.kind == "attn"]
