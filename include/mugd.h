@@ -190,6 +190,10 @@ int  mugd_s4_kernel_gen(mugd_handle* h,
 int  mugd_gemm_tc_query(mugd_handle* h, const mugd_gemm* g, int32_t sm_count, int32_t* supported, int32_t* splits,
                         int64_t* workspace_bytes, int32_t* n_tiles);
 
+/* debugging aid: when set (device pointer to 8 x int64), CTA (0,0,0) of every tensor-core GEMM launch writes
+ * %globaltimer stamps {kernel entry, setup done, accumulator ready, tile staged in smem, epilogue done}; pass NULL to disable */
+int  mugd_debug_set_tc_timing(long long* device_buf4);
+
 /* ---- utility ---------------------------------------------------------------------------------- */
 int  mugd_fill_i32(int32_t* dst, int32_t value, void* stream);
 /* sizeof() of {mugd_op, mugd_gemm, mugd_groupnorm, mugd_layernorm, mugd_attention, mugd_s4conv,

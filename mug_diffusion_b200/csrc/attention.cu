@@ -6,117 +6,177 @@
 // The post-softmax gain multiplies the numerator only; the softmax denominator accumulates plain p.
 // Self attention (Lk = Lq) and cross attention to the 21 prompt tokens (Lk = 21) share the kernel.
 //
-// One thread owns one query row (q, accumulator and running max/sum in registers); a CTA of 64 queries
-// streams K/V tiles of 32 keys through shared memory, read back as warp-broadcast float4 (conflict-free).
+// Register-tiled FFMA formulation: a CTA of 256 threads (16 x 16) owns 64 queries of one (sample, head) and
+// streams 64-key tiles.  S = Q K^T is a 64x64xD smem-tiled product with 4x4 micro-tiles (operands stored
+// k-major so both are read as conflict-free float4), the online softmax runs on the micro-tile with
+// 16-lane shuffle reductions, P*gain goes back to shared memory transposed, and O += P V is a second
+// 64 x D x 64 product.  Exact fp32 (expf, IEEE division): this is 2.6 % of the FLOPs, the parity-critical
+// part (non-standard bias + gain) rather than the fast part of the network.
 #include "common.cuh"
 
 #include <math.h>
 
 namespace mugd {
 
-constexpr int AT_Q = 64;    // queries (threads) per CTA
-constexpr int AT_TK = 32;   // keys per smem tile
+constexpr int AT_BQ = 64;
+constexpr int AT_BK = 64;
+constexpr int AT_PAD = 4;
+constexpr int AT_THREADS = 256;
 
 template <int D>
-__global__ void __launch_bounds__(AT_Q)
-attention_kernel(const mugd_attention a) {
-    __shared__ __align__(16) float Ks[AT_TK][D];
-    __shared__ __align__(16) float Vs[AT_TK][D];
-    extern __shared__ float tabs[];           // [2][2P+1] : relpos column h, cgain column h
-    const int P = a.pos_max, NT = 2 * P + 1;
-    float* rel = tabs;
-    float* cg = tabs + NT;
+struct AttSmem {
+    static constexpr int QT = D * (AT_BQ + AT_PAD);
+    static constexpr int KT = D * (AT_BK + AT_PAD);
+    static constexpr int VS = AT_BK * D;
+    static constexpr int PT = AT_BK * (AT_BQ + AT_PAD);
+    static constexpr int FLOATS = QT + KT + VS + PT;
+};
 
+template <int D>
+__global__ void __launch_bounds__(AT_THREADS)
+attention_kernel(const mugd_attention a) {
+    constexpr int DC = D / 16;                 // output columns per thread
+    constexpr int SQ = AT_BQ + AT_PAD, SK = AT_BK + AT_PAD;
+    extern __shared__ __align__(16) float sm[];
+    float* Qt = sm;                            // [D][SQ]   Qt[k][row]
+    float* Kt = Qt + AttSmem<D>::QT;           // [D][SK]   Kt[k][col]
+    float* Vs = Kt + AttSmem<D>::KT;           // [BK][D]
+    float* Pt = Vs + AttSmem<D>::VS;           // [BK][SQ]  Pt[key][row] = p * gain
+    float* rel = Pt + AttSmem<D>::PT;          // [2P+1]
+    const int P = a.pos_max, NT = 2 * P + 1;
+    float* cg = rel + NT;
+
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int b = blockIdx.z, h = blockIdx.y;
-    const int i = blockIdx.x * AT_Q + threadIdx.x;    // query index
-    const bool active = i < a.Lq;
-    for (int t = threadIdx.x; t < NT; t += AT_Q) {
+    const int q0 = blockIdx.x * AT_BQ;
+    for (int t = tid; t < NT; t += AT_THREADS) {
         rel[t] = a.relpos[t * a.H + h];
         cg[t] = a.cgain[t * a.H + h];
     }
-
-    float q[D], acc[D];
-#pragma unroll
-    for (int d = 0; d < D; ++d) acc[d] = 0.f;
-    if (active) {
-        const float* qp = a.q + ((int64_t)b * a.Lq + i) * a.ldq + h * D;
-#pragma unroll
-        for (int d = 0; d < D; d += 4) {
-            const float4 v = ld_f4(qp + d);
-            q[d] = v.x; q[d + 1] = v.y; q[d + 2] = v.z; q[d + 3] = v.w;
-        }
-    } else {
-#pragma unroll
-        for (int d = 0; d < D; ++d) q[d] = 0.f;
-    }
-    float mrun = -INFINITY, lrun = 0.f;
-
-    const float* kbase = a.k + (int64_t)b * a.Lk * a.ldk + h * D;
-    const float* vbase = a.v + (int64_t)b * a.Lk * a.ldv + h * D;
     constexpr int QD = D / 4;
-    for (int j0 = 0; j0 < a.Lk; j0 += AT_TK) {
-        __syncthreads();   // previous tile fully consumed (also orders the table writes on the first pass)
-        for (int t = threadIdx.x; t < AT_TK * QD; t += AT_Q) {
+    {
+        const float* qb = a.q + (int64_t)b * a.Lq * a.ldq + h * D;
+        for (int t = tid; t < AT_BQ * QD; t += AT_THREADS) {
+            const int r = t / QD, c = (t - r * QD) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (q0 + r < a.Lq) v = ld_f4(qb + (int64_t)(q0 + r) * a.ldq + c);
+            Qt[(c + 0) * SQ + r] = v.x; Qt[(c + 1) * SQ + r] = v.y; Qt[(c + 2) * SQ + r] = v.z; Qt[(c + 3) * SQ + r] = v.w;
+        }
+    }
+    float m_i[4], l_i[4], o[4][DC];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        m_i[i] = -INFINITY; l_i[i] = 0.f;
+#pragma unroll
+        for (int c = 0; c < DC; ++c) o[i][c] = 0.f;
+    }
+    const float* kb = a.k + (int64_t)b * a.Lk * a.ldk + h * D;
+    const float* vb = a.v + (int64_t)b * a.Lk * a.ldv + h * D;
+
+    for (int j0 = 0; j0 < a.Lk; j0 += AT_BK) {
+        __syncthreads();                       // previous tile consumed (first pass: Qt / tables written)
+        for (int t = tid; t < AT_BK * QD; t += AT_THREADS) {
             const int r = t / QD, c = (t - r * QD) * 4;
             float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
             if (j0 + r < a.Lk) {
-                kv = ld_f4(kbase + (int64_t)(j0 + r) * a.ldk + c);
-                vv = ld_f4(vbase + (int64_t)(j0 + r) * a.ldv + c);
+                kv = ld_f4(kb + (int64_t)(j0 + r) * a.ldk + c);
+                vv = ld_f4(vb + (int64_t)(j0 + r) * a.ldv + c);
             }
-            *reinterpret_cast<float4*>(&Ks[r][c]) = kv;
-            *reinterpret_cast<float4*>(&Vs[r][c]) = vv;
+            Kt[(c + 0) * SK + r] = kv.x; Kt[(c + 1) * SK + r] = kv.y; Kt[(c + 2) * SK + r] = kv.z; Kt[(c + 3) * SK + r] = kv.w;
+            *reinterpret_cast<float4*>(&Vs[r * D + c]) = vv;
         }
         __syncthreads();
-        const int nk = min(AT_TK, a.Lk - j0);
-        float s[AT_TK];
-        float tmax = -INFINITY;
+        // ---- S = Q K^T on a 4x4 micro-tile ---------------------------------------------------------------
+        float s[4][4];
 #pragma unroll
-        for (int r = 0; r < AT_TK; ++r) {
-            float dot = 0.f;
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int d = 0; d < D; d += 4) {
-                const float4 kv = *reinterpret_cast<const float4*>(&Ks[r][d]);
-                dot = fmaf(q[d], kv.x, dot);
-                dot = fmaf(q[d + 1], kv.y, dot);
-                dot = fmaf(q[d + 2], kv.z, dot);
-                dot = fmaf(q[d + 3], kv.w, dot);
-            }
-            int idx = (j0 + r) - i;
-            idx = max(-P, min(P, idx)) + P;
-            const float sv = (r < nk) ? (dot + rel[idx]) * a.scale : -INFINITY;
-            s[r] = sv;
-            tmax = fmaxf(tmax, sv);
+            for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
+#pragma unroll 8
+        for (int kk = 0; kk < D; ++kk) {
+            const float4 qa = *reinterpret_cast<const float4*>(&Qt[kk * SQ + ty * 4]);
+            const float4 kv = *reinterpret_cast<const float4*>(&Kt[kk * SK + tx * 4]);
+            const float qf[4] = {qa.x, qa.y, qa.z, qa.w}, kf[4] = {kv.x, kv.y, kv.z, kv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) s[i][j] = fmaf(qf[i], kf[j], s[i][j]);
         }
-        const float mnew = fmaxf(mrun, tmax);          // finite: every tile holds >= 1 valid key
-        const float corr = expf(mrun - mnew);          // exp(-inf) = 0 on the first tile
-        lrun *= corr;
+        // ---- bias, scale, mask, online softmax ------------------------------------------------------------
+        float pc[4][4];
 #pragma unroll
-        for (int d = 0; d < D; ++d) acc[d] *= corr;
+        for (int i = 0; i < 4; ++i) {
+            const int qi = q0 + ty * 4 + i;
+            float mx = -INFINITY;
+            int idx[4];
 #pragma unroll
-        for (int r = 0; r < AT_TK; ++r) {
-            const float pexp = expf(s[r] - mnew);      // 0 for masked keys
-            lrun += pexp;
-            int idx = (j0 + r) - i;
-            idx = max(-P, min(P, idx)) + P;
-            const float pc = pexp * cg[idx];
-#pragma unroll
-            for (int d = 0; d < D; d += 4) {
-                const float4 vv = *reinterpret_cast<const float4*>(&Vs[r][d]);
-                acc[d] = fmaf(pc, vv.x, acc[d]);
-                acc[d + 1] = fmaf(pc, vv.y, acc[d + 1]);
-                acc[d + 2] = fmaf(pc, vv.z, acc[d + 2]);
-                acc[d + 3] = fmaf(pc, vv.w, acc[d + 3]);
+            for (int j = 0; j < 4; ++j) {
+                const int kj = j0 + tx * 4 + j;
+                idx[j] = max(-P, min(P, kj - qi)) + P;
+                s[i][j] = (kj < a.Lk) ? (s[i][j] + rel[idx[j]]) * a.scale : -INFINITY;
+                mx = fmaxf(mx, s[i][j]);
             }
-        }
-        mrun = mnew;
-    }
-    if (active) {
-        const float inv = 1.0f / lrun;
-        float* op = a.o + ((int64_t)b * a.Lq + i) * a.ldo + h * D;
 #pragma unroll
-        for (int d = 0; d < D; d += 4)
-            st_f4(op + d, make_float4(acc[d] * inv, acc[d + 1] * inv, acc[d + 2] * inv, acc[d + 3] * inv));
+            for (int off = 8; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+            const float mnew = fmaxf(m_i[i], mx);          // finite: column j0 of every tile is a valid key
+            const float corr = expf(m_i[i] - mnew);
+            float rs = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float pe = expf(s[i][j] - mnew);      // 0 for masked keys
+                rs += pe;
+                pc[i][j] = pe * cg[idx[j]];
+            }
+#pragma unroll
+            for (int off = 8; off > 0; off >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, off);
+            l_i[i] = l_i[i] * corr + rs;
+            m_i[i] = mnew;
+#pragma unroll
+            for (int c = 0; c < DC; ++c) o[i][c] *= corr;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<float4*>(&Pt[(tx * 4 + j) * SQ + ty * 4]) = make_float4(pc[0][j], pc[1][j], pc[2][j], pc[3][j]);
+        __syncthreads();
+        // ---- O += P V ----------------------------------------------------------------------------------------
+        const int nk = min(AT_BK, a.Lk - j0);
+#pragma unroll 4
+        for (int kk = 0; kk < nk; ++kk) {
+            const float4 pa = *reinterpret_cast<const float4*>(&Pt[kk * SQ + ty * 4]);
+            const float pf[4] = {pa.x, pa.y, pa.z, pa.w};
+            float vf[DC];
+#pragma unroll
+            for (int c = 0; c < DC; ++c) vf[c] = Vs[kk * D + tx * DC + c];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int c = 0; c < DC; ++c) o[i][c] = fmaf(pf[i], vf[c], o[i][c]);
+        }
     }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int qi = q0 + ty * 4 + i;
+        if (qi < a.Lq) {
+            const float inv = 1.0f / l_i[i];
+            float* op = a.o + ((int64_t)b * a.Lq + qi) * a.ldo + h * D + tx * DC;
+#pragma unroll
+            for (int c = 0; c < DC; ++c) op[c] = o[i][c] * inv;
+        }
+    }
+}
+
+template <int D>
+static int attention_launch(const mugd_attention& a, cudaStream_t st) {
+    const size_t bytes = sizeof(float) * (AttSmem<D>::FLOATS + 2 * (2 * a.pos_max + 1));
+    static size_t configured = 0;
+    if (bytes > configured) {
+        MUGD_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        configured = bytes;
+    }
+    dim3 grid((a.Lq + AT_BQ - 1) / AT_BQ, a.H, a.B);
+    attention_kernel<D><<<grid, AT_THREADS, bytes, st>>>(a);
+    MUGD_CHECK_CUDA(cudaGetLastError());
+    return MUGD_OK;
 }
 
 int launch_attention(const DeviceInfo&, const mugd_attention& a, cudaStream_t st, int* launches) {
@@ -127,12 +187,8 @@ int launch_attention(const DeviceInfo&, const mugd_attention& a, cudaStream_t st
                      a.ldv % 4 == 0 && a.ldo % 4 == 0, "attention: alignment");
     MUGD_REQUIRE(a.ldq >= a.H * a.D && a.ldk >= a.H * a.D && a.ldv >= a.H * a.D && a.ldo >= a.H * a.D, "attention: ld < H*D");
     MUGD_REQUIRE(a.relpos && a.cgain, "attention: tables missing");
-    dim3 grid((a.Lq + AT_Q - 1) / AT_Q, a.H, a.B);
-    const size_t dyn = sizeof(float) * 2 * (2 * a.pos_max + 1);
-    if (a.D == 32) attention_kernel<32><<<grid, AT_Q, dyn, st>>>(a);
-    else if (a.D == 48) attention_kernel<48><<<grid, AT_Q, dyn, st>>>(a);
-    else attention_kernel<64><<<grid, AT_Q, dyn, st>>>(a);
-    MUGD_CHECK_CUDA(cudaGetLastError());
+    int rc = (a.D == 32) ? attention_launch<32>(a, st) : (a.D == 48) ? attention_launch<48>(a, st) : attention_launch<64>(a, st);
+    if (rc != MUGD_OK) return rc;
     if (launches) *launches += 1;
     return MUGD_OK;
 }

@@ -18,8 +18,9 @@
 //   warp 2      TMEM allocator (BN fp32 columns x 128 lanes).
 //   warps 4-7   epilogue     : tcgen05.ld 32x32b (thread = one output row, 32 columns at a time) -> bias /
 //                              time-embedding row / SiLU / GELU / GEGLU / GLU / residual -> 128-byte row stores.
-//                              With split-K the partial tile goes to a workspace and the last CTA of the tile
-//                              (atomic ticket) reduces the splits in fixed order (deterministic) and runs the epilogue.
+//                              staged through shared memory so that all global traffic is row-contiguous/coalesced.
+//                              With split-K the partial tile goes to an L2-resident workspace and a second, fully
+//                              parallel kernel sums the splits in fixed order (deterministic) and runs the epilogue.
 //
 // Reference call sites are the same as gemm_simt.cu (which remains the exact-fp32 referee and the fallback for
 // shapes this kernel does not take: K % 32 != 0, N < 64, strided / upsampling convs).
@@ -44,9 +45,15 @@ struct TcParams {
     int32_t Lrows, Bs;        // row structure of the A tensor map (Lrows = rows per sample, Bs samples)
     int32_t box_l, box_b;     // TMA box: box_l rows of box_b consecutive samples (box_l*box_b <= 128)
     int32_t tiles_per_sample; // when Lrows >= 128
+    long long* dbg;           // optional: CTA (0,0,0) writes globaltimer stamps {entry, setup done, accumulator ready, tile staged, epilogue done}
 };
 
 // ---- raw PTX helpers ---------------------------------------------------------------------------------
+__device__ __forceinline__ long long gtimer() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -133,49 +140,88 @@ struct TcSmem {
     static constexpr uint32_t TOTAL = TILE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN>
-__device__ __forceinline__ void tc_epilogue_store(const mugd_gemm& g, const float* v, int m, int n, const float* rowvec) {
-    // v: 32 consecutive accumulator columns n..n+31 of output row m (N % 4 == 0 guaranteed)
-    const int bidx = m / g.Lout;
+// Fused epilogue math on 4 consecutive accumulator columns.  ACT / GATE are compile-time so that the compiler
+// cannot if-convert the branches into "compute SiLU, GELU and both gates for every element, then select"
+// (which it did, costing ~4 us per tile); callers dispatch once per kernel on the (uniform) act/gate values.
+template <int ACT, int GATE>
+__device__ __forceinline__ void tc_finish4(const mugd_gemm& g, float4 acc, float4 bia, float4 rvv, float4 res, int m, int nn) {
+    float x[4] = {acc.x + bia.x + rvv.x, acc.y + bia.y + rvv.y, acc.z + bia.z + rvv.z, acc.w + bia.w + rvv.w};
+    if constexpr (ACT == MUGD_ACT_SILU) {
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        const int nn = n + q * 4;
-        if (nn >= g.N) break;
-        float x[4] = {v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]};
-        if (g.bias) {
-            const float4 bb = ld_f4(g.bias + nn);
-            x[0] += bb.x; x[1] += bb.y; x[2] += bb.z; x[3] += bb.w;
-        }
-        if (rowvec) {
-            const float4 rv = ld_f4(rowvec + (int64_t)bidx * g.rowvec_b_stride + nn);
-            x[0] += rv.x; x[1] += rv.y; x[2] += rv.z; x[3] += rv.w;
-        }
-        if (g.act == MUGD_ACT_SILU) {
+        for (int j = 0; j < 4; ++j) x[j] = silu_f(x[j]);
+    } else if constexpr (ACT == MUGD_ACT_GELU) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) x[j] = silu_f(x[j]);
-        } else if (g.act == MUGD_ACT_GELU) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) x[j] = gelu_f(x[j]);
+        for (int j = 0; j < 4; ++j) x[j] = gelu_f(x[j]);
+    }
+    if constexpr (GATE == MUGD_GATE_NONE) {
+        st_f4(g.C + (int64_t)m * g.ldc + nn, make_float4(x[0] + res.x, x[1] + res.y, x[2] + res.z, x[3] + res.w));
+    } else {
+        float o0, o1;
+        if constexpr (GATE == MUGD_GATE_GEGLU) { o0 = x[0] * gelu_f(x[1]); o1 = x[2] * gelu_f(x[3]); }
+        else { o0 = x[0] * sigmoid_f(x[1]); o1 = x[2] * sigmoid_f(x[3]); }
+        const int no = nn >> 1;
+        if (g.residual) {
+            const float2 rr = *reinterpret_cast<const float2*>(g.residual + (int64_t)m * g.ldr + no);
+            o0 += rr.x; o1 += rr.y;
         }
-        if (g.gate == MUGD_GATE_NONE) {
-            if (g.residual) {
-                const float4 rr = ld_f4(g.residual + (int64_t)m * g.ldr + nn);
-                x[0] += rr.x; x[1] += rr.y; x[2] += rr.z; x[3] += rr.w;
+        *reinterpret_cast<float2*>(g.C + (int64_t)m * g.ldc + no) = make_float2(o0, o1);
+    }
+}
+
+// phase 2 of the epilogue for one CTA: read the staged accumulator tile from shared memory (row pitch BN+4) and
+// finish it with coalesced global traffic; U float4 per thread in flight, every global load issued before any use.
+template <int BN, int ACT, int GATE>
+__device__ __forceinline__ void tc_store_tile(const mugd_gemm& g, uint32_t stage, int m_base, int n0, int rows_valid, const float* rowvec) {
+    constexpr int SP = BN + 4;
+    constexpr int C4 = BN / 4;
+    constexpr int U = 8;
+#pragma unroll 1
+    for (int i0 = 0; i0 < TC_BM * C4; i0 += TC_THREADS * U) {
+        float4 acc[U], bia[U], rvv[U], res[U];
+        bool ok[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int idx = i0 + u * TC_THREADS + (int)threadIdx.x;
+            const int row = idx / C4, c4 = idx - row * C4;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(acc[u].x), "=f"(acc[u].y), "=f"(acc[u].z), "=f"(acc[u].w)
+                         : "r"(stage + (uint32_t)(row * SP + c4 * 4) * 4u));
+            const int m = m_base + row, nn = n0 + c4 * 4;
+            ok[u] = row < rows_valid && m < g.M && nn < g.N;
+            bia[u] = rvv[u] = res[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok[u]) {
+                if (g.bias) bia[u] = ld_f4(g.bias + nn);
+                if (rowvec) rvv[u] = ld_f4(rowvec + (int64_t)(m / g.Lout) * g.rowvec_b_stride + nn);
+                if (GATE == MUGD_GATE_NONE && g.residual) res[u] = ld_f4(g.residual + (int64_t)m * g.ldr + nn);
             }
-            st_f4(g.C + (int64_t)m * g.ldc + nn, make_float4(x[0], x[1], x[2], x[3]));
-        } else {
-            float o0, o1;
-            if (g.gate == MUGD_GATE_GEGLU) { o0 = x[0] * gelu_f(x[1]); o1 = x[2] * gelu_f(x[3]); }
-            else { o0 = x[0] * sigmoid_f(x[1]); o1 = x[2] * sigmoid_f(x[3]); }
-            const int no = nn >> 1;
-            if (g.residual) {
-                const float2 rr = *reinterpret_cast<const float2*>(g.residual + (int64_t)m * g.ldr + no);
-                o0 += rr.x; o1 += rr.y;
-            }
-            *reinterpret_cast<float2*>(g.C + (int64_t)m * g.ldc + no) = make_float2(o0, o1);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (!ok[u]) continue;
+            const int idx = i0 + u * TC_THREADS + (int)threadIdx.x;
+            const int row = idx / C4, c4 = idx - row * C4;
+            tc_finish4<ACT, GATE>(g, acc[u], bia[u], rvv[u], res[u], m_base + row, n0 + c4 * 4);
         }
     }
 }
+
+// single float4 variant used by the split-K reduce kernel
+template <int ACT, int GATE>
+__device__ __forceinline__ void tc_epi4(const mugd_gemm& g, float4 acc, int m, int nn, const float* rowvec) {
+    float4 bia = make_float4(0.f, 0.f, 0.f, 0.f), rvv = bia, res = bia;
+    if (g.bias) bia = ld_f4(g.bias + nn);
+    if (rowvec) rvv = ld_f4(rowvec + (int64_t)(m / g.Lout) * g.rowvec_b_stride + nn);
+    if (GATE == MUGD_GATE_NONE && g.residual) res = ld_f4(g.residual + (int64_t)m * g.ldr + nn);
+    tc_finish4<ACT, GATE>(g, acc, bia, rvv, res, m, nn);
+}
+
+#define TC_DISPATCH_EPI(g, CALL)                                                                      \
+    do {                                                                                              \
+        if ((g).gate == MUGD_GATE_GEGLU) { CALL(MUGD_ACT_NONE, MUGD_GATE_GEGLU); }                    \
+        else if ((g).gate == MUGD_GATE_GLU) { CALL(MUGD_ACT_NONE, MUGD_GATE_GLU); }                   \
+        else if ((g).act == MUGD_ACT_SILU) { CALL(MUGD_ACT_SILU, MUGD_GATE_NONE); }                   \
+        else if ((g).act == MUGD_ACT_GELU) { CALL(MUGD_ACT_GELU, MUGD_GATE_NONE); }                   \
+        else { CALL(MUGD_ACT_NONE, MUGD_GATE_NONE); }                                                 \
+    } while (0)
 
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -216,6 +262,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int it_end = (int)(((long long)p.total_it * (blockIdx.z + 1)) / p.splits);
     const int nit = it_end - it_begin;
 
+    const bool dbg_cta = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+    if (dbg_cta && threadIdx.x == 0) p.dbg[0] = gtimer();
     // ---- one-time setup ------------------------------------------------------------------------------
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -235,6 +283,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    if (dbg_cta && threadIdx.x == 0) p.dbg[1] = gtimer();
 
     if (warp == 0) {
         // ===================================== TMA producer =====================================
@@ -304,69 +353,109 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ===================================== epilogue =========================================
         mbar_wait(bar_accum, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (dbg_cta && ct == 0) p.dbg[2] = gtimer();
         const int q = warp & 3;                                        // TMEM lane quarter this warp may read
         const int r = q * 32 + lane;                                   // tile row == TMEM lane
-        const int m = m_base + r;
-        const bool row_ok = (r < rows_valid) && (m < g.M);
-        const int step = g.step ? *g.step : 0;
-        const float* rowvec = g.rowvec ? g.rowvec + (int64_t)step * g.rowvec_step_stride : nullptr;
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+        // phase 1: TMEM -> registers -> shared (the pipeline buffers are free: every TMA landed, every MMA retired).
+        // Row pitch BN+4 floats keeps the per-row float4 stores and the row-contiguous reads below conflict-free.
+        constexpr int SP = BN + 4;
+        const uint32_t stage = base;
         float v[32];
-        if (p.splits == 1) {
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                tmem_ld32(trow + (uint32_t)c0, v);
-                if (row_ok && n0 + c0 < g.N) tc_epilogue_store<BN>(g, v, m, n0 + c0, rowvec);
-            }
-        } else {
-            const int tile_lin = blockIdx.y * gridDim.x + blockIdx.x;
-            float* wst = p.ws + ((int64_t)tile_lin * p.splits) * (TC_BM * BN);
-            float* mine = wst + (int64_t)blockIdx.z * (TC_BM * BN) + (int64_t)r * BN;
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                tmem_ld32(trow + (uint32_t)c0, v);
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            tmem_ld32(trow + (uint32_t)c0, v);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) st_f4(mine + c0 + j * 4, make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]));
-            }
-            __threadfence();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            __shared__ int s_last;
-            if (ct == 0) {
-                const int prev = atomicAdd(p.counters + tile_lin, 1);
-                s_last = (prev == p.splits - 1) ? 1 : 0;
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (s_last) {
-                __threadfence();
-                if (row_ok) {
-#pragma unroll 1
-                    for (int c0 = 0; c0 < BN; c0 += 32) {
-                        if (n0 + c0 >= g.N) break;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = 0.f;
-                        for (int z = 0; z < p.splits; ++z) {               // fixed order -> deterministic
-                            const float* src = wst + (int64_t)z * (TC_BM * BN) + (int64_t)r * BN + c0;
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const float4 t4 = __ldcg(reinterpret_cast<const float4*>(src + j * 4));
-                                v[j * 4] += t4.x; v[j * 4 + 1] += t4.y; v[j * 4 + 2] += t4.z; v[j * 4 + 3] += t4.w;
-                            }
-                        }
-                        tc_epilogue_store<BN>(g, v, m, n0 + c0, rowvec);
-                    }
-                }
-                if (ct == 0) p.counters[tile_lin] = 0;                      // ready for the next launch / graph replay
-            }
+            for (int j = 0; j < 8; ++j)
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stage + (uint32_t)(r * SP + c0 + j * 4) * 4u), "f"(v[j * 4]),
+                             "f"(v[j * 4 + 1]), "f"(v[j * 4 + 2]), "f"(v[j * 4 + 3]) : "memory");
         }
+        if (dbg_cta && ct == 0) p.dbg[3] = gtimer();
     }
-    // ---- teardown -------------------------------------------------------------------------------------
+    // ---- phase 2 (all 8 warps): consecutive threads take consecutive float4 of a row -> coalesced global traffic.
+    // The accumulator tile is complete in shared memory once the 4 epilogue warps pass this barrier; the producer /
+    // MMA / allocator warps have nothing left to do and join in.
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    {
+        const int step = g.step ? *g.step : 0;
+        const float* rowvec = g.rowvec ? g.rowvec + (int64_t)step * g.rowvec_step_stride : nullptr;
+        const uint32_t stage = base;
+        if (p.splits > 1) {
+            const int tile_lin = blockIdx.y * gridDim.x + blockIdx.x;
+            float* wsp = p.ws + ((int64_t)tile_lin * p.splits + blockIdx.z) * (TC_BM * BN);
+            constexpr int SP = BN + 4;
+            constexpr int C4 = BN / 4;
+            constexpr int U = 8;
+#pragma unroll 1
+            for (int i0 = 0; i0 < TC_BM * C4; i0 += TC_THREADS * U) {
+                float4 acc[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int idx = i0 + u * TC_THREADS + (int)threadIdx.x;
+                    const int row = idx / C4, c4 = idx - row * C4;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(acc[u].x), "=f"(acc[u].y), "=f"(acc[u].z), "=f"(acc[u].w)
+                                 : "r"(stage + (uint32_t)(row * SP + c4 * 4) * 4u));
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) st_f4(wsp + (i0 + u * TC_THREADS + (int)threadIdx.x) * 4, acc[u]);   // [row][BN] dense
+            }
+        } else {
+#define TC_CALL_STORE(A_, G_) tc_store_tile<BN, A_, G_>(g, stage, m_base, n0, rows_valid, rowvec)
+            TC_DISPATCH_EPI(g, TC_CALL_STORE);
+#undef TC_CALL_STORE
+        }
+        if (dbg_cta && threadIdx.x == 0) p.dbg[4] = gtimer();
+    }
+    // ---- teardown (all tcgen05.ld completed before the phase-2 barrier) ----------------------------------
     if (warp == 2) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
     }
 }
+
+// split-K second pass: sum the partial tiles in fixed split order (deterministic) and run the fused epilogue.
+// One thread per (row, 32-column chunk); fully parallel over the GPU and L2-resident.
+template <int BN>
+__global__ void __launch_bounds__(256)
+gemm_tc_reduce_kernel(const TcParams p, int gx, int gy) {
+    const mugd_gemm& g = p.g;
+    constexpr int C4 = BN / 4;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)gx * gy * TC_BM * C4;
+    if (idx >= total) return;
+    const int c4 = (int)(idx % C4);
+    const int r = (int)((idx / C4) % TC_BM);
+    const int tile_lin = (int)(idx / ((long long)C4 * TC_BM));
+    const int bx = tile_lin % gx, by = tile_lin / gx;
+    int b_base, l_base, rows_valid;
+    if (p.Lrows >= TC_BM) {
+        b_base = by / p.tiles_per_sample;
+        l_base = (by % p.tiles_per_sample) * TC_BM;
+        rows_valid = min(TC_BM, p.Lrows - l_base);
+    } else {
+        b_base = by * p.box_b;
+        l_base = 0;
+        rows_valid = min(p.box_b, p.Bs - b_base) * p.Lrows;
+    }
+    const int m = b_base * p.Lrows + l_base + r;
+    const int n = bx * BN + c4 * 4;
+    if (r >= rows_valid || m >= g.M || n >= g.N) return;
+    const float* src = p.ws + ((long long)tile_lin * p.splits) * (TC_BM * BN) + (long long)r * BN + c4 * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int z = 0; z < p.splits; ++z) {                                   // fixed order -> deterministic
+        const float4 t4 = __ldcg(reinterpret_cast<const float4*>(src + (long long)z * (TC_BM * BN)));
+        acc.x += t4.x; acc.y += t4.y; acc.z += t4.z; acc.w += t4.w;
+    }
+    const int step = g.step ? *g.step : 0;
+    const float* rowvec = g.rowvec ? g.rowvec + (int64_t)step * g.rowvec_step_stride : nullptr;
+#define TC_CALL_EPI(A_, G_) tc_epi4<A_, G_>(g, acc, m, n, rowvec)
+    TC_DISPATCH_EPI(g, TC_CALL_EPI);
+#undef TC_CALL_EPI
+}
+
+static long long* g_tc_dbg = nullptr;
 
 // =====================================================================================================
 // host side
@@ -421,10 +510,16 @@ static TcGeometry tc_geometry(const mugd_gemm& g, int sm_count, int forced_split
     const int tiles = t.gx * t.gy;
     if (forced_split > 0) splits = forced_split;
     else if (tiles < sm_count) {
-        splits = (sm_count + tiles - 1) / tiles;
-        const int max_by_k = t.total_it / 4 > 0 ? t.total_it / 4 : 1;     // keep >= 4 k-steps per split
-        if (splits > max_by_k) splits = max_by_k;
-        if (splits > 16) splits = 16;
+        // cost model from the B200 micro-benchmark (tools/bench_gemm.py): a CTA needs ~1 us to fill its pipeline and
+        // ~0.7 us per k-step; splitting adds the workspace round trip and a second (reduce) launch, ~5 us.
+        float best = 1e30f;
+        for (int sp = 1; sp <= 16 && sp <= t.total_it; ++sp) {
+            const int per = (t.total_it + sp - 1) / sp;
+            if (sp > 1 && per < 2) break;
+            const int waves = (tiles * sp + sm_count - 1) / sm_count;
+            const float est = waves * (1.0f + 0.7f * per) + (sp > 1 ? 5.0f : 0.0f);
+            if (est < best - 0.25f) { best = est; splits = sp; }
+        }
     }
     if (splits > t.total_it) splits = t.total_it;
     if (splits < 1) splits = 1;
@@ -444,6 +539,11 @@ static int tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmWhi, const CUt
     dim3 grid(t.gx, t.gy, t.splits);
     gemm_tc_kernel<BN><<<grid, TC_THREADS, TcSmem<BN>::TOTAL, st>>>(tmA, tmWhi, tmWlo, p);
     MUGD_CHECK_CUDA(cudaGetLastError());
+    if (t.splits > 1) {
+        const long long total = (long long)t.gx * t.gy * TC_BM * (BN / 4);
+        gemm_tc_reduce_kernel<BN><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p, t.gx, t.gy);
+        MUGD_CHECK_CUDA(cudaGetLastError());
+    }
     return MUGD_OK;
 }
 
@@ -453,10 +553,9 @@ int launch_gemm_tc(const DeviceInfo& dev, const mugd_gemm& g, cudaStream_t st, i
     MUGD_REQUIRE(enc != nullptr, "gemm_tc: cuTensorMapEncodeTiled not available from the driver");
     const TcGeometry t = tc_geometry(g, dev.sm_count, g.split_k);
     if (t.splits > 1) {
-        MUGD_REQUIRE(g.workspace && g.counters, "gemm_tc: split-K needs workspace and counters");
+        MUGD_REQUIRE(g.workspace, "gemm_tc: split-K needs a workspace");
         MUGD_REQUIRE(g.workspace_bytes >= t.ws_floats * 4, "gemm_tc: workspace too small (%lld < %lld)", (long long)g.workspace_bytes,
                      (long long)t.ws_floats * 4);
-        MUGD_REQUIRE(g.n_counters >= t.gx * t.gy, "gemm_tc: need %d tile counters, have %d", t.gx * t.gy, g.n_counters);
     }
     CUtensorMap tmA, tmWhi, tmWlo;
     {
@@ -493,13 +592,19 @@ int launch_gemm_tc(const DeviceInfo& dev, const mugd_gemm& g, cudaStream_t st, i
     p.box_l = t.box_l;
     p.box_b = t.box_b;
     p.tiles_per_sample = t.tiles_per_sample;
+    p.dbg = g_tc_dbg;
     int rc = (t.BN == 128) ? tc_launch<128>(tmA, tmWhi, tmWlo, p, t, st) : tc_launch<64>(tmA, tmWhi, tmWlo, p, t, st);
     if (rc != MUGD_OK) return rc;
-    if (launches) *launches += 1;
+    if (launches) *launches += (t.splits > 1) ? 2 : 1;
     return MUGD_OK;
 }
 
 }  // namespace mugd
+
+extern "C" int mugd_debug_set_tc_timing(long long* device_buf4) {
+    mugd::g_tc_dbg = device_buf4;
+    return MUGD_OK;
+}
 
 extern "C" int mugd_gemm_tc_query(mugd_handle*, const mugd_gemm* g, int32_t sm_count, int32_t* supported, int32_t* splits,
                                   int64_t* workspace_bytes, int32_t* n_tiles) {

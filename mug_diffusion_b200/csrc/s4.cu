@@ -24,58 +24,69 @@ constexpr int S4_CH = 32;       // channels per CTA
 constexpr int S4_WARPS = 8;
 constexpr int S4_R = 8;         // outputs per block
 
+// KS: kernel taps staged in shared memory next to u (2 * L * 128 B); otherwise streamed through L1 (long L).
+template <bool KS>
 __global__ void __launch_bounds__(S4_CH * S4_WARPS)
 s4conv_kernel(const mugd_s4conv s, int nsplit) {
-    extern __shared__ float us[];          // [L][32]
+    extern __shared__ float smem_s4[];     // us[L][32] then ks[L][32]
+    float* us = smem_s4;
+    float* ks = smem_s4 + (size_t)s.L * S4_CH;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int h = blockIdx.x * S4_CH + lane;
     const int b = blockIdx.y;
     const int L = s.L;
     const float* ub = s.u + (int64_t)b * L * s.ldu + blockIdx.x * S4_CH;
-    for (int l = warp; l < L; l += S4_WARPS) us[l * S4_CH + lane] = ub[(int64_t)l * s.ldu + lane];
+    const float* Kh = s.Kt + h;            // tap j at Kh[j*H]
+    for (int l = warp; l < L; l += S4_WARPS) {
+        us[l * S4_CH + lane] = ub[(int64_t)l * s.ldu + lane];
+        if (KS) ks[l * S4_CH + lane] = Kh[(int64_t)l * s.H];
+    }
     __syncthreads();
 
-    const float* Kh = s.Kt + h;            // tap j at Kh[j*H]
     const float Dh = s.D[h];
     float* yb = s.y + (int64_t)b * L * s.ldy + h;
     const int nblk = (L + S4_R - 1) / S4_R;
+    const int npairs = (nblk + 1) / 2;
     const int worker = blockIdx.z * S4_WARPS + warp;
     const int nworkers = nsplit * S4_WARPS;
-    // heavy (late) blocks first so the tail of the schedule is made of light blocks
-    for (int bi = nblk - 1 - worker; bi >= 0; bi -= nworkers) {
-        const int l0 = bi * S4_R;
-        float acc[S4_R];
+    // the cost of block bi grows linearly with bi (causal): pairing block p with block nblk-1-p gives every
+    // worker the same amount of work
+    for (int p = worker; p < npairs; p += nworkers) {
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            const int bi = half == 0 ? (nblk - 1 - p) : p;
+            if (half == 1 && bi == nblk - 1 - p) break;
+            const int l0 = bi * S4_R;
+            float acc[S4_R];
 #pragma unroll
-        for (int r = 0; r < S4_R; ++r) acc[r] = 0.f;
-        float win[2 * S4_R];               // win[i] = u[l0 - jc - 8 + i]
-#pragma unroll
-        for (int r = 0; r < S4_R; ++r) {
-            const int li = l0 + r;
-            win[S4_R + r] = (li < L) ? us[li * S4_CH + lane] : 0.f;
-        }
-        for (int jc = 0; jc < l0 + S4_R; jc += S4_R) {
+            for (int r = 0; r < S4_R; ++r) acc[r] = 0.f;
+            float win[2 * S4_R];               // win[i] = u[l0 - jc - 8 + i]
 #pragma unroll
             for (int r = 0; r < S4_R; ++r) {
-                const int li = l0 - jc - S4_R + r;
-                win[r] = (li >= 0) ? us[li * S4_CH + lane] : 0.f;
+                const int li = l0 + r;
+                win[S4_R + r] = (li < L) ? us[li * S4_CH + lane] : 0.f;
             }
-            float kk[S4_R];
+            for (int jc = 0; jc < l0 + S4_R; jc += S4_R) {
+                float kk[S4_R];
 #pragma unroll
-            for (int jj = 0; jj < S4_R; ++jj) {
-                const int j = jc + jj;
-                kk[jj] = (j < L) ? __ldg(Kh + (int64_t)j * s.H) : 0.f;
+                for (int r = 0; r < S4_R; ++r) {
+                    const int li = l0 - jc - S4_R + r;
+                    win[r] = (li >= 0) ? us[li * S4_CH + lane] : 0.f;
+                    const int j = jc + r;
+                    kk[r] = (j < L) ? (KS ? ks[j * S4_CH + lane] : __ldg(Kh + (int64_t)j * s.H)) : 0.f;
+                }
+#pragma unroll
+                for (int jj = 0; jj < S4_R; ++jj)
+#pragma unroll
+                    for (int r = 0; r < S4_R; ++r) acc[r] = fmaf(kk[jj], win[S4_R + r - jj], acc[r]);
+#pragma unroll
+                for (int r = 0; r < S4_R; ++r) win[S4_R + r] = win[r];
             }
 #pragma unroll
-            for (int jj = 0; jj < S4_R; ++jj)
-#pragma unroll
-                for (int r = 0; r < S4_R; ++r) acc[r] = fmaf(kk[jj], win[S4_R + r - jj], acc[r]);
-#pragma unroll
-            for (int r = 0; r < S4_R; ++r) win[S4_R + r] = win[r];
-        }
-#pragma unroll
-        for (int r = 0; r < S4_R; ++r) {
-            const int li = l0 + r;
-            if (li < L) yb[(int64_t)li * s.ldy] = gelu_f(acc[r] + Dh * us[li * S4_CH + lane]);
+            for (int r = 0; r < S4_R; ++r) {
+                const int li = l0 + r;
+                if (li < L) yb[(int64_t)li * s.ldy] = gelu_f(acc[r] + Dh * us[li * S4_CH + lane]);
+            }
         }
     }
 }
@@ -83,19 +94,22 @@ s4conv_kernel(const mugd_s4conv s, int nsplit) {
 int launch_s4conv(const DeviceInfo& dev, const mugd_s4conv& s, cudaStream_t st, int* launches) {
     MUGD_REQUIRE(s.B > 0 && s.L > 0 && s.H > 0 && s.H % S4_CH == 0, "s4conv: H=%d must be a positive multiple of %d", s.H, S4_CH);
     MUGD_REQUIRE(s.ldu >= s.H && s.ldy >= s.H, "s4conv: ld < H");
-    const size_t smem = (size_t)s.L * S4_CH * sizeof(float);
-    MUGD_REQUIRE((int)smem <= dev.max_smem_optin, "s4conv: L=%d needs %zu B of shared memory (max %d)", s.L, smem, dev.max_smem_optin);
-    static int configured = 0;
-    if (configured < (int)smem) {
-        MUGD_CHECK_CUDA(cudaFuncSetAttribute(s4conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.max_smem_optin));
-        configured = dev.max_smem_optin;
+    const size_t smem_u = (size_t)s.L * S4_CH * sizeof(float);
+    MUGD_REQUIRE((int)smem_u <= dev.max_smem_optin, "s4conv: L=%d needs %zu B of shared memory (max %d)", s.L, smem_u, dev.max_smem_optin);
+    const bool ks = 2 * smem_u <= (size_t)dev.max_smem_optin;
+    static bool configured = false;
+    if (!configured) {
+        MUGD_CHECK_CUDA(cudaFuncSetAttribute(s4conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.max_smem_optin));
+        MUGD_CHECK_CUDA(cudaFuncSetAttribute(s4conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.max_smem_optin));
+        configured = true;
     }
     const int base = (s.H / S4_CH) * s.B;
+    const int npairs = ((s.L + S4_R - 1) / S4_R + 1) / 2;
     int nsplit = 1;
-    const int nblk = (s.L + S4_R - 1) / S4_R;
-    while (base * nsplit < 2 * dev.sm_count && nsplit * 2 * S4_WARPS <= nblk && nsplit < 16) nsplit *= 2;
+    while (base * nsplit < 2 * dev.sm_count && nsplit * 2 * S4_WARPS <= npairs && nsplit < 16) nsplit *= 2;
     dim3 grid(s.H / S4_CH, s.B, nsplit);
-    s4conv_kernel<<<grid, S4_CH * S4_WARPS, smem, st>>>(s, nsplit);
+    if (ks) s4conv_kernel<true><<<grid, S4_CH * S4_WARPS, 2 * smem_u, st>>>(s, nsplit);
+    else s4conv_kernel<false><<<grid, S4_CH * S4_WARPS, smem_u, st>>>(s, nsplit);
     MUGD_CHECK_CUDA(cudaGetLastError());
     if (launches) *launches += 1;
     return MUGD_OK;
