@@ -158,6 +158,7 @@ int  mugd_create(int device, mugd_handle** out);           /* MUGD_ERR_NO_DEVICE
 void mugd_destroy(mugd_handle* h);
 int  mugd_device_info(mugd_handle* h, int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
 int  mugd_set_gemm_impl(mugd_handle* h, int impl);         /* default for ops with impl == AUTO         */
+int  mugd_set_pdl(int enabled);                            /* programmatic dependent launch (default off) */
 
 /* ---- single op (parity tests call every kernel through this) ---------------------------------- */
 int  mugd_op_run(mugd_handle* h, const mugd_op* op, void* stream);

@@ -9,6 +9,7 @@
 namespace mugd {
 
 static thread_local char g_err[1024] = "";
+bool g_use_pdl = false;   // measured on B200: 5.12 ms/step with PDL edges vs 4.46 without (L512_B4_cfg5) -> off by default
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -102,6 +103,11 @@ int mugd_set_gemm_impl(mugd_handle* h, int impl) {
     MUGD_REQUIRE(h, "null handle");
     MUGD_REQUIRE(impl == MUGD_GEMM_SIMT || impl == MUGD_GEMM_TC, "set_gemm_impl: %d", impl);
     h->default_gemm_impl = impl;
+    return MUGD_OK;
+}
+
+int mugd_set_pdl(int enabled) {
+    g_use_pdl = enabled != 0;
     return MUGD_OK;
 }
 

@@ -46,6 +46,8 @@ attention_kernel(const mugd_attention a) {
     const int P = a.pos_max, NT = 2 * P + 1;
     float* cg = rel + NT;
 
+    pdl_trigger();
+    pdl_wait();
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int b = blockIdx.z, h = blockIdx.y;
     const int q0 = blockIdx.x * AT_BQ;
@@ -174,8 +176,7 @@ static int attention_launch(const mugd_attention& a, cudaStream_t st) {
         configured = bytes;
     }
     dim3 grid((a.Lq + AT_BQ - 1) / AT_BQ, a.H, a.B);
-    attention_kernel<D><<<grid, AT_THREADS, bytes, st>>>(a);
-    MUGD_CHECK_CUDA(cudaGetLastError());
+    MUGD_CHECK_CUDA(launch_k(attention_kernel<D>, grid, dim3(AT_THREADS), bytes, st, a));
     return MUGD_OK;
 }
 

@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <utility>
 
 #include "../../include/mugd.h"
 
@@ -54,7 +55,31 @@ int launch_step_advance(const DeviceInfo& dev, const mugd_step_advance& a, cudaS
 int launch_gemm_tc(const DeviceInfo& dev, const mugd_gemm& g, cudaStream_t st, int* launches);
 bool gemm_tc_supported(const mugd_gemm& g);
 
+// Programmatic dependent launch (PDL): every hot-path kernel is launched with the programmatic-stream-serialization
+// attribute, signals `launch_dependents` at entry and executes `griddepcontrol.wait` before its first global-memory
+// access.  The next kernel's launch latency and prologue (block scheduling, barrier init, TMEM allocation,
+// tensor-map fetch) then overlap the tail of the current one; data hazards are unchanged because the wait
+// only returns when the prerequisite grid has completed and flushed.
+extern bool g_use_pdl;
+
 #ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_use_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- device helpers ---------------------------------------------------------------------------
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }

@@ -12,6 +12,8 @@ namespace mugd {
 // ATen ops (no FMA contraction), so given identical eps the update is bit-identical.
 __global__ void __launch_bounds__(256)
 ddim_update_kernel(const mugd_ddim_update d) {
+    pdl_trigger();
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= d.n) return;
     const int step = d.step ? *d.step : 0;
@@ -38,8 +40,7 @@ ddim_update_kernel(const mugd_ddim_update d) {
 
 int launch_ddim_update(const DeviceInfo&, const mugd_ddim_update& d, cudaStream_t st, int* launches) {
     MUGD_REQUIRE(d.n > 0 && d.S > 0 && d.x && d.eps && d.coef, "ddim_update: bad arguments");
-    ddim_update_kernel<<<(d.n + 255) / 256, 256, 0, st>>>(d);
-    MUGD_CHECK_CUDA(cudaGetLastError());
+    MUGD_CHECK_CUDA(launch_k(ddim_update_kernel, dim3((d.n + 255) / 256), dim3(256), 0, st, d));
     if (launches) *launches += 1;
     return MUGD_OK;
 }
@@ -48,6 +49,8 @@ int launch_ddim_update(const DeviceInfo&, const mugd_ddim_update& d, cudaStream_
 __global__ void __launch_bounds__(256)
 transpose_kernel(const mugd_transpose t) {
     __shared__ float tile[32][33];
+    pdl_trigger();
+    pdl_wait();
     const int b = blockIdx.z;
     const int c0 = blockIdx.y * 32, l0 = blockIdx.x * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
@@ -88,14 +91,15 @@ int launch_transpose(const DeviceInfo&, const mugd_transpose& t, cudaStream_t st
     if (t.to_nlc) MUGD_REQUIRE(t.ldo >= t.C, "transpose: ldo < C");
     else MUGD_REQUIRE(t.ldi >= t.C, "transpose: ldi < C");
     dim3 grid((t.L + 31) / 32, (t.C + 31) / 32, t.B);
-    transpose_kernel<<<grid, 256, 0, st>>>(t);
-    MUGD_CHECK_CUDA(cudaGetLastError());
+    MUGD_CHECK_CUDA(launch_k(transpose_kernel, grid, dim3(256), 0, st, t));
     if (launches) *launches += 1;
     return MUGD_OK;
 }
 
 __global__ void __launch_bounds__(256)
 copy2d_kernel(const mugd_copy2d c) {
+    pdl_trigger();
+    pdl_wait();
     const int q = c.cols >> 2;
     const int64_t total = (int64_t)c.rows * q;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -111,19 +115,21 @@ int launch_copy2d(const DeviceInfo& dev, const mugd_copy2d& c, cudaStream_t st, 
     const int64_t total = (int64_t)c.rows * (c.cols / 4);
     int blocks = (int)((total + 255) / 256);
     if (blocks > dev.sm_count * 8) blocks = dev.sm_count * 8;
-    copy2d_kernel<<<blocks, 256, 0, st>>>(c);
-    MUGD_CHECK_CUDA(cudaGetLastError());
+    MUGD_CHECK_CUDA(launch_k(copy2d_kernel, dim3(blocks), dim3(256), 0, st, c));
     if (launches) *launches += 1;
     return MUGD_OK;
 }
 
-__global__ void step_advance_kernel(int32_t* step) { *step += 1; }
+__global__ void step_advance_kernel(int32_t* step) {
+    pdl_trigger();
+    pdl_wait();
+    *step += 1;
+}
 __global__ void fill_i32_kernel(int32_t* p, int32_t v) { *p = v; }
 
 int launch_step_advance(const DeviceInfo&, const mugd_step_advance& a, cudaStream_t st, int* launches) {
     MUGD_REQUIRE(a.step, "step_advance: null counter");
-    step_advance_kernel<<<1, 1, 0, st>>>(a.step);
-    MUGD_CHECK_CUDA(cudaGetLastError());
+    MUGD_CHECK_CUDA(launch_k(step_advance_kernel, dim3(1), dim3(1), 0, st, a.step));
     if (launches) *launches += 1;
     return MUGD_OK;
 }

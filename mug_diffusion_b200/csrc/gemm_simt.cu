@@ -46,6 +46,8 @@ gemm_simt_kernel(const GemmParams p) {
     __shared__ __align__(16) float As[2][SG_BK][SA];
     __shared__ __align__(16) float Ws[2][SG_BK][SW];
 
+    pdl_trigger();
+    pdl_wait();
     const mugd_gemm& g = p.g;
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;
@@ -241,10 +243,10 @@ int launch_gemm(const DeviceInfo& dev, const mugd_gemm& g, int default_impl, cud
     const long tiles128 = (long)((g.M + 127) / 128) * ((g.N + 127) / 128);
     if (tiles128 >= 2L * dev.sm_count) {
         dim3 grid((g.N + 127) / 128, (g.M + 127) / 128);
-        gemm_simt_kernel<2, 2><<<grid, SG_THREADS, 0, st>>>(p);
+        MUGD_CHECK_CUDA(launch_k(gemm_simt_kernel<2, 2>, grid, dim3(SG_THREADS), 0, st, p));
     } else {
         dim3 grid((g.N + 63) / 64, (g.M + 63) / 64);
-        gemm_simt_kernel<1, 1><<<grid, SG_THREADS, 0, st>>>(p);
+        MUGD_CHECK_CUDA(launch_k(gemm_simt_kernel<1, 1>, grid, dim3(SG_THREADS), 0, st, p));
     }
     MUGD_CHECK_CUDA(cudaGetLastError());
     if (launches) *launches += 1;

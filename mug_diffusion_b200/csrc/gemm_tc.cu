@@ -262,8 +262,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int it_end = (int)(((long long)p.total_it * (blockIdx.z + 1)) / p.splits);
     const int nit = it_end - it_begin;
 
+    pdl_trigger();                      // let the next kernel's launch + prologue overlap this one
     const bool dbg_cta = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
-    if (dbg_cta && threadIdx.x == 0) p.dbg[0] = gtimer();
     // ---- one-time setup ------------------------------------------------------------------------------
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -283,7 +283,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-    if (dbg_cta && threadIdx.x == 0) p.dbg[1] = gtimer();
+    // barriers, TMEM and descriptors are set up: from here on global memory written by the previous kernel is touched
+    pdl_wait();
+    if (dbg_cta && threadIdx.x == 0) { p.dbg[0] = gtimer(); p.dbg[1] = p.dbg[0]; }
 
     if (warp == 0) {
         // ===================================== TMA producer =====================================
@@ -419,6 +421,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 template <int BN>
 __global__ void __launch_bounds__(256)
 gemm_tc_reduce_kernel(const TcParams p, int gx, int gy) {
+    pdl_trigger();
+    pdl_wait();
     const mugd_gemm& g = p.g;
     constexpr int C4 = BN / 4;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -516,6 +520,7 @@ static TcGeometry tc_geometry(const mugd_gemm& g, int sm_count, int forced_split
         for (int sp = 1; sp <= 16 && sp <= t.total_it; ++sp) {
             const int per = (t.total_it + sp - 1) / sp;
             if (sp > 1 && per < 2) break;
+            if (sp > 1 && tiles * sp > 2 * sm_count) break;              // bounds the workspace: < 2*SMs partial tiles
             const int waves = (tiles * sp + sm_count - 1) / sm_count;
             const float est = waves * (1.0f + 0.7f * per) + (sp > 1 ? 5.0f : 0.0f);
             if (est < best - 0.25f) { best = est; splits = sp; }
@@ -537,12 +542,10 @@ static int tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmWhi, const CUt
         configured = true;
     }
     dim3 grid(t.gx, t.gy, t.splits);
-    gemm_tc_kernel<BN><<<grid, TC_THREADS, TcSmem<BN>::TOTAL, st>>>(tmA, tmWhi, tmWlo, p);
-    MUGD_CHECK_CUDA(cudaGetLastError());
+    MUGD_CHECK_CUDA(launch_k(gemm_tc_kernel<BN>, grid, dim3(TC_THREADS), TcSmem<BN>::TOTAL, st, tmA, tmWhi, tmWlo, p));
     if (t.splits > 1) {
         const long long total = (long long)t.gx * t.gy * TC_BM * (BN / 4);
-        gemm_tc_reduce_kernel<BN><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p, t.gx, t.gy);
-        MUGD_CHECK_CUDA(cudaGetLastError());
+        MUGD_CHECK_CUDA(launch_k(gemm_tc_reduce_kernel<BN>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, p, t.gx, t.gy));
     }
     return MUGD_OK;
 }

@@ -17,6 +17,8 @@ __global__ void __launch_bounds__(GN_THREADS)
 groupnorm_silu_kernel(const float* __restrict__ x, int64_t ldx, float* __restrict__ y, int64_t ldy,
                       const float* __restrict__ gamma, const float* __restrict__ beta,
                       int L, int C, int G, float eps, int silu) {
+    pdl_trigger();
+    pdl_wait();
     const int g = blockIdx.x, b = blockIdx.y;
     const int cg = C / G;
     const int q = cg >> 2;                 // float4 per row of this group
@@ -75,8 +77,8 @@ int launch_groupnorm(const DeviceInfo&, const mugd_groupnorm& g, cudaStream_t st
                  "groupnorm: operands must be 16-byte aligned with ld %% 4 == 0");
     MUGD_REQUIRE(g.ldx >= g.C && g.ldy >= g.C, "groupnorm: leading dimension smaller than C");
     dim3 grid(g.G, g.B);
-    groupnorm_silu_kernel<<<grid, GN_THREADS, 0, st>>>(g.x, g.ldx, g.y, g.ldy, g.gamma, g.beta, g.L, g.C, g.G, g.eps, g.silu);
-    MUGD_CHECK_CUDA(cudaGetLastError());
+    MUGD_CHECK_CUDA(launch_k(groupnorm_silu_kernel, grid, dim3(GN_THREADS), 0, st, g.x, g.ldx, g.y, g.ldy, g.gamma, g.beta, g.L, g.C, g.G,
+                             g.eps, g.silu));
     if (launches) *launches += 1;
     return MUGD_OK;
 }
@@ -88,6 +90,8 @@ constexpr int LN_MAXQ = 8;   // float4 per lane
 __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_kernel(const float* __restrict__ x, int64_t ldx, float* __restrict__ y, int64_t ldy,
                  const float* __restrict__ gamma, const float* __restrict__ beta, int rows, int C, float eps) {
+    pdl_trigger();
+    pdl_wait();
     const int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
@@ -138,8 +142,8 @@ int launch_layernorm(const DeviceInfo&, const mugd_layernorm& g, cudaStream_t st
     MUGD_REQUIRE(g.ldx % 4 == 0 && g.ldy % 4 == 0 && aligned16(g.x) && aligned16(g.y) && aligned16(g.gamma) && aligned16(g.beta),
                  "layernorm: operands must be 16-byte aligned with ld %% 4 == 0");
     const int blocks = (g.rows + LN_WARPS - 1) / LN_WARPS;
-    layernorm_kernel<<<blocks, LN_WARPS * 32, 0, st>>>(g.x, g.ldx, g.y, g.ldy, g.gamma, g.beta, g.rows, g.C, g.eps);
-    MUGD_CHECK_CUDA(cudaGetLastError());
+    MUGD_CHECK_CUDA(launch_k(layernorm_kernel, dim3(blocks), dim3(LN_WARPS * 32), 0, st, g.x, g.ldx, g.y, g.ldy, g.gamma, g.beta, g.rows,
+                             g.C, g.eps));
     if (launches) *launches += 1;
     return MUGD_OK;
 }

@@ -31,6 +31,8 @@ s4conv_kernel(const mugd_s4conv s, int nsplit) {
     extern __shared__ float smem_s4[];     // us[L][32] then ks[L][32]
     float* us = smem_s4;
     float* ks = smem_s4 + (size_t)s.L * S4_CH;
+    pdl_trigger();
+    pdl_wait();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int h = blockIdx.x * S4_CH + lane;
     const int b = blockIdx.y;
@@ -108,9 +110,8 @@ int launch_s4conv(const DeviceInfo& dev, const mugd_s4conv& s, cudaStream_t st, 
     int nsplit = 1;
     while (base * nsplit < 2 * dev.sm_count && nsplit * 2 * S4_WARPS <= npairs && nsplit < 16) nsplit *= 2;
     dim3 grid(s.H / S4_CH, s.B, nsplit);
-    if (ks) s4conv_kernel<true><<<grid, S4_CH * S4_WARPS, 2 * smem_u, st>>>(s, nsplit);
-    else s4conv_kernel<false><<<grid, S4_CH * S4_WARPS, smem_u, st>>>(s, nsplit);
-    MUGD_CHECK_CUDA(cudaGetLastError());
+    if (ks) MUGD_CHECK_CUDA(launch_k(s4conv_kernel<true>, grid, dim3(S4_CH * S4_WARPS), 2 * smem_u, st, s, nsplit));
+    else MUGD_CHECK_CUDA(launch_k(s4conv_kernel<false>, grid, dim3(S4_CH * S4_WARPS), smem_u, st, s, nsplit));
     if (launches) *launches += 1;
     return MUGD_OK;
 }

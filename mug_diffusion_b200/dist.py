@@ -50,12 +50,18 @@ def broadcast_blob(state_dict: Optional[Dict[str, torch.Tensor]], cfg: ModelConf
 
 
 def gather_batch(local: torch.Tensor, sizes: Sequence[int], dst: int = 0) -> Optional[torch.Tensor]:
-    """Optional final gather of per-rank results (e.g. logits [b_r,16,8L]) onto ``dst``."""
+    """Optional final gather of per-rank results (e.g. logits [b_r,16,8L]) onto ``dst``.  Shards may differ by one
+    sample, collectives want equal shapes: pad to the largest shard, gather, trim."""
     world = dist.get_world_size()
     rank = dist.get_rank()
+    mx = max(sizes)
+    padded = local.contiguous()
+    if padded.shape[0] < mx:
+        pad = torch.zeros((mx - padded.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        padded = torch.cat([padded, pad], dim=0)
     if rank == dst:
-        bufs = [torch.empty((sizes[r],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device) for r in range(world)]
-        dist.gather(local.contiguous(), bufs, dst=dst)
-        return torch.cat(bufs, dim=0)
-    dist.gather(local.contiguous(), None, dst=dst)
+        bufs = [torch.empty_like(padded) for _ in range(world)]
+        dist.gather(padded, bufs, dst=dst)
+        return torch.cat([bufs[r][:sizes[r]] for r in range(world)], dim=0)
+    dist.gather(padded, None, dst=dst)
     return None

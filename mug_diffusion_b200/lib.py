@@ -132,6 +132,7 @@ def load() -> C.CDLL:
     lib.mugd_s4_kernel_gen.argtypes = [C.c_void_p] + [C.c_void_p] * 7 + [C.c_int32] * 4 + [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     lib.mugd_gemm_tc_query.argtypes = [C.c_void_p, C.POINTER(Gemm), C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                        C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
+    lib.mugd_set_pdl.argtypes = [C.c_int]
     lib.mugd_debug_set_tc_timing.argtypes = [C.c_void_p]
     lib.mugd_fill_i32.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
     lib.mugd_abi_sizes.argtypes = [C.POINTER(C.c_int32), C.c_int32]
@@ -142,6 +143,8 @@ def load() -> C.CDLL:
     mine = [C.sizeof(t) for t in (Op, Gemm, GroupNorm, LayerNorm, Attention, S4Conv, DdimUpdate, Transpose, Copy2D)]
     if list(sizes) != mine:
         raise MugdError(f"struct layout mismatch: C {list(sizes)} vs ctypes {mine}")
+    if os.environ.get("MUGD_PDL", "0") == "1":          # A/B switch for programmatic dependent launch (default off)
+        lib.mugd_set_pdl(1)
     _lib = lib
     return lib
 
@@ -158,5 +161,5 @@ def check(rc: int, what: str = ""):
 EXPORTED_SYMBOLS = [
     "mugd_abi_version", "mugd_last_error", "mugd_create", "mugd_destroy", "mugd_device_info", "mugd_set_gemm_impl",
     "mugd_op_run", "mugd_plan_create", "mugd_plan_run", "mugd_plan_capture", "mugd_plan_replay",
-    "mugd_plan_launch_count", "mugd_plan_destroy", "mugd_s4_kernel_gen", "mugd_fill_i32", "mugd_abi_sizes", "mugd_gemm_tc_query", "mugd_debug_set_tc_timing",
+    "mugd_plan_launch_count", "mugd_plan_destroy", "mugd_s4_kernel_gen", "mugd_fill_i32", "mugd_abi_sizes", "mugd_gemm_tc_query", "mugd_set_pdl", "mugd_debug_set_tc_timing",
 ]
