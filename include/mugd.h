@@ -191,6 +191,10 @@ int  mugd_s4_kernel_gen(mugd_handle* h,
 int  mugd_gemm_tc_query(mugd_handle* h, const mugd_gemm* g, int32_t sm_count, int32_t* supported, int32_t* splits,
                         int64_t* workspace_bytes, int32_t* n_tiles);
 
+/* split-K reduction of the tensor-core GEMM: 0 (default) = partial tiles through the workspace + a reduce kernel;
+ * 1 = the splits of a tile run as one thread-block cluster and reduce through distributed shared memory (slower on B200) */
+int  mugd_set_tc_cluster_reduce(int enabled);
+
 /* debugging aid: when set (device pointer to 8 x int64), CTA (0,0,0) of every tensor-core GEMM launch writes
  * %globaltimer stamps {kernel entry, setup done, accumulator ready, tile staged in smem, epilogue done}; pass NULL to disable */
 int  mugd_debug_set_tc_timing(long long* device_buf4);

@@ -77,7 +77,14 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
     cfg.numAttrs = g_use_pdl ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
-__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// Early trigger (dependents become resident while this grid still runs) measured SLOWER on B200 for this launch
+// mix (5.12 vs 4.46 ms/step); without it the trigger is implicit at grid completion and PDL only overlaps the
+// dependent's launch with this grid's memory flush.  Kept behind a macro for experiments.
+__device__ __forceinline__ void pdl_trigger() {
+#ifdef MUGD_PDL_EARLY_TRIGGER
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ---- device helpers ---------------------------------------------------------------------------

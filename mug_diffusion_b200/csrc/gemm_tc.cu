@@ -45,6 +45,7 @@ struct TcParams {
     int32_t Lrows, Bs;        // row structure of the A tensor map (Lrows = rows per sample, Bs samples)
     int32_t box_l, box_b;     // TMA box: box_l rows of box_b consecutive samples (box_l*box_b <= 128)
     int32_t tiles_per_sample; // when Lrows >= 128
+    int32_t cluster;          // split-K CTAs of a tile form a thread-block cluster and reduce through DSMEM
     long long* dbg;           // optional: CTA (0,0,0) writes globaltimer stamps {entry, setup done, accumulator ready, tile staged, epilogue done}
 };
 
@@ -383,7 +384,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int step = g.step ? *g.step : 0;
         const float* rowvec = g.rowvec ? g.rowvec + (int64_t)step * g.rowvec_step_stride : nullptr;
         const uint32_t stage = base;
-        if (p.splits > 1) {
+        if (p.splits > 1 && p.cluster) {
+            // ---- split-K reduction through distributed shared memory: the `splits` CTAs of this tile are one cluster
+            // (1,1,splits).  Every CTA owns a band of rows, sums that band over all peers' staged tiles in rank order
+            // (deterministic), finishes it with the fused epilogue.  No workspace round trip, no second launch.
+            asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+            constexpr int SP = BN + 4;
+            constexpr int C4 = BN / 4;
+            const int rows_per = (TC_BM + p.splits - 1) / p.splits;
+            const int r0 = (int)blockIdx.z * rows_per;
+            const int r1 = min(TC_BM, r0 + rows_per);
+            const int n4 = max(0, r1 - r0) * C4;
+            for (int i = (int)threadIdx.x; i < n4; i += TC_THREADS) {
+                const int row = r0 + i / C4, c4 = i % C4;
+                const uint32_t laddr = stage + (uint32_t)(row * SP + c4 * 4) * 4u;
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+                for (int z = 0; z < p.splits; ++z) {
+                    uint32_t raddr;
+                    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(laddr), "r"(z));
+                    float4 t4;
+                    asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t4.x), "=f"(t4.y), "=f"(t4.z), "=f"(t4.w) : "r"(raddr));
+                    acc.x += t4.x; acc.y += t4.y; acc.z += t4.z; acc.w += t4.w;
+                }
+                const int m = m_base + row, nn = n0 + c4 * 4;
+                if (row < rows_valid && m < g.M && nn < g.N) {
+#define TC_CALL_EPI(A_, G_) tc_epi4<A_, G_>(g, acc, m, nn, rowvec)
+                    TC_DISPATCH_EPI(g, TC_CALL_EPI);
+#undef TC_CALL_EPI
+                }
+            }
+            // peers may still be reading this CTA's tile: leave together
+            asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+        } else if (p.splits > 1) {
             const int tile_lin = blockIdx.y * gridDim.x + blockIdx.x;
             float* wsp = p.ws + ((int64_t)tile_lin * p.splits + blockIdx.z) * (TC_BM * BN);
             constexpr int SP = BN + 4;
@@ -460,6 +493,10 @@ gemm_tc_reduce_kernel(const TcParams p, int gx, int gy) {
 }
 
 static long long* g_tc_dbg = nullptr;
+// Split-K reduction through a thread-block cluster + DSMEM instead of workspace + reduce kernel.  Works (tests pass)
+// but measured slower on B200: clusters of 197 KB-smem CTAs schedule poorly (8 co-resident SMs of one GPC) and DSMEM
+// reads cost ~4 us per tile: GEMM family 4.50 ms vs 3.38 ms per step -> off by default, kept for experiments.
+static bool g_tc_cluster = false;
 
 // =====================================================================================================
 // host side
@@ -517,12 +554,13 @@ static TcGeometry tc_geometry(const mugd_gemm& g, int sm_count, int forced_split
         // cost model from the B200 micro-benchmark (tools/bench_gemm.py): a CTA needs ~1 us to fill its pipeline and
         // ~0.7 us per k-step; splitting adds the workspace round trip and a second (reduce) launch, ~5 us.
         float best = 1e30f;
-        for (int sp = 1; sp <= 16 && sp <= t.total_it; ++sp) {
+        const int sp_max = g_tc_cluster ? 8 : 16;
+        for (int sp = 1; sp <= sp_max && sp <= t.total_it; ++sp) {
             const int per = (t.total_it + sp - 1) / sp;
             if (sp > 1 && per < 2) break;
             if (sp > 1 && tiles * sp > 2 * sm_count) break;              // bounds the workspace: < 2*SMs partial tiles
             const int waves = (tiles * sp + sm_count - 1) / sm_count;
-            const float est = waves * (1.0f + 0.7f * per) + (sp > 1 ? 5.0f : 0.0f);
+            const float est = waves * (1.0f + 0.7f * per) + (sp > 1 ? (g_tc_cluster ? 2.0f : 5.0f) : 0.0f);
             if (est < best - 0.25f) { best = est; splits = sp; }
         }
     }
@@ -542,6 +580,24 @@ static int tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmWhi, const CUt
         configured = true;
     }
     dim3 grid(t.gx, t.gy, t.splits);
+    if (p.cluster && t.splits > 1) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid;
+        cfg.blockDim = dim3(TC_THREADS);
+        cfg.dynamicSmemBytes = TcSmem<BN>::TOTAL;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 1;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = (unsigned)t.splits;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = g_use_pdl ? 2 : 1;
+        MUGD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN>, tmA, tmWhi, tmWlo, p));
+        return MUGD_OK;
+    }
     MUGD_CHECK_CUDA(launch_k(gemm_tc_kernel<BN>, grid, dim3(TC_THREADS), TcSmem<BN>::TOTAL, st, tmA, tmWhi, tmWlo, p));
     if (t.splits > 1) {
         const long long total = (long long)t.gx * t.gy * TC_BM * (BN / 4);
@@ -555,7 +611,8 @@ int launch_gemm_tc(const DeviceInfo& dev, const mugd_gemm& g, cudaStream_t st, i
     EncodeTiledFn enc = get_encode();
     MUGD_REQUIRE(enc != nullptr, "gemm_tc: cuTensorMapEncodeTiled not available from the driver");
     const TcGeometry t = tc_geometry(g, dev.sm_count, g.split_k);
-    if (t.splits > 1) {
+    const bool use_cluster = g_tc_cluster && t.splits > 1 && t.splits <= 8;
+    if (t.splits > 1 && !use_cluster) {
         MUGD_REQUIRE(g.workspace, "gemm_tc: split-K needs a workspace");
         MUGD_REQUIRE(g.workspace_bytes >= t.ws_floats * 4, "gemm_tc: workspace too small (%lld < %lld)", (long long)g.workspace_bytes,
                      (long long)t.ws_floats * 4);
@@ -596,13 +653,19 @@ int launch_gemm_tc(const DeviceInfo& dev, const mugd_gemm& g, cudaStream_t st, i
     p.box_b = t.box_b;
     p.tiles_per_sample = t.tiles_per_sample;
     p.dbg = g_tc_dbg;
+    p.cluster = use_cluster ? 1 : 0;
     int rc = (t.BN == 128) ? tc_launch<128>(tmA, tmWhi, tmWlo, p, t, st) : tc_launch<64>(tmA, tmWhi, tmWlo, p, t, st);
     if (rc != MUGD_OK) return rc;
-    if (launches) *launches += (t.splits > 1) ? 2 : 1;
+    if (launches) *launches += (t.splits > 1 && !use_cluster) ? 2 : 1;
     return MUGD_OK;
 }
 
 }  // namespace mugd
+
+extern "C" int mugd_set_tc_cluster_reduce(int enabled) {
+    mugd::g_tc_cluster = enabled != 0;
+    return MUGD_OK;
+}
 
 extern "C" int mugd_debug_set_tc_timing(long long* device_buf4) {
     mugd::g_tc_dbg = device_buf4;
