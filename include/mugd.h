@@ -58,7 +58,10 @@ enum mugd_conv_mode {
     MUGD_CONV_NONE = 0,        /* taps=1: Linear / 1x1 conv (unet.py skip_connection, attention.py proj_in)  */
     MUGD_CONV_SAME = 1,        /* taps=3, pad 1: nn.Conv1d(k=3,padding=1)                                    */
     MUGD_CONV_DOWN = 2,        /* taps=3, right-pad 1, stride 2: models.py:84-91 Downsample                  */
-    MUGD_CONV_UP = 3           /* nearest x2 then taps=3 pad 1: models.py:66-70 Upsample                     */
+    MUGD_CONV_UP = 3,          /* nearest x2 then taps=3 pad 1: models.py:66-70 Upsample                     */
+    MUGD_CONV_TAPS = 4         /* `taps` consecutive rows l+tap_shift .. (zero outside the sample), Lin == Lout: the
+                                  two parity halves of Upsample (y[2j] = W0 x[j-1] + (W1+W2) x[j],
+                                  y[2j+1] = (W0+W1) x[j] + W2 x[j+1]) run as 2-tap GEMMs on half the rows         */
 };
 enum mugd_act { MUGD_ACT_NONE = 0, MUGD_ACT_SILU = 1, MUGD_ACT_GELU = 2 };
 /* gated epilogues: weight rows are interleaved (value_j, gate_j) by the packer; output has N/2 columns */
@@ -84,7 +87,7 @@ typedef struct mugd_gemm {
     int32_t act, gate, impl;
     int32_t split_k;                       /* tensor-core path: 0 = auto, >0 forces the K split            */
     int32_t n_counters;                    /* entries available in `counters`                              */
-    int32_t reserved0;
+    int32_t tap_shift;                     /* MUGD_CONV_TAPS: source row of tap t is l + t + tap_shift     */
     void* workspace; int64_t workspace_bytes; /* split-K partial tiles (see mugd_gemm_tc_query)            */
     int32_t* counters;                     /* zero-initialised tile tickets, left zero by every launch     */
 } mugd_gemm;
@@ -194,6 +197,9 @@ int  mugd_gemm_tc_query(mugd_handle* h, const mugd_gemm* g, int32_t sm_count, in
 /* split-K reduction of the tensor-core GEMM: 0 (default) = partial tiles through the workspace + a reduce kernel;
  * 1 = the splits of a tile run as one thread-block cluster and reduce through distributed shared memory (slower on B200) */
 int  mugd_set_tc_cluster_reduce(int enabled);
+
+/* experiments: force the tensor-core tile width (128 or 256) where legal; 0 = cost model */
+int  mugd_debug_set_tc_tile_n(int bn);
 
 /* debugging aid: when set (device pointer to 8 x int64), CTA (0,0,0) of every tensor-core GEMM launch writes
  * %globaltimer stamps {kernel entry, setup done, accumulator ready, tile staged in smem, epilogue done}; pass NULL to disable */

@@ -22,7 +22,7 @@ struct GemmParams {
     int nk;  // total k-steps = taps*K/16
 };
 
-__device__ __forceinline__ int conv_src_row(int mode, int l, int t, int Lin, int Lout) {
+__device__ __forceinline__ int conv_src_row(int mode, int l, int t, int Lin, int Lout, int tap_shift) {
     // returns source row inside the sample or -1 for the zero padding
     if (mode == MUGD_CONV_NONE) return l;
     if (mode == MUGD_CONV_SAME) {
@@ -32,6 +32,10 @@ __device__ __forceinline__ int conv_src_row(int mode, int l, int t, int Lin, int
     if (mode == MUGD_CONV_DOWN) {
         const int r = 2 * l + t;
         return (r < Lin) ? r : -1;
+    }
+    if (mode == MUGD_CONV_TAPS) {
+        const int r = l + t + tap_shift;
+        return (r >= 0 && r < Lin) ? r : -1;
     }
     // MUGD_CONV_UP: index on the x2-upsampled axis, then halve
     const int r = l + t - 1;
@@ -82,7 +86,7 @@ gemm_simt_kernel(const GemmParams p) {
         for (int r = 0; r < RM; ++r) {
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (a_b[r] >= 0) {
-                const int src = conv_src_row(g.conv_mode, a_l[r], t, g.Lin, g.Lout);
+                const int src = conv_src_row(g.conv_mode, a_l[r], t, g.Lin, g.Lout, g.tap_shift);
                 if (src >= 0) v = ld_f4(g.A + ((int64_t)a_b[r] * g.Lin + src) * g.lda + k0 + a_kq * 4);
             }
             ra[r] = v;
@@ -209,8 +213,9 @@ static int validate_gemm(const mugd_gemm& g) {
     MUGD_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, "gemm: empty shape M=%d N=%d K=%d", g.M, g.N, g.K);
     MUGD_REQUIRE(g.K % 16 == 0, "gemm: K=%d must be a multiple of 16", g.K);
     MUGD_REQUIRE(g.N % 4 == 0, "gemm: N=%d must be a multiple of 4", g.N);
-    MUGD_REQUIRE(g.taps == 1 || g.taps == 3, "gemm: taps=%d must be 1 or 3", g.taps);
-    MUGD_REQUIRE((g.conv_mode == MUGD_CONV_NONE) == (g.taps == 1), "gemm: conv_mode %d inconsistent with taps %d", g.conv_mode, g.taps);
+    MUGD_REQUIRE(g.taps >= 1 && g.taps <= 3, "gemm: taps=%d must be 1..3", g.taps);
+    if (g.conv_mode == MUGD_CONV_TAPS) MUGD_REQUIRE(g.Lin == g.Lout, "gemm: CONV_TAPS needs Lin == Lout");
+    else MUGD_REQUIRE((g.conv_mode == MUGD_CONV_NONE) ? (g.taps == 1) : (g.taps == 3), "gemm: conv_mode %d inconsistent with taps %d", g.conv_mode, g.taps);
     MUGD_REQUIRE(g.Lout > 0 && g.Lin > 0 && g.M % g.Lout == 0, "gemm: M=%d not a multiple of Lout=%d", g.M, g.Lout);
     if (g.conv_mode == MUGD_CONV_NONE || g.conv_mode == MUGD_CONV_SAME)
         MUGD_REQUIRE(g.Lin == g.Lout, "gemm: Lin must equal Lout for conv_mode %d", g.conv_mode);

@@ -226,7 +226,8 @@ __device__ __forceinline__ void tc_epi4(const mugd_gemm& g, float4 acc, int m, i
 
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWhi,
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA1,
+               const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmWhi,
                const __grid_constant__ CUtensorMap tmWlo, const TcParams p) {
     using S = TcSmem<BN>;
     constexpr int STAGES = S::STAGES;
@@ -300,8 +301,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int t = it / p.kblocks;
                 const int kb = it - t * p.kblocks;
                 mbar_expect_tx(bar_full(s), a_tx + 2 * S::B_BYTES);
-                const int lshift = (g.conv_mode == MUGD_CONV_SAME) ? (t - 1) : 0;
-                tma_load_3d(a_hi(s), &tmA, bar_full(s), kb * TC_BK, l_base + lshift, b_base);
+                // row addressing per tap: SAME = l+t-1, TAPS = l+t+shift (zero fill outside the sample by TMA bounds);
+                // DOWN (stride 2, right pad) uses one strided tensor map per tap (row l of map t = source row 2l+t)
+                const CUtensorMap* ma = &tmA;
+                int lshift = 0;
+                if (g.conv_mode == MUGD_CONV_SAME) lshift = t - 1;
+                else if (g.conv_mode == MUGD_CONV_TAPS) lshift = t + g.tap_shift;
+                else if (g.conv_mode == MUGD_CONV_DOWN) ma = (t == 0) ? &tmA : (t == 1 ? &tmA1 : &tmA2);
+                tma_load_3d(a_hi(s), ma, bar_full(s), kb * TC_BK, l_base + lshift, b_base);
                 tma_load_2d(b_hi(s), &tmWhi, bar_full(s), t * g.K + kb * TC_BK, n0);
                 tma_load_2d(b_lo(s), &tmWlo, bar_full(s), t * g.K + kb * TC_BK, n0);
             }
@@ -493,6 +500,7 @@ gemm_tc_reduce_kernel(const TcParams p, int gx, int gy) {
 }
 
 static long long* g_tc_dbg = nullptr;
+static int g_tc_force_bn = 0;        // experiments: 0 = cost model, 128 / 256 = force the tile width where legal
 // Split-K reduction through a thread-block cluster + DSMEM instead of workspace + reduce kernel.  Works (tests pass)
 // but measured slower on B200: clusters of 197 KB-smem CTAs schedule poorly (8 co-resident SMs of one GPC) and DSMEM
 // reads cost ~4 us per tile: GEMM family 4.50 ms vs 3.38 ms per step -> off by default, kept for experiments.
@@ -522,7 +530,9 @@ struct TcGeometry {
 };
 
 bool gemm_tc_supported(const mugd_gemm& g) {
-    if (!(g.conv_mode == MUGD_CONV_NONE || g.conv_mode == MUGD_CONV_SAME)) return false;
+    if (!(g.conv_mode == MUGD_CONV_NONE || g.conv_mode == MUGD_CONV_SAME || g.conv_mode == MUGD_CONV_DOWN ||
+          g.conv_mode == MUGD_CONV_TAPS)) return false;
+    if (g.conv_mode == MUGD_CONV_DOWN && g.Lout < 2) return false;
     if (g.K % TC_BK != 0 || g.N < 64 || g.N % 4 != 0) return false;
     if (!g.W_hi || !g.W_lo) return false;
     if (g.lda % 4 != 0 || !aligned16(g.A) || !aligned16(g.W_hi) || !aligned16(g.W_lo)) return false;
@@ -545,25 +555,35 @@ static TcGeometry tc_geometry(const mugd_gemm& g, int sm_count, int forced_split
         t.tiles_per_sample = 1;
         t.gy = (t.Bs + t.box_b - 1) / t.box_b;
     }
-    t.gx = (g.N + t.BN - 1) / t.BN;
     t.total_it = g.taps * (g.K / TC_BK);
+    // Cost model from the B200 micro-benchmark (tools/bench_gemm.py): a CTA needs ~1 us to fill its pipeline and
+    // ~0.7 us per k-step with 128-wide tiles (~1.05 us with 256-wide tiles, which do twice the math per step but
+    // only 2 pipeline stages fit); splitting K adds the workspace round trip and a second (reduce) launch, ~5 us.
+    // Candidates: tile width 128 (or 64 for narrow N), 256 when N allows it, each with its best K split.
     int splits = 1;
-    const int tiles = t.gx * t.gy;
-    if (forced_split > 0) splits = forced_split;
-    else if (tiles < sm_count) {
-        // cost model from the B200 micro-benchmark (tools/bench_gemm.py): a CTA needs ~1 us to fill its pipeline and
-        // ~0.7 us per k-step; splitting adds the workspace round trip and a second (reduce) launch, ~5 us.
-        float best = 1e30f;
-        const int sp_max = g_tc_cluster ? 8 : 16;
-        for (int sp = 1; sp <= sp_max && sp <= t.total_it; ++sp) {
+    float best = 1e30f;
+    const int bn_lo = (g.N >= 128) ? 128 : 64;
+    const int tc_bn_env = g_tc_force_bn;
+    for (int cand = 0; cand < 2; ++cand) {
+        const int bn = cand == 0 ? bn_lo : 256;
+        if (cand == 1 && g.N < 256) break;
+        if (tc_bn_env && bn != tc_bn_env && !(tc_bn_env == 256 && g.N < 256 && cand == 0)) continue;
+        const int gx = (g.N + bn - 1) / bn;
+        const int tiles = gx * t.gy;
+        const float kstep = bn == 256 ? 1.05f : (bn == 128 ? 0.7f : 0.5f);
+        // 256-wide tiles only pay off unsplit (measured: l1/l2 FF1 and the B=64 convs gain 15-25 %, split cases lose)
+        const int sp_max = forced_split > 0 ? forced_split : ((tiles < sm_count && bn != 256) ? (g_tc_cluster ? 8 : 16) : 1);
+        for (int sp = forced_split > 0 ? forced_split : 1; sp <= sp_max && sp <= t.total_it; ++sp) {
             const int per = (t.total_it + sp - 1) / sp;
-            if (sp > 1 && per < 2) break;
-            if (sp > 1 && tiles * sp > 2 * sm_count) break;              // bounds the workspace: < 2*SMs partial tiles
+            if (forced_split <= 0 && sp > 1 && per < 2) break;
+            if (forced_split <= 0 && sp > 1 && tiles * sp > 2 * sm_count) break;   // bounds the workspace: < 2*SMs partial tiles
             const int waves = (tiles * sp + sm_count - 1) / sm_count;
-            const float est = waves * (1.0f + 0.7f * per) + (sp > 1 ? (g_tc_cluster ? 2.0f : 5.0f) : 0.0f);
-            if (est < best - 0.25f) { best = est; splits = sp; }
+            const float est = waves * (1.0f + kstep * per) + (sp > 1 ? (g_tc_cluster ? 2.0f : 5.0f) : 0.0f);
+            if (est < best - 0.25f) { best = est; splits = sp; t.BN = bn; }
         }
     }
+    t.gx = (g.N + t.BN - 1) / t.BN;
+    const int tiles = t.gx * t.gy;
     if (splits > t.total_it) splits = t.total_it;
     if (splits < 1) splits = 1;
     t.splits = splits;
@@ -572,8 +592,9 @@ static TcGeometry tc_geometry(const mugd_gemm& g, int sm_count, int forced_split
 }
 
 template <int BN>
-static int tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmWhi, const CUtensorMap& tmWlo, const TcParams& p,
+static int tc_launch(const CUtensorMap* tmAs, const CUtensorMap& tmWhi, const CUtensorMap& tmWlo, const TcParams& p,
                      const TcGeometry& t, cudaStream_t st) {
+    const CUtensorMap &tmA = tmAs[0], &tmA1 = tmAs[1], &tmA2 = tmAs[2];
     static bool configured = false;
     if (!configured) {
         MUGD_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcSmem<BN>::TOTAL));
@@ -595,10 +616,10 @@ static int tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmWhi, const CUt
         attr[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = g_use_pdl ? 2 : 1;
-        MUGD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN>, tmA, tmWhi, tmWlo, p));
+        MUGD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN>, tmA, tmA1, tmA2, tmWhi, tmWlo, p));
         return MUGD_OK;
     }
-    MUGD_CHECK_CUDA(launch_k(gemm_tc_kernel<BN>, grid, dim3(TC_THREADS), TcSmem<BN>::TOTAL, st, tmA, tmWhi, tmWlo, p));
+    MUGD_CHECK_CUDA(launch_k(gemm_tc_kernel<BN>, grid, dim3(TC_THREADS), TcSmem<BN>::TOTAL, st, tmA, tmA1, tmA2, tmWhi, tmWlo, p));
     if (t.splits > 1) {
         const long long total = (long long)t.gx * t.gy * TC_BM * (BN / 4);
         MUGD_CHECK_CUDA(launch_k(gemm_tc_reduce_kernel<BN>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, p, t.gx, t.gy));
@@ -617,13 +638,19 @@ int launch_gemm_tc(const DeviceInfo& dev, const mugd_gemm& g, cudaStream_t st, i
         MUGD_REQUIRE(g.workspace_bytes >= t.ws_floats * 4, "gemm_tc: workspace too small (%lld < %lld)", (long long)g.workspace_bytes,
                      (long long)t.ws_floats * 4);
     }
-    CUtensorMap tmA, tmWhi, tmWlo;
-    {
-        cuuint64_t dims[3] = {(cuuint64_t)g.K, (cuuint64_t)t.Lrows, (cuuint64_t)t.Bs};
-        cuuint64_t strides[2] = {(cuuint64_t)g.lda * 4, (cuuint64_t)t.Lrows * (cuuint64_t)g.lda * 4};
+    CUtensorMap tmAs[3], tmWhi, tmWlo;
+    for (int tap = 0; tap < 3; ++tap) {
+        if (tap > 0 && g.conv_mode != MUGD_CONV_DOWN) { tmAs[tap] = tmAs[0]; continue; }
+        const bool down = g.conv_mode == MUGD_CONV_DOWN;
+        // DOWN: row l of the map of tap t is source row 2l+t; the last row of tap 2 is the right padding -> out of bounds
+        const cuuint64_t rows = down ? (cuuint64_t)(t.Lrows - (tap == 2 ? 1 : 0)) : (cuuint64_t)t.Lrows;
+        const cuuint64_t sample_rows = down ? (cuuint64_t)g.Lin : (cuuint64_t)t.Lrows;
+        cuuint64_t dims[3] = {(cuuint64_t)g.K, rows, (cuuint64_t)t.Bs};
+        cuuint64_t strides[2] = {(cuuint64_t)g.lda * 4 * (down ? 2 : 1), sample_rows * (cuuint64_t)g.lda * 4};
         cuuint32_t box[3] = {(cuuint32_t)TC_BK, (cuuint32_t)t.box_l, (cuuint32_t)t.box_b};
         cuuint32_t estr[3] = {1, 1, 1};
-        CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(g.A), dims, strides, box, estr,
+        const float* basep = g.A + (down ? (int64_t)tap * g.lda : 0);
+        CUresult r = enc(&tmAs[tap], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(basep), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         MUGD_REQUIRE(r == CUDA_SUCCESS, "gemm_tc: cuTensorMapEncodeTiled(A) failed with %d (K=%d L=%d B=%d lda=%lld)", (int)r, g.K,
@@ -654,13 +681,19 @@ int launch_gemm_tc(const DeviceInfo& dev, const mugd_gemm& g, cudaStream_t st, i
     p.tiles_per_sample = t.tiles_per_sample;
     p.dbg = g_tc_dbg;
     p.cluster = use_cluster ? 1 : 0;
-    int rc = (t.BN == 128) ? tc_launch<128>(tmA, tmWhi, tmWlo, p, t, st) : tc_launch<64>(tmA, tmWhi, tmWlo, p, t, st);
+    int rc = (t.BN == 256) ? tc_launch<256>(tmAs, tmWhi, tmWlo, p, t, st)
+             : (t.BN == 128) ? tc_launch<128>(tmAs, tmWhi, tmWlo, p, t, st) : tc_launch<64>(tmAs, tmWhi, tmWlo, p, t, st);
     if (rc != MUGD_OK) return rc;
     if (launches) *launches += (t.splits > 1 && !use_cluster) ? 2 : 1;
     return MUGD_OK;
 }
 
 }  // namespace mugd
+
+extern "C" int mugd_debug_set_tc_tile_n(int bn) {
+    mugd::g_tc_force_bn = (bn == 128 || bn == 256) ? bn : 0;
+    return MUGD_OK;
+}
 
 extern "C" int mugd_set_tc_cluster_reduce(int enabled) {
     mugd::g_tc_cluster = enabled != 0;
@@ -676,7 +709,8 @@ extern "C" int mugd_gemm_tc_query(mugd_handle*, const mugd_gemm* g, int32_t sm_c
                                   int64_t* workspace_bytes, int32_t* n_tiles) {
     using namespace mugd;
     MUGD_REQUIRE(g, "gemm_tc_query: null");
-    const bool ok = (g->conv_mode == MUGD_CONV_NONE || g->conv_mode == MUGD_CONV_SAME) && g->K % TC_BK == 0 && g->N >= 64 && g->N % 4 == 0;
+    const bool ok = (g->conv_mode == MUGD_CONV_NONE || g->conv_mode == MUGD_CONV_SAME || g->conv_mode == MUGD_CONV_DOWN ||
+                     g->conv_mode == MUGD_CONV_TAPS) && g->K % TC_BK == 0 && g->N >= 64 && g->N % 4 == 0;
     if (supported) *supported = ok ? 1 : 0;
     if (!ok) {
         if (splits) *splits = 0;

@@ -90,7 +90,7 @@ class OpList:
              mode: int = L_.CONV_NONE, Lin: int = 0, Lout: int = 0, act: int = L_.ACT_NONE,
              gate: int = L_.GATE_NONE, residual: Optional[View] = None, rowvec: int = 0,
              rowvec_b_stride: int = 0, rowvec_step_stride: int = 0, step: int = 0, impl: int = L_.GEMM_AUTO,
-             W_hi: int = 0, W_lo: int = 0, split_k: int = 0, tag: int = 0):
+             W_hi: int = 0, W_lo: int = 0, split_k: int = 0, tap_shift: int = 0, tag: int = 0):
         g = L_.Gemm()
         M = out.rows
         g.A, g.lda = A.ptr, A.ld
@@ -98,6 +98,7 @@ class OpList:
             W_hi, W_lo = self.tc_map[W]
         g.W, g.W_hi, g.W_lo, g.bias = W, W_hi or None, W_lo or None, bias or None
         g.split_k = split_k
+        g.tap_shift = tap_shift
         g.rowvec, g.rowvec_b_stride, g.rowvec_step_stride = rowvec or None, rowvec_b_stride, rowvec_step_stride
         g.step = step or None
         if residual is not None:
@@ -156,6 +157,20 @@ class OpList:
         assert src.rows == dst.rows and src.cols == dst.cols
         d.src, d.lds, d.dst, d.ldd, d.rows, d.cols = src.ptr, src.ld, dst.ptr, dst.ld, src.rows, src.cols
         self.add(L_.OP_COPY2D, d, tag)
+
+
+def emit_upsample_conv(ops: "OpList", blob: WeightBlob, wfn, prefix: str, x: View, out: View, Lin: int, cin: int, cout: int, tag: int):
+    """Upsample (nearest x2) + conv3 (models.py:66-70).  With the parity-split weights of the packer this is two 2-tap
+    GEMMs over the Lin input rows writing the even / odd output rows (row stride 2*ld) -- 2/3 of the FLOPs of the
+    literal form and eligible for the tensor-core kernel; otherwise the generic MUGD_CONV_UP addressing is used."""
+    if (prefix + "conv.up_even.weight") in blob.entries:
+        for parity, name, shift in ((0, "conv.up_even.weight", -1), (1, "conv.up_odd.weight", 0)):
+            dst = View(out.ptr + 4 * parity * out.ld, 2 * out.ld, x.rows, out.cols)
+            ops.gemm(x, wfn(prefix + name), cout, cin, dst, bias=wfn(prefix + "conv.bias"), taps=2, mode=L_.CONV_TAPS,
+                     Lin=Lin, Lout=Lin, tap_shift=shift, tag=tag)
+    else:
+        ops.gemm(x, wfn(prefix + "conv.weight"), cout, cin, out, bias=wfn(prefix + "conv.bias"), taps=3, mode=L_.CONV_UP,
+                 Lin=Lin, Lout=2 * Lin, tag=tag)
 
 
 def tc_weight_map(blob: WeightBlob, wbase: int) -> Dict[int, Tuple[int, int]]:
@@ -340,8 +355,7 @@ class UNetCompiler:
                 if b.kind == "up":
                     tgt_rows = rows[lvl - 1]
                     out = final_out if (last and final_out is not None) else arena.alloc(tgt_rows, b.cout)
-                    ops.gemm(cur, self.w(b.prefix + "conv.weight"), b.cout, b.cin, out, bias=self.w(b.prefix + "conv.bias"),
-                             taps=3, mode=L_.CONV_UP, Lin=lens[lvl], Lout=lens[lvl - 1], tag=TAG_UPDOWN)
+                    emit_upsample_conv(ops, self.blob, self.w, b.prefix, cur, out, lens[lvl], b.cin, b.cout, TAG_UPDOWN)
                     lvl -= 1
                     cur = out
                     continue
@@ -463,8 +477,7 @@ class DecoderCompiler:
                 cur = o
             elif b.kind == "up":
                 o = arena.alloc(B * Lr * 2, b.cout)
-                ops.gemm(cur, self.w(p + "conv.weight"), b.cout, b.cin, o, bias=self.w(p + "conv.bias"), taps=3,
-                         mode=L_.CONV_UP, Lin=Lr, Lout=2 * Lr, tag=TAG_UPDOWN)
+                emit_upsample_conv(ops, self.blob, self.w, p, cur, o, Lr, b.cin, b.cout, TAG_UPDOWN)
                 cur = o
             elif b.kind == "dec_out":
                 t = arena.alloc(B * Lr, b.cin)

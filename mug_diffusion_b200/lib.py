@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "libmugd.so")
 
 # ---- enums (include/mugd.h) ------------------------------------------------------------------------
 OP_GEMM, OP_GROUPNORM, OP_LAYERNORM, OP_ATTENTION, OP_S4CONV, OP_DDIM_UPDATE, OP_TRANSPOSE, OP_COPY2D, OP_STEP_ADVANCE = range(1, 10)
-CONV_NONE, CONV_SAME, CONV_DOWN, CONV_UP = range(4)
+CONV_NONE, CONV_SAME, CONV_DOWN, CONV_UP, CONV_TAPS = range(5)
 ACT_NONE, ACT_SILU, ACT_GELU = range(3)
 GATE_NONE, GATE_GEGLU, GATE_GLU = range(3)
 GEMM_AUTO, GEMM_SIMT, GEMM_TC = range(3)
@@ -30,7 +30,7 @@ class Gemm(C.Structure):
                 ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
                 ("taps", C.c_int32), ("conv_mode", C.c_int32), ("Lin", C.c_int32), ("Lout", C.c_int32),
                 ("act", C.c_int32), ("gate", C.c_int32), ("impl", C.c_int32),
-                ("split_k", C.c_int32), ("n_counters", C.c_int32), ("reserved0", C.c_int32),
+                ("split_k", C.c_int32), ("n_counters", C.c_int32), ("tap_shift", C.c_int32),
                 ("workspace", _f), ("workspace_bytes", C.c_int64), ("counters", _f)]
 
 
@@ -144,6 +144,9 @@ def load() -> C.CDLL:
     if list(sizes) != mine:
         raise MugdError(f"struct layout mismatch: C {list(sizes)} vs ctypes {mine}")
     lib.mugd_set_tc_cluster_reduce.argtypes = [C.c_int]
+    lib.mugd_debug_set_tc_tile_n.argtypes = [C.c_int]
+    if os.environ.get("MUGD_TC_BN"):
+        lib.mugd_debug_set_tc_tile_n(int(os.environ["MUGD_TC_BN"]))
     if os.environ.get("MUGD_TC_CLUSTER", "0") == "1":   # A/B switch: split-K reduction through cluster DSMEM
         lib.mugd_set_tc_cluster_reduce(1)
     if os.environ.get("MUGD_PDL", "0") == "1":          # A/B switch for programmatic dependent launch (default off)
@@ -164,5 +167,5 @@ def check(rc: int, what: str = ""):
 EXPORTED_SYMBOLS = [
     "mugd_abi_version", "mugd_last_error", "mugd_create", "mugd_destroy", "mugd_device_info", "mugd_set_gemm_impl",
     "mugd_op_run", "mugd_plan_create", "mugd_plan_run", "mugd_plan_capture", "mugd_plan_replay",
-    "mugd_plan_launch_count", "mugd_plan_destroy", "mugd_s4_kernel_gen", "mugd_fill_i32", "mugd_abi_sizes", "mugd_gemm_tc_query", "mugd_set_pdl", "mugd_set_tc_cluster_reduce", "mugd_debug_set_tc_timing",
+    "mugd_plan_launch_count", "mugd_plan_destroy", "mugd_s4_kernel_gen", "mugd_fill_i32", "mugd_abi_sizes", "mugd_gemm_tc_query", "mugd_set_pdl", "mugd_set_tc_cluster_reduce", "mugd_debug_set_tc_tile_n", "mugd_debug_set_tc_timing",
 ]

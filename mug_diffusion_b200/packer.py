@@ -165,8 +165,15 @@ def _pack_block(blob: WeightBlob, sd: Dict[str, torch.Tensor], b: Block):
         blob.add_shaped(p + "out_layer.weight", _conv3(sd[p + "out_layer.weight"]))
         blob.add_shaped(p + "out_layer.bias", sd[p + "out_layer.bias"])
     elif b.kind in ("down", "up"):
-        blob.add_shaped(p + "conv.weight", _conv3(sd[p + "conv.weight"]))
+        w = sd[p + "conv.weight"]
+        blob.add_shaped(p + "conv.weight", _conv3(w))
         blob.add_shaped(p + "conv.bias", sd[p + "conv.bias"])
+        if b.kind == "up":
+            # nearest-x2 upsample followed by conv3 == two 2-tap convs on the un-upsampled rows (models.py:66-70):
+            #   y[2j]   = W0 x[j-1] + (W1+W2) x[j]        y[2j+1] = (W0+W1) x[j] + W2 x[j+1]
+            w0, w1, w2 = w[:, :, 0], w[:, :, 1], w[:, :, 2]
+            blob.add_shaped(p + "conv.up_even.weight", torch.cat([w0, w1 + w2], dim=1).contiguous())
+            blob.add_shaped(p + "conv.up_odd.weight", torch.cat([w0 + w1, w2], dim=1).contiguous())
     elif b.kind == "out":
         blob.add_shaped(p + "0.weight", sd[p + "0.weight"])
         blob.add_shaped(p + "0.bias", sd[p + "0.bias"])

@@ -122,3 +122,43 @@ def test_tc_matches_simt_closely_and_beats_plain_tf32(R):
     e_tc, e_si = rel_err(ncl(out_tc.cpu(), B), ref), rel_err(ncl(out_si.cpu(), B), ref)
     print(f"long-K conv: tc err {e_tc:.2e}  simt err {e_si:.2e}")
     assert e_tc < 5e-6 and e_si < 5e-6
+
+
+@pytest.mark.parametrize("B,L,C", [(2, 512, 128), (4, 256, 256), (3, 128, 384), (8, 64, 64)])
+def test_tc_downsample(R, B, L, C):
+    """models.py:84-91: right-pad 1, conv3 stride 2 -- one strided TMA tensor map per tap"""
+    x, w, b = g("dx", (B, C, L)), g("dw", (C, C, 3)) / math.sqrt(3 * C), 0.1 * g("db", (C,))
+    ref = F.conv1d(F.pad(x.double(), (0, 1)), w.double(), b.double(), stride=2)
+    wp = w.permute(0, 2, 1).contiguous().reshape(C, 3 * C)
+    xc, bc = nlc(x).cuda(), b.cuda()
+    out = torch.zeros(B * L // 2, C).cuda()
+    run_tc(R, view(xc), wp, C, C, view(out), bias=ptr(bc), taps=3, mode=L_.CONV_DOWN, Lin=L, Lout=L // 2)
+    e = rel_err(ncl(out.cpu(), B), ref)
+    print(f"tc_down B={B} L={L} C={C} rel_err={e:.2e}")
+    assert e < TOL
+
+
+@pytest.mark.parametrize("impl", [L_.GEMM_TC, L_.GEMM_SIMT])
+@pytest.mark.parametrize("B,L,C", [(2, 128, 256), (3, 64, 512), (2, 256, 64)])
+def test_upsample_as_two_parity_gemms(R, impl, B, L, C):
+    """models.py:66-70 nearest x2 + conv3 == y[2j] = W0 x[j-1] + (W1+W2) x[j], y[2j+1] = (W0+W1) x[j] + W2 x[j+1]"""
+    from mug_diffusion_b200.engine import View
+    x, w, b = g("ux", (B, C, L)), g("uw", (C, C, 3)) / math.sqrt(3 * C), 0.1 * g("ub", (C,))
+    ref = F.conv1d(x.double().repeat_interleave(2, dim=-1), w.double(), b.double(), padding=1)
+    w0, w1, w2 = w[:, :, 0], w[:, :, 1], w[:, :, 2]
+    we, wo = torch.cat([w0, w1 + w2], dim=1).contiguous(), torch.cat([w0 + w1, w2], dim=1).contiguous()
+    xc, bc = nlc(x).cuda(), b.cuda()
+    out = torch.zeros(B * 2 * L, C).cuda()
+    keep = []
+    ops = OpList()
+    for parity, wt, shift in ((0, we, -1), (1, wo, 0)):
+        hi, lo = tf32_split(wt)
+        wc, hc, lc = wt.cuda(), hi.cuda(), lo.cuda()
+        keep += [wc, hc, lc]
+        dst = View(out.data_ptr() + 4 * parity * C, 2 * C, B * L, C)
+        ops.gemm(view(xc), ptr(wc), C, C, dst, W_hi=ptr(hc), W_lo=ptr(lc), bias=ptr(bc), taps=2, mode=L_.CONV_TAPS, Lin=L, Lout=L,
+                 tap_shift=shift, impl=impl)
+    R.run(ops)
+    e = rel_err(ncl(out.cpu(), B), ref)
+    print(f"upsample parity impl={impl} B={B} L={L} C={C} rel_err={e:.2e}")
+    assert e < TOL
