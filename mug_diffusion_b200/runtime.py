@@ -169,9 +169,20 @@ class Session:
             L_int = int(eng.blob.meta[k + "L"])
             L_req = self.Lz // b.ds
             if L_req > L_int:
-                raise L_.MugdError(
-                    f"S4 layer {b.prefix}: requested length {L_req} exceeds the checkpoint's internal kernel length "
-                    f"{L_int}; lengthen C~ with mug_diffusion_b200.s4_setup.double_length() before packing (s4.py:557-584)")
+                # same one-time, persistent mutation the reference performs in SSKernelNPLR._setup_C (s4.py:557-584):
+                # lengthen C~ on the host, store it back into the weight blob and remember the new internal length
+                from . import s4_setup
+
+                def grab(n):
+                    e = eng.blob.entries[k + n]
+                    cnt = int(np.prod(e.shape))
+                    return eng.weights[e.offset:e.offset + cnt].view(e.shape).detach().cpu()
+
+                params = {n: grab(n) for n in ("C", "log_dt", "P", "inv_w_real", "w_imag")}
+                C_new, L_int = s4_setup.lengthen(params, L_int, L_req)
+                e = eng.blob.entries[k + "C"]
+                eng.weights[e.offset:e.offset + C_new.numel()].copy_(C_new.reshape(-1).to(eng.device))
+                eng.blob.meta[k + "L"] = L_int
             need = 16 * b.cin * (L_int // 2 + 1)
             if ws is None or ws.numel() * 8 < need:
                 ws = torch.empty(need // 8 + 2, dtype=torch.float64, device=eng.device)

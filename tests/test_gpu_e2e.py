@@ -42,6 +42,17 @@ def test_unet_forward_vs_reference_golden(name, golden_dir):
     assert rel_err(eps, gold) < 1e-4
 
 
+def test_unet_forward_lengthens_s4_state_like_reference(golden_dir):
+    """weights persisted at z_length 48, request at 96: every S4 layer must double its C~ (s4.py:557-584)"""
+    _models.clear()
+    m = MugDiffusionB200.from_state_dict(synth.synthetic_state_dict(48), z_length=96)
+    inp = synth.synthetic_inputs(2, 96)
+    eps = m.model.forward(inp["x_T"].cuda(), torch.tensor([981, 1]).cuda(), inp["c"].cuda(), [w.cuda() for w in inp["w"]])
+    gold = gc.load_golden(os.path.join(golden_dir, "unet_L96_from48.npz"))["eps"]
+    assert rel_err(eps, gold) < 1e-4
+    assert m.engine.blob.meta["model.unet_model.input_blocks.2.1.s4_model.kernel.kernel.L"] == 96
+
+
 def test_unet_forward_vs_oracle_other_batch():
     """a shape with no golden: B=3, L=160, distinct timesteps -> live oracle"""
     L, B = 160, 3

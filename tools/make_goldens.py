@@ -103,6 +103,28 @@ def make_ddim():
         save(name, z=z.numpy(), logits=logits.numpy(), pred_x0_first=pred[0].numpy(), pred_x0_last=pred[-1].numpy())
 
 
+@torch.no_grad()
+def make_s4_lengthen():
+    """C~ lengthening (s4.py:557-584): a layer persisted at L=48 asked for L=96 (doubling), then 4x (two doublings),
+    and a never-run layer (L buffer 0) initialised at 96."""
+    out = {}
+    for tag, L_state, L_req in (("double", 48, 96), ("double2", 24, 96), ("init", 0, 96)):
+        model, _ = fresh_model(max(L_state, 8) if L_state else 96)
+        mod = get_module(model, "model.unet_model.input_blocks.2.1").s4_model.kernel.kernel
+        mod.L.fill_(L_state)
+        k, _ = mod(L=L_req)
+        out[tag + ".C"] = mod.C.detach().numpy().copy()
+        out[tag + ".L"] = np.asarray([int(mod.L.item())], dtype=np.float32)
+        out[tag + ".K"] = k[0].numpy().copy()
+    save("s4_lengthen", **out)
+    # whole U-Net: weights persisted at z_length 48 (S4 buffers 48/24/12/6), evaluated at 96 -> every S4 layer doubles
+    model, _ = fresh_model(48)
+    inp = synth.synthetic_inputs(2, 96)
+    eps = model.model.forward(inp["x_T"], torch.tensor([981, 1]), inp["c"], synth.wave_list(inp["w"]))
+    save("unet_L96_from48", eps=eps.numpy())
+
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
@@ -115,3 +137,7 @@ if __name__ == "__main__":
         make_unet()
     if a.only in (None, "ddim"):
         make_ddim()
+    if a.only in (None, "s4len"):
+        make_s4_lengthen()
+
+
