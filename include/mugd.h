@@ -198,6 +198,10 @@ int  mugd_gemm_tc_query(mugd_handle* h, const mugd_gemm* g, int32_t sm_count, in
  * 1 = the splits of a tile run as one thread-block cluster and reduce through distributed shared memory (slower on B200) */
 int  mugd_set_tc_cluster_reduce(int enabled);
 
+/* tensor-core GEMM variant: 1 (default) = split activations go to tensor memory and the MMAs read A from TMEM (TS form);
+ * 0 = both operands from shared memory (SS form) */
+int  mugd_set_tc_a_in_tmem(int enabled);
+
 /* experiments: force the tensor-core tile width (128 or 256) where legal; 0 = cost model */
 int  mugd_debug_set_tc_tile_n(int bn);
 

@@ -102,6 +102,30 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// A operand from tensor memory (lane = row, one 32-bit column per K element), B from shared memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+          "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+          "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+          "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
+          "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
+          "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
+          "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
+          "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -132,11 +156,12 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
     return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 
-template <int BN>
+template <int BN, bool AT>
 struct TcSmem {
     static constexpr uint32_t B_BYTES = BN * TC_BK * 4;
-    static constexpr uint32_t STAGE_BYTES = 2 * TC_A_BYTES + 2 * B_BYTES;
-    static constexpr int STAGES = (BN == 256) ? 2 : (BN == 128 ? 3 : 4);
+    static constexpr uint32_t A_BUFS = AT ? 1 : 2;            // AT: only the raw tile lives in smem (hi/lo go to TMEM)
+    static constexpr uint32_t STAGE_BYTES = A_BUFS * TC_A_BYTES + 2 * B_BYTES;
+    static constexpr int STAGES = AT ? ((BN == 256) ? 2 : (BN == 128 ? 4 : 6)) : ((BN == 256) ? 2 : (BN == 128 ? 3 : 4));
     static constexpr uint32_t TILE_BYTES = STAGES * STAGE_BYTES;
     static constexpr uint32_t TOTAL = TILE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
@@ -224,13 +249,20 @@ __device__ __forceinline__ void tc_epi4(const mugd_gemm& g, float4 acc, int m, i
         else { CALL(MUGD_ACT_NONE, MUGD_GATE_NONE); }                                                 \
     } while (0)
 
-template <int BN>
+// AT = true: the converter writes a_hi / a_lo straight into tensor memory (tcgen05.st) and the MMAs take A from TMEM
+// (.kind::tf32 "TS" form).  That removes the converter's 32 KB of shared-memory writes and the 3 x 16 KB of A-operand
+// reads per k-step from the shared-memory port, which is what bounds the all-smem ("SS") variant.
+template <int BN, bool AT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmWhi,
                const __grid_constant__ CUtensorMap tmWlo, const TcParams p) {
-    using S = TcSmem<BN>;
+    using S = TcSmem<BN, AT>;
     constexpr int STAGES = S::STAGES;
+    // TMEM columns: accumulator [0, BN), then (AT) per stage 32 columns a_hi + 32 columns a_lo
+    constexpr int TMEM_NEED = AT ? BN + STAGES * 64 : BN;
+    constexpr int TMEM_COLS = TMEM_NEED <= 64 ? 64 : (TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512));
+    static_assert(TMEM_NEED <= 512, "tensor memory budget");
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // SWIZZLE_128B needs 1024-B alignment
     const uint32_t bars = base + S::TILE_BYTES;                          // barrier block (8-byte aligned)
@@ -242,8 +274,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t tmem_slot = bars + 8u * (3 * STAGES + 1);
     auto a_hi = [&](int s) { return base + s * S::STAGE_BYTES; };
     auto a_lo = [&](int s) { return base + s * S::STAGE_BYTES + TC_A_BYTES; };
-    auto b_hi = [&](int s) { return base + s * S::STAGE_BYTES + 2 * TC_A_BYTES; };
-    auto b_lo = [&](int s) { return base + s * S::STAGE_BYTES + 2 * TC_A_BYTES + S::B_BYTES; };
+    auto b_hi = [&](int s) { return base + s * S::STAGE_BYTES + S::A_BUFS * TC_A_BYTES; };
+    auto b_lo = [&](int s) { return base + s * S::STAGE_BYTES + S::A_BUFS * TC_A_BYTES + S::B_BYTES; };
 
     const mugd_gemm& g = p.g;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -277,7 +309,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)BN) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -324,14 +356,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
                 mbar_wait(bar_conv(s), ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint64_t dah = umma_desc(a_hi(s)), dal = umma_desc(a_lo(s));
                 const uint64_t dbh = umma_desc(b_hi(s)), dbl = umma_desc(b_lo(s));
+                if constexpr (AT) {
+                    const uint32_t ta_hi = tmem_base + (uint32_t)(BN + s * 64), ta_lo = ta_hi + 32u;
 #pragma unroll
-                for (int kk = 0; kk < TC_BK / 8; ++kk) {
-                    const uint64_t ko = (uint64_t)(kk * 2);         // 8 fp32 = 32 bytes = 2 x 16-byte units
-                    umma_tf32(tmem_base, dal + ko, dbh + ko, idesc, (i > 0 || kk > 0) ? 1u : 0u);
-                    umma_tf32(tmem_base, dah + ko, dbl + ko, idesc, 1u);
-                    umma_tf32(tmem_base, dah + ko, dbh + ko, idesc, 1u);
+                    for (int kk = 0; kk < TC_BK / 8; ++kk) {
+                        const uint64_t ko = (uint64_t)(kk * 2);     // 8 fp32 = 32 bytes = 2 x 16-byte units
+                        umma_tf32_ts(tmem_base, ta_lo + kk * 8, dbh + ko, idesc, (i > 0 || kk > 0) ? 1u : 0u);
+                        umma_tf32_ts(tmem_base, ta_hi + kk * 8, dbl + ko, idesc, 1u);
+                        umma_tf32_ts(tmem_base, ta_hi + kk * 8, dbh + ko, idesc, 1u);
+                    }
+                } else {
+                    const uint64_t dah = umma_desc(a_hi(s)), dal = umma_desc(a_lo(s));
+#pragma unroll
+                    for (int kk = 0; kk < TC_BK / 8; ++kk) {
+                        const uint64_t ko = (uint64_t)(kk * 2);
+                        umma_tf32(tmem_base, dal + ko, dbh + ko, idesc, (i > 0 || kk > 0) ? 1u : 0u);
+                        umma_tf32(tmem_base, dah + ko, dbl + ko, idesc, 1u);
+                        umma_tf32(tmem_base, dah + ko, dbh + ko, idesc, 1u);
+                    }
                 }
                 umma_commit(bar_empty(s));                            // stage reusable once these MMAs retire
             }
@@ -344,6 +387,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int s = i % STAGES;
             const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
             mbar_wait(bar_full(s), ph);
+            if constexpr (AT) {
+                // thread = tile row (= TMEM lane): read the row's 128 bytes out of the 128B-swizzled tile (16-byte chunk c
+                // of row r sits at chunk c ^ (r & 7)), split, and store hi / lo to this stage's TMEM columns
+                const int r = (warp & 3) * 32 + lane;
+                const uint32_t rowaddr = a_hi(s) + (uint32_t)r * 128u;
+                float hi[32], lo[32];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    float4 x;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
+                                 : "r"(rowaddr + (uint32_t)((c ^ (r & 7)) * 16)));
+                    hi[c * 4] = to_tf32(x.x); hi[c * 4 + 1] = to_tf32(x.y); hi[c * 4 + 2] = to_tf32(x.z); hi[c * 4 + 3] = to_tf32(x.w);
+                    lo[c * 4] = to_tf32(x.x - hi[c * 4]); lo[c * 4 + 1] = to_tf32(x.y - hi[c * 4 + 1]);
+                    lo[c * 4 + 2] = to_tf32(x.z - hi[c * 4 + 2]); lo[c * 4 + 3] = to_tf32(x.w - hi[c * 4 + 3]);
+                }
+                const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(BN + s * 64);
+                tmem_st32(ta, hi);
+                tmem_st32(ta + 32u, lo);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            } else {
             const uint32_t hi_addr = a_hi(s), lo_addr = a_lo(s);
 #pragma unroll
             for (int j = 0; j < (int)(TC_A_BYTES / 16 / 128); ++j) {   // 8 x 16 bytes per thread
@@ -357,6 +421,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(lo_addr + off), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA (async proxy)
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_conv(s));
         }
@@ -452,7 +517,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ---- teardown (all tcgen05.ld completed before the phase-2 barrier) ----------------------------------
     if (warp == 2) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
     }
 }
 
@@ -500,6 +565,7 @@ gemm_tc_reduce_kernel(const TcParams p, int gx, int gy) {
 }
 
 static long long* g_tc_dbg = nullptr;
+static bool g_tc_a_in_tmem = true;   // A operand of the MMAs from tensor memory (TS form) instead of shared memory (SS)
 static int g_tc_force_bn = 0;        // experiments: 0 = cost model, 128 / 256 = force the tile width where legal
 // Split-K reduction through a thread-block cluster + DSMEM instead of workspace + reduce kernel.  Works (tests pass)
 // but measured slower on B200: clusters of 197 KB-smem CTAs schedule poorly (8 co-resident SMs of one GPC) and DSMEM
@@ -591,13 +657,13 @@ static TcGeometry tc_geometry(const mugd_gemm& g, int sm_count, int forced_split
     return t;
 }
 
-template <int BN>
+template <int BN, bool AT>
 static int tc_launch(const CUtensorMap* tmAs, const CUtensorMap& tmWhi, const CUtensorMap& tmWlo, const TcParams& p,
                      const TcGeometry& t, cudaStream_t st) {
     const CUtensorMap &tmA = tmAs[0], &tmA1 = tmAs[1], &tmA2 = tmAs[2];
     static bool configured = false;
     if (!configured) {
-        MUGD_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcSmem<BN>::TOTAL));
+        MUGD_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, AT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcSmem<BN, AT>::TOTAL));
         configured = true;
     }
     dim3 grid(t.gx, t.gy, t.splits);
@@ -605,7 +671,7 @@ static int tc_launch(const CUtensorMap* tmAs, const CUtensorMap& tmWhi, const CU
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = grid;
         cfg.blockDim = dim3(TC_THREADS);
-        cfg.dynamicSmemBytes = TcSmem<BN>::TOTAL;
+        cfg.dynamicSmemBytes = TcSmem<BN, AT>::TOTAL;
         cfg.stream = st;
         cudaLaunchAttribute attr[2];
         attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -616,10 +682,10 @@ static int tc_launch(const CUtensorMap* tmAs, const CUtensorMap& tmWhi, const CU
         attr[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = g_use_pdl ? 2 : 1;
-        MUGD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN>, tmA, tmA1, tmA2, tmWhi, tmWlo, p));
+        MUGD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, AT>, tmA, tmA1, tmA2, tmWhi, tmWlo, p));
         return MUGD_OK;
     }
-    MUGD_CHECK_CUDA(launch_k(gemm_tc_kernel<BN>, grid, dim3(TC_THREADS), TcSmem<BN>::TOTAL, st, tmA, tmA1, tmA2, tmWhi, tmWlo, p));
+    MUGD_CHECK_CUDA(launch_k(gemm_tc_kernel<BN, AT>, grid, dim3(TC_THREADS), TcSmem<BN, AT>::TOTAL, st, tmA, tmA1, tmA2, tmWhi, tmWlo, p));
     if (t.splits > 1) {
         const long long total = (long long)t.gx * t.gy * TC_BM * (BN / 4);
         MUGD_CHECK_CUDA(launch_k(gemm_tc_reduce_kernel<BN>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, p, t.gx, t.gy));
@@ -681,14 +747,24 @@ int launch_gemm_tc(const DeviceInfo& dev, const mugd_gemm& g, cudaStream_t st, i
     p.tiles_per_sample = t.tiles_per_sample;
     p.dbg = g_tc_dbg;
     p.cluster = use_cluster ? 1 : 0;
-    int rc = (t.BN == 256) ? tc_launch<256>(tmAs, tmWhi, tmWlo, p, t, st)
-             : (t.BN == 128) ? tc_launch<128>(tmAs, tmWhi, tmWlo, p, t, st) : tc_launch<64>(tmAs, tmWhi, tmWlo, p, t, st);
+    int rc;
+    if (g_tc_a_in_tmem)
+        rc = (t.BN == 256) ? tc_launch<256, true>(tmAs, tmWhi, tmWlo, p, t, st)
+             : (t.BN == 128) ? tc_launch<128, true>(tmAs, tmWhi, tmWlo, p, t, st) : tc_launch<64, true>(tmAs, tmWhi, tmWlo, p, t, st);
+    else
+        rc = (t.BN == 256) ? tc_launch<256, false>(tmAs, tmWhi, tmWlo, p, t, st)
+             : (t.BN == 128) ? tc_launch<128, false>(tmAs, tmWhi, tmWlo, p, t, st) : tc_launch<64, false>(tmAs, tmWhi, tmWlo, p, t, st);
     if (rc != MUGD_OK) return rc;
     if (launches) *launches += (t.splits > 1 && !use_cluster) ? 2 : 1;
     return MUGD_OK;
 }
 
 }  // namespace mugd
+
+extern "C" int mugd_set_tc_a_in_tmem(int enabled) {
+    mugd::g_tc_a_in_tmem = enabled != 0;
+    return MUGD_OK;
+}
 
 extern "C" int mugd_debug_set_tc_tile_n(int bn) {
     mugd::g_tc_force_bn = (bn == 128 || bn == 256) ? bn : 0;
