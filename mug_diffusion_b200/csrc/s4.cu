@@ -20,31 +20,36 @@ namespace mugd {
 // (1) causal long convolution.  lane = channel (coalesced), each warp owns blocks of 8 consecutive
 // outputs; a 16-deep register window slides over u (smem) while K taps stream from L1/L2.
 // =====================================================================================================
-constexpr int S4_CH = 32;       // channels per CTA
 constexpr int S4_WARPS = 8;
 constexpr int S4_R = 8;         // outputs per block
 
-// KS: kernel taps staged in shared memory next to u (2 * L * 128 B); otherwise streamed through L1 (long L).
-template <bool KS>
-__global__ void __launch_bounds__(S4_CH * S4_WARPS)
+// CH channels per CTA (32: one lane per channel; 16: the two half-warps share 16 channels and split the taps of every
+// chunk by parity, accumulators are added with one shuffle at the end -- used when two L x 32 tiles do not fit).
+// KS: kernel taps staged in shared memory next to u (2 * L * CH * 4 B); otherwise streamed through L1 (very long L).
+template <bool KS, int CH>
+__global__ void __launch_bounds__(32 * S4_WARPS)
 s4conv_kernel(const mugd_s4conv s, int nsplit) {
-    extern __shared__ float smem_s4[];     // us[L][32] then ks[L][32]
+    constexpr int NSUB = 32 / CH;
+    extern __shared__ float smem_s4[];     // us[L][CH] then ks[L][CH]
     float* us = smem_s4;
-    float* ks = smem_s4 + (size_t)s.L * S4_CH;
+    float* ks = smem_s4 + (size_t)s.L * CH;
     pdl_trigger();
     pdl_wait();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int h = blockIdx.x * S4_CH + lane;
+    const int ch = lane % CH, sub = lane / CH;
+    const int h = blockIdx.x * CH + ch;
     const int b = blockIdx.y;
     const int L = s.L;
-    const float* ub = s.u + (int64_t)b * L * s.ldu + blockIdx.x * S4_CH;
-    const float* Kh = s.Kt + h;            // tap j at Kh[j*H]
-    for (int l = warp; l < L; l += S4_WARPS) {
-        us[l * S4_CH + lane] = ub[(int64_t)l * s.ldu + lane];
-        if (KS) ks[l * S4_CH + lane] = Kh[(int64_t)l * s.H];
+    const float* ub = s.u + (int64_t)b * L * s.ldu + blockIdx.x * CH;
+    const float* Kc = s.Kt + blockIdx.x * CH;  // tap j of channel c at Kc[j*H + c]
+    for (int i = threadIdx.x; i < L * CH; i += 32 * S4_WARPS) {
+        const int l = i / CH, c = i - l * CH;
+        us[i] = ub[(int64_t)l * s.ldu + c];
+        if (KS) ks[i] = Kc[(int64_t)l * s.H + c];
     }
     __syncthreads();
 
+    const float* Kh = s.Kt + h;
     const float Dh = s.D[h];
     float* yb = s.y + (int64_t)b * L * s.ldy + h;
     const int nblk = (L + S4_R - 1) / S4_R;
@@ -66,52 +71,70 @@ s4conv_kernel(const mugd_s4conv s, int nsplit) {
 #pragma unroll
             for (int r = 0; r < S4_R; ++r) {
                 const int li = l0 + r;
-                win[S4_R + r] = (li < L) ? us[li * S4_CH + lane] : 0.f;
+                win[S4_R + r] = (li < L) ? us[li * CH + ch] : 0.f;
             }
             for (int jc = 0; jc < l0 + S4_R; jc += S4_R) {
-                float kk[S4_R];
+                float kk[S4_R / NSUB];
 #pragma unroll
                 for (int r = 0; r < S4_R; ++r) {
                     const int li = l0 - jc - S4_R + r;
-                    win[r] = (li >= 0) ? us[li * S4_CH + lane] : 0.f;
-                    const int j = jc + r;
-                    kk[r] = (j < L) ? (KS ? ks[j * S4_CH + lane] : __ldg(Kh + (int64_t)j * s.H)) : 0.f;
+                    win[r] = (li >= 0) ? us[li * CH + ch] : 0.f;
                 }
 #pragma unroll
-                for (int jj = 0; jj < S4_R; ++jj)
+                for (int i = 0; i < S4_R / NSUB; ++i) {
+                    const int j = jc + sub + NSUB * i;
+                    kk[i] = (j < L) ? (KS ? ks[j * CH + ch] : __ldg(Kh + (int64_t)j * s.H)) : 0.f;
+                }
 #pragma unroll
-                    for (int r = 0; r < S4_R; ++r) acc[r] = fmaf(kk[jj], win[S4_R + r - jj], acc[r]);
+                for (int i = 0; i < S4_R / NSUB; ++i) {
+#pragma unroll
+                    for (int r = 0; r < S4_R; ++r) {
+                        // tap jj = sub + NSUB*i : window index S4_R + r - jj.  `sub` is 0 when NSUB == 1, else 0/1: select
+                        const float wv = (NSUB == 1) ? win[S4_R + r - i] : (sub ? win[S4_R + r - 1 - NSUB * i] : win[S4_R + r - NSUB * i]);
+                        acc[r] = fmaf(kk[i], wv, acc[r]);
+                    }
+                }
 #pragma unroll
                 for (int r = 0; r < S4_R; ++r) win[S4_R + r] = win[r];
             }
+            if (NSUB == 2) {
 #pragma unroll
-            for (int r = 0; r < S4_R; ++r) {
-                const int li = l0 + r;
-                if (li < L) yb[(int64_t)li * s.ldy] = gelu_f(acc[r] + Dh * us[li * S4_CH + lane]);
+                for (int r = 0; r < S4_R; ++r) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], 16);
+            }
+            if (sub == 0) {
+#pragma unroll
+                for (int r = 0; r < S4_R; ++r) {
+                    const int li = l0 + r;
+                    if (li < L) yb[(int64_t)li * s.ldy] = gelu_f(acc[r] + Dh * us[li * CH + ch]);
+                }
             }
         }
     }
 }
 
 int launch_s4conv(const DeviceInfo& dev, const mugd_s4conv& s, cudaStream_t st, int* launches) {
-    MUGD_REQUIRE(s.B > 0 && s.L > 0 && s.H > 0 && s.H % S4_CH == 0, "s4conv: H=%d must be a positive multiple of %d", s.H, S4_CH);
+    MUGD_REQUIRE(s.B > 0 && s.L > 0 && s.H > 0 && s.H % 32 == 0, "s4conv: H=%d must be a positive multiple of 32", s.H);
     MUGD_REQUIRE(s.ldu >= s.H && s.ldy >= s.H, "s4conv: ld < H");
-    const size_t smem_u = (size_t)s.L * S4_CH * sizeof(float);
-    MUGD_REQUIRE((int)smem_u <= dev.max_smem_optin, "s4conv: L=%d needs %zu B of shared memory (max %d)", s.L, smem_u, dev.max_smem_optin);
-    const bool ks = 2 * smem_u <= (size_t)dev.max_smem_optin;
+    const size_t tile32 = (size_t)s.L * 32 * sizeof(float);
+    MUGD_REQUIRE((int)tile32 <= dev.max_smem_optin, "s4conv: L=%d needs %zu B of shared memory (max %d)", s.L, tile32, dev.max_smem_optin);
+    // 0: u+K tiles of 32 channels; 1: u+K tiles of 16 channels; 2: u tile of 32 channels, K through L1
+    const int variant = (2 * tile32 <= (size_t)dev.max_smem_optin) ? 0 : (tile32 <= (size_t)dev.max_smem_optin ? 1 : 2);
     static bool configured = false;
     if (!configured) {
-        MUGD_CHECK_CUDA(cudaFuncSetAttribute(s4conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.max_smem_optin));
-        MUGD_CHECK_CUDA(cudaFuncSetAttribute(s4conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.max_smem_optin));
+        MUGD_CHECK_CUDA(cudaFuncSetAttribute(s4conv_kernel<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.max_smem_optin));
+        MUGD_CHECK_CUDA(cudaFuncSetAttribute(s4conv_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.max_smem_optin));
+        MUGD_CHECK_CUDA(cudaFuncSetAttribute(s4conv_kernel<false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.max_smem_optin));
         configured = true;
     }
-    const int base = (s.H / S4_CH) * s.B;
+    const int ch = variant == 1 ? 16 : 32;
+    const int base = (s.H / ch) * s.B;
     const int npairs = ((s.L + S4_R - 1) / S4_R + 1) / 2;
     int nsplit = 1;
     while (base * nsplit < 2 * dev.sm_count && nsplit * 2 * S4_WARPS <= npairs && nsplit < 16) nsplit *= 2;
-    dim3 grid(s.H / S4_CH, s.B, nsplit);
-    if (ks) MUGD_CHECK_CUDA(launch_k(s4conv_kernel<true>, grid, dim3(S4_CH * S4_WARPS), 2 * smem_u, st, s, nsplit));
-    else MUGD_CHECK_CUDA(launch_k(s4conv_kernel<false>, grid, dim3(S4_CH * S4_WARPS), smem_u, st, s, nsplit));
+    dim3 grid(s.H / ch, s.B, nsplit);
+    if (variant == 0) MUGD_CHECK_CUDA(launch_k(s4conv_kernel<true, 32>, grid, dim3(32 * S4_WARPS), 2 * tile32, st, s, nsplit));
+    else if (variant == 1) MUGD_CHECK_CUDA(launch_k(s4conv_kernel<true, 16>, grid, dim3(32 * S4_WARPS), tile32, st, s, nsplit));
+    else MUGD_CHECK_CUDA(launch_k(s4conv_kernel<false, 32>, grid, dim3(32 * S4_WARPS), tile32, st, s, nsplit));
     if (launches) *launches += 1;
     return MUGD_OK;
 }

@@ -66,6 +66,22 @@ def test_unet_forward_vs_oracle_other_batch():
     assert rel_err(eps, ref) < 1e-4
 
 
+@pytest.mark.parametrize("L,B", [(32, 3), (224, 2), (64, 5)])
+def test_unet_forward_small_and_ragged_lengths(L, B):
+    """shortest legal chart (L=32 -> level lengths 32/16/8/4), lengths that are not multiples of the 128-row GEMM tile
+    (224 -> 224/112/56/28: partial tiles and several samples per tile), odd batch: live oracle"""
+    sd = synth.synthetic_state_dict(L)
+    m = model_for(L)
+    inp = synth.synthetic_inputs(B, L, seed=7 + L)
+    t = torch.arange(B) * 211 + 3
+    with torch.no_grad():
+        ref = orc.unet_forward(sd, inp["x_T"], t, inp["c"], inp["w"])
+        zref = orc.decoder_forward(sd, inp["x_T"])
+    eps = m.model.forward(inp["x_T"].cuda(), t.cuda(), inp["c"].cuda(), [w.cuda() for w in inp["w"]])
+    assert rel_err(eps, ref) < 1e-4
+    assert rel_err(m.model.decode(inp["x_T"].cuda()), zref) < 1e-4
+
+
 def _notes_match(logits, ref_logits, tol_abs):
     mine, ref = orc.notes_from_logits(logits.cpu()), orc.notes_from_logits(ref_logits)
     flips = mine != ref
