@@ -375,6 +375,34 @@ def main():
                note=f"one sampler.sample(S={K}) + decode request per GPU from pinned host inputs to host logits; "
                     f"{n_steps_e2e} DDIM steps; per-step bytes = request bytes / steps")
 
+    # ---- secondary numbers SURVEY §8d asks for: the same loop without guidance (scale 1 -> Beff = B) and the decode ----
+    secondary = None
+    if rank == 0:
+        def timed_request(scale, S2):
+            c = host["c"].to(dev); uc = host["uc"].to(dev); w = [t.to(dev) for t in host["w"]]; xT = host["x_T"].to(dev)
+            sampler.sample(S=2, c=c, w=w, batch_size=B, shape=(16, L), verbose=False, x_T=xT, eta=0.0, unconditional_guidance_scale=scale,
+                           unconditional_conditioning=uc, tqdm_class=_NoBar)                      # session build + capture
+            b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            b0.record()
+            z, _ = sampler.sample(S=S2, c=c, w=w, batch_size=B, shape=(16, L), verbose=False, x_T=xT, eta=0.0,
+                                  unconditional_guidance_scale=scale, unconditional_conditioning=uc, tqdm_class=_NoBar)
+            b1.record()
+            torch.cuda.synchronize()
+            return z, len(sampler.ddim_timesteps) / (b0.elapsed_time(b1) / 1000.0)
+        z, v_nocfg = timed_request(1.0, 50)
+        model.model.decode(z)
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        d0.record()
+        for _ in range(3):
+            model.model.decode(z)
+        d1.record()
+        torch.cuda.synchronize()
+        secondary = dict(steps_per_s_without_cfg=v_nocfg, unet_batch_without_cfg=B,
+                         note_steps="sampler.sample(S=50, scale=1.0) through the public API incl. per-request setup",
+                         decode_ms=d0.elapsed_time(d1) / 3, decode_note=f"model.model.decode of {B} latents [16,{L}] -> logits [16,{8 * L}]")
+
     # ---- CPU baseline (rank 0, N=1 only, bounded sample) ------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -389,7 +417,7 @@ def main():
                                 cfg_scale=wl["scale"], schedule_S=S, gemm_impl=eng.gemm_impl, parallelism=f"replica-sharded batch x{world}",
                                 l2="working set exceeds L2: 421 MB of fp32 weights are streamed every step",
                                 gflop_per_step=Beff * GFLOP_PER_EVAL.get(L, 0.0), outputs_finite=finite),
-                    roofline=roof, cpu_baseline=cpu, e2e=e2e, gpu_launches=launches_per_step * args.steps,
+                    roofline=roof, cpu_baseline=cpu, e2e=e2e, secondary=secondary, gpu_launches=launches_per_step * args.steps,
                     launches_per_step=launches_per_step, clocks=clock_info)
         print(json.dumps(line))
     if world > 1:

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MUGD_ABI_VERSION 5
+#define MUGD_ABI_VERSION 6
 
 typedef struct mugd_handle mugd_handle;   /* one device + scratch state            */
 typedef struct mugd_plan mugd_plan;       /* validated launch plan (+ CUDA graph)  */
@@ -50,7 +50,8 @@ enum mugd_op_kind {
     MUGD_OP_DDIM_UPDATE = 6,   /* CFG combine + x_{t-1} update                                              */
     MUGD_OP_TRANSPOSE = 7,     /* [B,C,L] <-> [B,L,C] with leading dimensions                                */
     MUGD_OP_COPY2D = 8,        /* strided row copy                                                           */
-    MUGD_OP_STEP_ADVANCE = 9   /* *step += 1                                                                 */
+    MUGD_OP_STEP_ADVANCE = 9,  /* *step += 1                                                                 */
+    MUGD_OP_NOTES = 10         /* decoder logits -> ordered note list (OsuManiaConvertor.array_to_objects)   */
 };
 
 /* A-operand row addressing of MUGD_OP_GEMM (rows are tokens of B samples, Lout output rows each) */
@@ -145,12 +146,23 @@ typedef struct mugd_copy2d {
 
 typedef struct mugd_step_advance { int32_t* step; } mugd_step_advance;
 
+/* Note extraction, mug/data/convertor.py:232-264 (from_logits): for key column c of chart b a note starts at every frame
+ * t with logit[t][c] > 0; start = round((t + clip(logit[t][K+c],0,1)) * frame_ms); it is a long note when the following
+ * frames have logit[.][2K+c] > 0 and no new start, end = round((t_end + clip(logit[t_end][3K+c],0,1)) * frame_ms), else -1.
+ * Output is compact and ordered by frame per (chart, column): count[b*K+c], start_ms/end_ms[(b*K+c)*T + i]. */
+typedef struct mugd_notes {
+    const float* logits; int64_t ld;       /* [B*T, 4K] channels-last decoder output                        */
+    int32_t* count; int32_t* start_ms; int32_t* end_ms;
+    double frame_ms;
+    int32_t B, T, K;
+} mugd_notes;
+
 typedef struct mugd_op {
     int32_t kind;
     int32_t tag;                           /* free for the host (profiling labels)                          */
     union {
         mugd_gemm gemm; mugd_groupnorm gn; mugd_layernorm ln; mugd_attention attn; mugd_s4conv s4;
-        mugd_ddim_update ddim; mugd_transpose tr; mugd_copy2d cp; mugd_step_advance adv;
+        mugd_ddim_update ddim; mugd_transpose tr; mugd_copy2d cp; mugd_step_advance adv; mugd_notes notes;
     } u;
 } mugd_op;
 
@@ -212,7 +224,7 @@ int  mugd_debug_set_tc_timing(long long* device_buf4);
 /* ---- utility ---------------------------------------------------------------------------------- */
 int  mugd_fill_i32(int32_t* dst, int32_t value, void* stream);
 /* sizeof() of {mugd_op, mugd_gemm, mugd_groupnorm, mugd_layernorm, mugd_attention, mugd_s4conv,
- * mugd_ddim_update, mugd_transpose, mugd_copy2d} so a foreign-language mirror can verify its layout */
+ * mugd_ddim_update, mugd_transpose, mugd_copy2d, mugd_notes} so a foreign-language mirror can verify its layout */
 int  mugd_abi_sizes(int32_t* out, int32_t n);
 
 #ifdef __cplusplus

@@ -134,6 +134,70 @@ int launch_step_advance(const DeviceInfo&, const mugd_step_advance& a, cudaStrea
     return MUGD_OK;
 }
 
+// ---- note extraction: OsuManiaConvertor.array_to_objects, mug/data/convertor.py:232-264 -------------
+// One CTA per (key column, chart).  Frames are visited in order in chunks of 256; the notes found in a chunk are
+// compacted with a ballot/prefix scan so the output is ordered by frame like the reference's np.where loop.
+__global__ void __launch_bounds__(256)
+notes_kernel(const mugd_notes n) {
+    pdl_trigger();
+    pdl_wait();
+    const int c = blockIdx.x, b = blockIdx.y;
+    const int K = n.K, T = n.T;
+    const float* Lg = n.logits + (int64_t)b * T * n.ld;
+    int32_t* st_out = n.start_ms + ((int64_t)b * K + c) * T;
+    int32_t* en_out = n.end_ms + ((int64_t)b * K + c) * T;
+    __shared__ int warp_cnt[8];
+    __shared__ int base_s;
+    if (threadIdx.x == 0) base_s = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int t0 = 0; t0 < T; t0 += 256) {
+        const int t = t0 + threadIdx.x;
+        bool is = false;
+        int start = 0, end = -1;
+        if (t < T && Lg[(int64_t)t * n.ld + c] > 0.f) {
+            is = true;
+            const float so = fminf(fmaxf(Lg[(int64_t)t * n.ld + K + c], 0.f), 1.f);
+            start = (int)rint(((double)t + (double)so) * n.frame_ms);           // python round(): half to even
+            if (t != T - 1) {
+                int i = t + 1;
+                while (i < T && Lg[(int64_t)i * n.ld + 2 * K + c] > 0.f && !(Lg[(int64_t)i * n.ld + c] > 0.f)) ++i;
+                const int ei = i - 1;
+                if (ei != t) {
+                    const float eo = fminf(fmaxf(Lg[(int64_t)ei * n.ld + 3 * K + c], 0.f), 1.f);
+                    end = (int)rint(((double)ei + (double)eo) * n.frame_ms);
+                }
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, is);
+        if (lane == 0) warp_cnt[warp] = __popc(m);
+        __syncthreads();
+        int off = base_s;
+        for (int w = 0; w < warp; ++w) off += warp_cnt[w];
+        if (is) {
+            const int pos = off + __popc(m & ((1u << lane) - 1u));
+            st_out[pos] = start;
+            en_out[pos] = end;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int tot = 0;
+            for (int w = 0; w < 8; ++w) tot += warp_cnt[w];
+            base_s += tot;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) n.count[b * K + c] = base_s;
+}
+
+int launch_notes(const DeviceInfo&, const mugd_notes& n, cudaStream_t st, int* launches) {
+    MUGD_REQUIRE(n.B > 0 && n.T > 0 && n.K > 0 && n.K <= 16 && n.ld >= 4 * n.K, "notes: bad shape B=%d T=%d K=%d", n.B, n.T, n.K);
+    MUGD_REQUIRE(n.logits && n.count && n.start_ms && n.end_ms && n.frame_ms > 0, "notes: null argument");
+    MUGD_CHECK_CUDA(launch_k(notes_kernel, dim3(n.K, n.B), dim3(256), 0, st, n));
+    if (launches) *launches += 1;
+    return MUGD_OK;
+}
+
 }  // namespace mugd
 
 extern "C" int mugd_fill_i32(int32_t* dst, int32_t value, void* stream) {

@@ -330,6 +330,26 @@ class DecoderSession:
         self.plan = Plan(engine, res["ops"])
         self.arena_bytes = nbytes
 
+    def notes(self, frame_ms: float, key_count: int = 4):
+        """Note extraction on the logits of the last ``decode`` (still resident, channels-last): returns
+        (count [B,K], start_ms [B,K,T], end_ms [B,K,T]) as CPU int32 tensors; only count and the used prefixes matter."""
+        eng = self.engine
+        B, T, K = self.B, self.Lout, key_count
+        assert 4 * K == eng.cfg.decoder.x_channels
+        cnt = torch.zeros(B, K, dtype=torch.int32, device=eng.device)
+        st = torch.full((B, K, T), -1, dtype=torch.int32, device=eng.device)
+        en = torch.full((B, K, T), -1, dtype=torch.int32, device=eng.device)
+        d = L_.Notes()
+        d.logits, d.ld = self.logits.ptr, self.logits.ld
+        d.count, d.start_ms, d.end_ms = _ptr(cnt), _ptr(st), _ptr(en)
+        d.frame_ms, d.B, d.T, d.K = float(frame_ms), B, T, K
+        ops = OpList()
+        ops.add(L_.OP_NOTES, d)
+        eng.run_ops(ops)
+        cnt_c = cnt.cpu()
+        nmax = int(cnt_c.max()) if cnt_c.numel() else 0
+        return cnt_c, st[:, :, :max(nmax, 1)].cpu(), en[:, :, :max(nmax, 1)].cpu()
+
     def decode(self, z: torch.Tensor) -> torch.Tensor:
         eng = self.engine
         cfg = eng.cfg.decoder
@@ -362,6 +382,24 @@ def s4_fft_nodes(L_int: int) -> torch.Tensor:
         t = torch.view_as_real(base ** torch.arange(0, L_int // 2 + 1)).contiguous()
         _NODE_CACHE[L_int] = t
     return t
+
+
+def hit_object_lines(count, start_ms, end_ms, key_count: int):
+    """Per chart: the .osu hit-object lines of OsuManiaConvertor.array_to_objects (convertor.py:257-264) from the
+    compact (column, frame-ordered) note lists the GPU produced; sorted by start time with a stable sort, like the reference."""
+    width = int(512 / key_count)
+    charts = []
+    for b in range(count.shape[0]):
+        items = []
+        for col in range(key_count):
+            n = int(count[b, col])
+            x = int(round((col + 0.5) * width))
+            for s_, e_ in zip(start_ms[b, col, :n].tolist(), end_ms[b, col, :n].tolist()):
+                line = f"{x},192,{s_},1,0,0:0:0:0:" if e_ == -1 else f"{x},192,{s_},128,0,{e_}:0:0:0:0:"
+                items.append((line, s_))
+        items.sort(key=lambda t: t[1])
+        charts.append([t[0] for t in items])
+    return charts
 
 
 def _all_blocks(comp: UNetCompiler):

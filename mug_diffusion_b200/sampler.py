@@ -91,6 +91,20 @@ class _Wrapper:
             return o.engine.decoder_session(B, Lz).decode(z)
 
 
+    @torch.no_grad()
+    def decode_to_hit_objects(self, z: torch.Tensor, frame_ms: float, key_count: int = 4):
+        """decode(z) followed by OsuManiaConvertor.array_to_objects (convertor.py:232-264) on the GPU: the [B,16,8L] logits
+        never leave the device, only the compact note lists do.  Returns one list of .osu hit-object lines per chart."""
+        from .runtime import hit_object_lines
+        o = self._o
+        with o.engine.lock:
+            B, _, Lz = z.shape
+            ds = o.engine.decoder_session(B, Lz)
+            ds.decode(z)
+            cnt, st, en = ds.notes(frame_ms, key_count)
+            return hit_object_lines(cnt, st, en, key_count)
+
+
 class MugDiffusionB200:
     """Drop-in for the reference ``DDPM`` object on the sampler path (attributes of SURVEY §8b)."""
 
@@ -114,6 +128,12 @@ class MugDiffusionB200:
     @classmethod
     def from_reference(cls, ddpm, device=None, gemm_impl: str = "auto") -> "MugDiffusionB200":
         """Build from a loaded reference ``DDPM`` (webui.py:83-100 / mapping.py:419-431)."""
+        sd_all, cfg = cls.config_from_reference(ddpm)
+        return cls(sd_all, cfg, int(ddpm.z_length), device, gemm_impl)
+
+    @staticmethod
+    def config_from_reference(ddpm):
+        """(state_dict on CPU, ModelConfig) read off a reference ``DDPM`` instance -- pure host logic, no GPU needed."""
         unet = ddpm.model.unet_model
         fs = ddpm.model.first_stage_model
         dd = fs.decoder
@@ -133,7 +153,7 @@ class MugDiffusionB200:
         cfg = ModelConfig(unet=UNetConfig.from_module(unet), decoder=dcfg, z_channels=int(ddpm.z_channels),
                           timesteps=int(ddpm.num_timesteps), linear_start=float(ddpm.linear_start),
                           linear_end=float(ddpm.linear_end))
-        return cls(sd_all, cfg, int(ddpm.z_length), device, gemm_impl)
+        return sd_all, cfg
 
     # the reference's q_sample, used only by the inpainting (mask) branch of ddim_sampling (ddim.py:141-144)
     def q_sample(self, x_start, t, noise=None):

@@ -385,3 +385,32 @@ def notes_from_logits(logits: torch.Tensor) -> torch.Tensor:
     OsuManiaConvertor.array_to_objects thresholds rows 0-3 (is_start) and 8-11 (is_holding) with
     ``> 0`` (from_logits) -- mug/data/convertor.py:211-216, 232-264.  Returns bool [B,8,T]."""
     return torch.cat([logits[:, 0:4], logits[:, 8:12]], dim=1) > 0
+
+
+def array_to_objects(note_array: np.ndarray, key_count: int, frame_ms: float) -> List[str]:
+    """OsuManiaConvertor.array_to_objects with from_logits=True  -- mug/data/convertor.py:211-264.
+    note_array: [4*key_count, T] decoder logits of one chart.  Returns the .osu hit-object lines sorted by start time
+    (stable), exactly as the reference writes them."""
+    a = np.asarray(note_array).transpose()                      # [T, 4K]
+    T = a.shape[0]
+    K = int(key_count)
+    width = int(512 / K)
+    out = []
+    for col in range(K):
+        for si in np.where(a[:, col] > 0)[0]:
+            so = np.clip(a[si, col + K], 0, 1)
+            start = int(round((si + so) * frame_ms))
+            end = -1
+            if si != T - 1:
+                i = si + 1
+                while i < T and a[i, col + 2 * K] > 0 and not a[i, col] > 0:
+                    i += 1
+                ei = i - 1
+                if ei != si:
+                    eo = np.clip(a[ei, col + 3 * K], 0, 1)
+                    end = int(round((ei + eo) * frame_ms))
+            x = int(round((col + 0.5) * width))
+            line = f"{x},192,{start},1,0,0:0:0:0:" if end == -1 else f"{x},192,{start},128,0,{end}:0:0:0:0:"
+            out.append((line, start))
+    out.sort(key=lambda t: t[1])
+    return [t[0] for t in out]

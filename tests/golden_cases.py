@@ -75,3 +75,18 @@ def attn_core_inputs(name: str, case: dict):
 def load_golden(path):
     with np.load(path) as z:
         return {k: torch.from_numpy(z[k]) for k in z.files}
+
+
+def synthetic_note_logits(B: int = 3, T: int = 700, seed: int = 9) -> torch.Tensor:
+    """[B,16,T] logits that hit the corner cases of array_to_objects: dense starts, long notes that run into the last
+    frame, a start on the last frame, holds interrupted by a new start, offsets outside [0,1] (clipped)."""
+    x = synth._gauss(synth._rng(seed, "notes"), (B, 16, T)) * 1.5
+    x[:, 0:4] -= 1.2                       # starts are sparse
+    x[:, 8:12] += 0.8                      # holds are common -> long notes
+    x[:, 4:8] = x[:, 4:8] * 2.0            # offsets beyond [0,1] -> clip
+    x[0, 0, T - 1] = 2.0                   # start on the last frame
+    x[1, 1, T - 40:] = -1.0
+    x[1, 1, T - 40] = 3.0                  # long note running to the end
+    x[1, 9, T - 39:] = 2.0
+    x[2, 2, 10:20] = 1.0                   # back-to-back starts
+    return x

@@ -155,3 +155,16 @@ def test_eta_noise_path_runs_and_is_seeded():
                               x_T=inp["x_T"].cuda(), eta=1.0, shape=(16, L))
         outs.append(z)
     assert torch.isfinite(outs[0]).all() and torch.equal(outs[0], outs[1])
+
+
+def test_mask_branch_with_zero_mask_is_identity():
+    """ddim.py:141-144 inpainting blend x = q_sample(x0,t)*mask + (1-mask)*x : with mask == 0 the trajectory must equal
+    the unmasked one bit for bit (the noisy x0 is multiplied by zero), which exercises the per-step host round trip"""
+    L, B = 96, 1
+    m = model_for(L)
+    inp = synth.synthetic_inputs(B, L)
+    sampler = DDIMSampler(m)
+    kw = dict(S=4, c=inp["c"].cuda(), w=[w.cuda() for w in inp["w"]], batch_size=B, verbose=False, x_T=inp["x_T"].cuda(), shape=(16, L))
+    z0, _ = sampler.sample(**kw)
+    z1, _ = sampler.sample(mask=torch.zeros(B, 16, L).cuda(), x0=torch.ones(B, 16, L).cuda(), **kw)
+    assert torch.equal(z0, z1)

@@ -125,6 +125,26 @@ def make_s4_lengthen():
 
 
 
+def make_hit_objects():
+    """OsuManiaConvertor.array_to_objects of the UNMODIFIED reference on the golden decoder logits (and on a synthetic
+    logit array that exercises long notes running to the last frame, back-to-back starts and clipped offsets)."""
+    import json
+    ref_shim.install_shims()
+    from mug.data.convertor import BeatmapMeta, OsuManiaConvertor
+    frame_ms = 512 / 4 / 22050 * 8 * 1000          # webui.py:341-342 hop 128 @ 22.05 kHz x audio_note_window_ratio 8
+    conv = OsuManiaConvertor(frame_ms=frame_ms, max_frame=4096, from_logits=True)
+    meta = BeatmapMeta(path="", cs=4)
+    out = {"frame_ms": frame_ms}
+    for name in ("ddim_L512_B1_S50_cfg5", "ddim_L96_B2_S10_cfg5"):
+        lg = gc.load_golden(os.path.join(GOLD, name + ".npz"))["logits"].numpy()
+        out[name] = [conv.array_to_objects(lg[b], meta) for b in range(lg.shape[0])]
+    syn = gc.synthetic_note_logits().numpy()
+    out["synthetic"] = [conv.array_to_objects(syn[b], meta) for b in range(syn.shape[0])]
+    with open(os.path.join(GOLD, "hit_objects.json"), "w") as f:
+        json.dump(out, f)
+    print("wrote hit_objects.json", {k: (len(v) if isinstance(v, list) else v) for k, v in out.items()}, [len(c) for c in out["synthetic"]])
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
@@ -139,5 +159,7 @@ if __name__ == "__main__":
         make_ddim()
     if a.only in (None, "s4len"):
         make_s4_lengthen()
+    if a.only in (None, "notes"):
+        make_hit_objects()
 
 
