@@ -88,7 +88,8 @@ typedef struct mugd_gemm {
     int32_t act, gate, impl;
     int32_t split_k;                       /* tensor-core path: 0 = auto, >0 forces the K split            */
     int32_t n_counters;                    /* entries available in `counters`                              */
-    int32_t tap_shift;                     /* MUGD_CONV_TAPS: source row of tap t is l + t + tap_shift     */
+    int32_t tap_shift;                     /* MUGD_CONV_TAPS: source row of tap t is l + (t + tap_shift) * dilation */
+    int32_t tap_dilation;                  /* MUGD_CONV_TAPS: 0/1 = dense taps; d = dilated conv (wave.py:425-433)  */
     void* workspace; int64_t workspace_bytes; /* split-K partial tiles (see mugd_gemm_tc_query)            */
     int32_t* counters;                     /* zero-initialised tile tickets, left zero by every launch     */
 } mugd_gemm;

@@ -22,7 +22,7 @@ struct GemmParams {
     int nk;  // total k-steps = taps*K/16
 };
 
-__device__ __forceinline__ int conv_src_row(int mode, int l, int t, int Lin, int Lout, int tap_shift) {
+__device__ __forceinline__ int conv_src_row(int mode, int l, int t, int Lin, int Lout, int tap_shift, int dil) {
     // returns source row inside the sample or -1 for the zero padding
     if (mode == MUGD_CONV_NONE) return l;
     if (mode == MUGD_CONV_SAME) {
@@ -34,7 +34,7 @@ __device__ __forceinline__ int conv_src_row(int mode, int l, int t, int Lin, int
         return (r < Lin) ? r : -1;
     }
     if (mode == MUGD_CONV_TAPS) {
-        const int r = l + t + tap_shift;
+        const int r = l + (t + tap_shift) * dil;
         return (r >= 0 && r < Lin) ? r : -1;
     }
     // MUGD_CONV_UP: index on the x2-upsampled axis, then halve
@@ -86,7 +86,7 @@ gemm_simt_kernel(const GemmParams p) {
         for (int r = 0; r < RM; ++r) {
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (a_b[r] >= 0) {
-                const int src = conv_src_row(g.conv_mode, a_l[r], t, g.Lin, g.Lout, g.tap_shift);
+                const int src = conv_src_row(g.conv_mode, a_l[r], t, g.Lin, g.Lout, g.tap_shift, g.tap_dilation > 1 ? g.tap_dilation : 1);
                 if (src >= 0) v = ld_f4(g.A + ((int64_t)a_b[r] * g.Lin + src) * g.lda + k0 + a_kq * 4);
             }
             ra[r] = v;

@@ -338,7 +338,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const CUtensorMap* ma = &tmA;
                 int lshift = 0;
                 if (g.conv_mode == MUGD_CONV_SAME) lshift = t - 1;
-                else if (g.conv_mode == MUGD_CONV_TAPS) lshift = t + g.tap_shift;
+                else if (g.conv_mode == MUGD_CONV_TAPS) lshift = (t + g.tap_shift) * (g.tap_dilation > 1 ? g.tap_dilation : 1);
                 else if (g.conv_mode == MUGD_CONV_DOWN) ma = (t == 0) ? &tmA : (t == 1 ? &tmA1 : &tmA2);
                 tma_load_3d(a_hi(s), ma, bar_full(s), kb * TC_BK, l_base + lshift, b_base);
                 tma_load_2d(b_hi(s), &tmWhi, bar_full(s), t * g.K + kb * TC_BK, n0);

@@ -90,7 +90,7 @@ class OpList:
              mode: int = L_.CONV_NONE, Lin: int = 0, Lout: int = 0, act: int = L_.ACT_NONE,
              gate: int = L_.GATE_NONE, residual: Optional[View] = None, rowvec: int = 0,
              rowvec_b_stride: int = 0, rowvec_step_stride: int = 0, step: int = 0, impl: int = L_.GEMM_AUTO,
-             W_hi: int = 0, W_lo: int = 0, split_k: int = 0, tap_shift: int = 0, tag: int = 0):
+             W_hi: int = 0, W_lo: int = 0, split_k: int = 0, tap_shift: int = 0, dilation: int = 1, tag: int = 0):
         g = L_.Gemm()
         M = out.rows
         g.A, g.lda = A.ptr, A.ld
@@ -99,6 +99,7 @@ class OpList:
         g.W, g.W_hi, g.W_lo, g.bias = W, W_hi or None, W_lo or None, bias or None
         g.split_k = split_k
         g.tap_shift = tap_shift
+        g.tap_dilation = dilation
         g.rowvec, g.rowvec_b_stride, g.rowvec_step_stride = rowvec or None, rowvec_b_stride, rowvec_step_stride
         g.step = step or None
         if residual is not None:

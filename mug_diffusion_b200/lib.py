@@ -30,7 +30,7 @@ class Gemm(C.Structure):
                 ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
                 ("taps", C.c_int32), ("conv_mode", C.c_int32), ("Lin", C.c_int32), ("Lout", C.c_int32),
                 ("act", C.c_int32), ("gate", C.c_int32), ("impl", C.c_int32),
-                ("split_k", C.c_int32), ("n_counters", C.c_int32), ("tap_shift", C.c_int32),
+                ("split_k", C.c_int32), ("n_counters", C.c_int32), ("tap_shift", C.c_int32), ("tap_dilation", C.c_int32),
                 ("workspace", _f), ("workspace_bytes", C.c_int64), ("counters", _f)]
 
 

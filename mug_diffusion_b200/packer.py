@@ -201,7 +201,7 @@ def all_unet_blocks(cfg: UNetConfig, prefix: str) -> List[Block]:
 
 def pack_model(sd: Dict[str, torch.Tensor], ucfg: UNetConfig, dcfg: DecoderConfig,
                unet_prefix: str = "model.unet_model.", dec_prefix: str = "model.first_stage_model.decoder.",
-               tensor_core_split: bool = True) -> WeightBlob:
+               tensor_core_split: bool = True, wave_cfg=None) -> WeightBlob:
     blob = WeightBlob()
     up = unet_prefix
     for n in ("time_embed.0.", "time_embed.2."):
@@ -223,6 +223,9 @@ def pack_model(sd: Dict[str, torch.Tensor], ucfg: UNetConfig, dcfg: DecoderConfi
         _pack_block(blob, sd, b)
     for b in decoder_layout(dcfg, dec_prefix):
         _pack_block(blob, sd, b)
+    if wave_cfg is not None or any(k.startswith("model.wave_model.") for k in sd):
+        from .wave import WaveConfig, pack_wave            # the audio encoder, once per request
+        pack_wave(blob, sd, wave_cfg or WaveConfig())
     if tensor_core_split:
         # pre-split every GEMM weight the tcgen05 kernel can take (K per tap % 32 == 0, N >= 64) into TF32 hi/lo
         for name in list(blob.entries):

@@ -112,6 +112,18 @@ class MugEngine:
             self.sessions[key] = s
         return s
 
+    def wave_session(self, B: int, T: int):
+        """Audio encoder plan for B mel-spectrograms of T frames; needs wave weights in the blob."""
+        if "wave_cfg" not in self.blob.meta:
+            raise L_.MugdError("this engine was packed without model.wave_model.* weights")
+        from .wave import WaveSession
+        key = ("wave", B, T)
+        s = self.dec_sessions.get(key)
+        if s is None:
+            s = WaveSession(self, B, T)
+            self.dec_sessions[key] = s
+        return s
+
     def decoder_session(self, B: int, Lz: int) -> "DecoderSession":
         key = (B, Lz)
         s = self.dec_sessions.get(key)

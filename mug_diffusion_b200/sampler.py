@@ -92,6 +92,16 @@ class _Wrapper:
 
 
     @torch.no_grad()
+    def wave_model(self, mel: torch.Tensor):
+        """Stands where ``model.model.wave_model`` stands (webui.py:371-374): MelspectrogramScaleEncoder1D.forward on the
+        GPU (mug/cond/wave.py:453-467).  Returns the 10-entry list the reference returns; entries the U-Net never reads
+        (all but the last four, unet.py:527-543) are None."""
+        o = self._o
+        with o.engine.lock:
+            B, _, T = mel.shape
+            return o.engine.wave_session(B, T).encode(mel)
+
+    @torch.no_grad()
     def decode_to_hit_objects(self, z: torch.Tensor, frame_ms: float, key_count: int = 4):
         """decode(z) followed by OsuManiaConvertor.array_to_objects (convertor.py:232-264) on the GPU: the [B,16,8L] logits
         never leave the device, only the compact note lists do.  Returns one list of .osu hit-object lines per chart."""

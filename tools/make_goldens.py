@@ -125,6 +125,20 @@ def make_s4_lengthen():
 
 
 
+@torch.no_grad()
+def make_wave():
+    """the reference audio encoder (wave.py:398-467) on a synthetic mel, T = 64 * 96 frames: last four level outputs"""
+    from mug_diffusion_b200 import wave as mwave
+    model, _ = ref_shim.load_reference_model()
+    wsd = mwave.synthetic_wave_state_dict()
+    missing, unexpected = model.load_state_dict(wsd, strict=False)
+    assert not [k for k in missing if k.startswith("model.wave_model.")] and not unexpected
+    mel = mwave.synthetic_mel(2, 64 * 96)
+    hs = model.model.wave_model(mel)
+    save("wave_T6144_B2", **{f"h{i}": hs[i].numpy() for i in range(6, 10)})
+    print([tuple(h.shape) for h in hs])
+
+
 def make_hit_objects():
     """OsuManiaConvertor.array_to_objects of the UNMODIFIED reference on the golden decoder logits (and on a synthetic
     logit array that exercises long notes running to the last frame, back-to-back starts and clipped offsets)."""
@@ -159,6 +173,8 @@ if __name__ == "__main__":
         make_ddim()
     if a.only in (None, "s4len"):
         make_s4_lengthen()
+    if a.only in (None, "wave"):
+        make_wave()
     if a.only in (None, "notes"):
         make_hit_objects()
 
