@@ -215,6 +215,10 @@ int  mugd_set_tc_cluster_reduce(int enabled);
  * 0 = both operands from shared memory (SS form) */
 int  mugd_set_tc_a_in_tmem(int enabled);
 
+/* split-K with at most `max_splits` parts is reduced inside the GEMM kernel by the last-arriving CTA of each tile (needs the
+ * `counters` of mugd_gemm); larger splits use the parallel reduce kernel.  0 (default) disables: measured slower on B200. */
+int  mugd_set_tc_inkernel_reduce_max(int max_splits);
+
 /* experiments: force the tensor-core tile width (128 or 256) where legal; 0 = cost model */
 int  mugd_debug_set_tc_tile_n(int bn);
 

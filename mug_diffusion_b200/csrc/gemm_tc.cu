@@ -45,6 +45,7 @@ struct TcParams {
     int32_t Lrows, Bs;        // row structure of the A tensor map (Lrows = rows per sample, Bs samples)
     int32_t box_l, box_b;     // TMA box: box_l rows of box_b consecutive samples (box_l*box_b <= 128)
     int32_t tiles_per_sample; // when Lrows >= 128
+    int32_t inkernel_reduce;  // split-K: the last-arriving CTA of a tile reduces it (few splits), no second launch
     int32_t cluster;          // split-K CTAs of a tile form a thread-block cluster and reduce through DSMEM
     long long* dbg;           // optional: CTA (0,0,0) writes globaltimer stamps {entry, setup done, accumulator ready, tile staged, epilogue done}
 };
@@ -507,6 +508,46 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                 for (int u = 0; u < U; ++u) st_f4(wsp + (i0 + u * TC_THREADS + (int)threadIdx.x) * 4, acc[u]);   // [row][BN] dense
             }
+            if (p.inkernel_reduce) {
+                // Few splits: the CTA that arrives last at the tile's ticket sums all partial tiles (fixed split order ->
+                // deterministic) straight out of L2 and runs the epilogue; nobody waits, so there is no co-residency
+                // requirement, and the second launch is saved.  Many splits keep the fully parallel reduce kernel.
+                __shared__ int s_ticket;
+                __threadfence();
+                __syncthreads();
+                if (threadIdx.x == 0) s_ticket = atomicAdd(p.counters + tile_lin, 1);
+                __syncthreads();
+                if (s_ticket == p.splits - 1) {
+                    __threadfence();
+                    const float* wst = p.ws + ((int64_t)tile_lin * p.splits) * (TC_BM * BN);
+#pragma unroll 1
+                    for (int i0 = 0; i0 < TC_BM * C4; i0 += TC_THREADS * 4) {
+                        float4 sum[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) sum[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        for (int z = 0; z < p.splits; ++z) {
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const float4 t4 = __ldcg(reinterpret_cast<const float4*>(
+                                    wst + (int64_t)z * (TC_BM * BN) + (int64_t)(i0 + u * TC_THREADS + (int)threadIdx.x) * 4));
+                                sum[u].x += t4.x; sum[u].y += t4.y; sum[u].z += t4.z; sum[u].w += t4.w;
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int idx = i0 + u * TC_THREADS + (int)threadIdx.x;
+                            const int row = idx / C4, c4 = idx - row * C4;
+                            const int m = m_base + row, nn = n0 + c4 * 4;
+                            if (row < rows_valid && m < g.M && nn < g.N) {
+#define TC_CALL_EPI(A_, G_) tc_epi4<A_, G_>(g, sum[u], m, nn, rowvec)
+                                TC_DISPATCH_EPI(g, TC_CALL_EPI);
+#undef TC_CALL_EPI
+                            }
+                        }
+                    }
+                    if (threadIdx.x == 0) p.counters[tile_lin] = 0;          // ticket back to rest for the next launch / replay
+                }
+            }
         } else {
 #define TC_CALL_STORE(A_, G_) tc_store_tile<BN, A_, G_>(g, stage, m_base, n0, rows_valid, rowvec)
             TC_DISPATCH_EPI(g, TC_CALL_STORE);
@@ -566,6 +607,10 @@ gemm_tc_reduce_kernel(const TcParams p, int gx, int gy) {
 
 static long long* g_tc_dbg = nullptr;
 static bool g_tc_a_in_tmem = true;   // A operand of the MMAs from tensor memory (TS form) instead of shared memory (SS)
+// Split counts up to this value reduce inside the GEMM kernel (last-arriving CTA of a tile, no second launch).  Measured
+// SLOWER on B200 (GEMM family 4.17 ms vs 3.01 ms per step at 4; worse at 8/16): one CTA pulling splits x 64 KB out of L2
+// costs more than the ~3 us reduce launch -> 0 (off) by default.
+static int g_tc_inkernel_max = 0;
 static int g_tc_force_bn = 0;        // experiments: 0 = cost model, 128 / 256 = force the tile width where legal
 // Split-K reduction through a thread-block cluster + DSMEM instead of workspace + reduce kernel.  Works (tests pass)
 // but measured slower on B200: clusters of 197 KB-smem CTAs schedule poorly (8 co-resident SMs of one GPC) and DSMEM
@@ -644,7 +689,7 @@ static TcGeometry tc_geometry(const mugd_gemm& g, int sm_count, int forced_split
             if (forced_split <= 0 && sp > 1 && per < 2) break;
             if (forced_split <= 0 && sp > 1 && tiles * sp > 2 * sm_count) break;   // bounds the workspace: < 2*SMs partial tiles
             const int waves = (tiles * sp + sm_count - 1) / sm_count;
-            const float est = waves * (1.0f + kstep * per) + (sp > 1 ? (g_tc_cluster ? 2.0f : 5.0f) : 0.0f);
+            const float est = waves * (1.0f + kstep * per) + (sp > 1 ? (g_tc_cluster ? 2.0f : (sp <= g_tc_inkernel_max ? 1.0f + 0.6f * sp : 5.0f)) : 0.0f);
             if (est < best - 0.25f) { best = est; splits = sp; t.BN = bn; }
         }
     }
@@ -686,7 +731,7 @@ static int tc_launch(const CUtensorMap* tmAs, const CUtensorMap& tmWhi, const CU
         return MUGD_OK;
     }
     MUGD_CHECK_CUDA(launch_k(gemm_tc_kernel<BN, AT>, grid, dim3(TC_THREADS), TcSmem<BN, AT>::TOTAL, st, tmA, tmA1, tmA2, tmWhi, tmWlo, p));
-    if (t.splits > 1) {
+    if (t.splits > 1 && !p.inkernel_reduce) {
         const long long total = (long long)t.gx * t.gy * TC_BM * (BN / 4);
         MUGD_CHECK_CUDA(launch_k(gemm_tc_reduce_kernel<BN>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, p, t.gx, t.gy));
     }
@@ -747,6 +792,7 @@ int launch_gemm_tc(const DeviceInfo& dev, const mugd_gemm& g, cudaStream_t st, i
     p.tiles_per_sample = t.tiles_per_sample;
     p.dbg = g_tc_dbg;
     p.cluster = use_cluster ? 1 : 0;
+    p.inkernel_reduce = (!use_cluster && t.splits > 1 && t.splits <= g_tc_inkernel_max && g.counters && g.n_counters >= t.gx * t.gy) ? 1 : 0;
     int rc;
     if (g_tc_a_in_tmem)
         rc = (t.BN == 256) ? tc_launch<256, true>(tmAs, tmWhi, tmWlo, p, t, st)
@@ -755,7 +801,7 @@ int launch_gemm_tc(const DeviceInfo& dev, const mugd_gemm& g, cudaStream_t st, i
         rc = (t.BN == 256) ? tc_launch<256, false>(tmAs, tmWhi, tmWlo, p, t, st)
              : (t.BN == 128) ? tc_launch<128, false>(tmAs, tmWhi, tmWlo, p, t, st) : tc_launch<64, false>(tmAs, tmWhi, tmWlo, p, t, st);
     if (rc != MUGD_OK) return rc;
-    if (launches) *launches += (t.splits > 1 && !use_cluster) ? 2 : 1;
+    if (launches) *launches += (t.splits > 1 && !use_cluster && !p.inkernel_reduce) ? 2 : 1;
     return MUGD_OK;
 }
 
@@ -763,6 +809,11 @@ int launch_gemm_tc(const DeviceInfo& dev, const mugd_gemm& g, cudaStream_t st, i
 
 extern "C" int mugd_set_tc_a_in_tmem(int enabled) {
     mugd::g_tc_a_in_tmem = enabled != 0;
+    return MUGD_OK;
+}
+
+extern "C" int mugd_set_tc_inkernel_reduce_max(int max_splits) {
+    mugd::g_tc_inkernel_max = max_splits < 0 ? 0 : max_splits;
     return MUGD_OK;
 }
 
