@@ -197,7 +197,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="L512_B4_cfg5_S50", choices=list(WORKLOADS))
-    ap.add_argument("--gemm", default=os.environ.get("MUGD_GEMM", "auto"), choices=["auto", "simt", "tc"])
+    ap.add_argument("--gemm", default=os.environ.get("MUGD_GEMM", "auto"), choices=["auto", "simt", "tc", "tc_tf32"],
+                    help="tc_tf32 = opt-in single-pass TF32 (NOT fp32-accurate; for characterisation only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=3)
     args = ap.parse_args()

@@ -219,6 +219,14 @@ int  mugd_set_tc_a_in_tmem(int enabled);
  * `counters` of mugd_gemm); larger splits use the parallel reduce kernel.  0 (default) disables: measured slower on B200. */
 int  mugd_set_tc_inkernel_reduce_max(int max_splits);
 
+/* OPT-IN speed mode: 1 = plain TF32 products (a_hi*w_hi only, ~2^-11 relative error per product, like cuDNN's allow_tf32 that
+ * the reference's own GPU path uses for convs); 0 (default) = 3xTF32, fp32-accurate.  Parity tests and bench.py use 0. */
+int  mugd_set_tc_single_pass_tf32(int enabled);
+
+/* weight-tile TMA multicast: clusters of up to `max_cluster` (0, 2 or 4) vertically adjacent output tiles load each weight tile
+ * once from L2 and multicast it (used only when the grid oversubscribes the SMs).  Default 0 (off): measured no faster on B200. */
+int  mugd_set_tc_multicast(int max_cluster);
+
 /* experiments: force the tensor-core tile width (128 or 256) where legal; 0 = cost model */
 int  mugd_debug_set_tc_tile_n(int bn);
 

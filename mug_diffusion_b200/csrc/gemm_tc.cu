@@ -45,6 +45,7 @@ struct TcParams {
     int32_t Lrows, Bs;        // row structure of the A tensor map (Lrows = rows per sample, Bs samples)
     int32_t box_l, box_b;     // TMA box: box_l rows of box_b consecutive samples (box_l*box_b <= 128)
     int32_t tiles_per_sample; // when Lrows >= 128
+    int32_t single_pass;      // 1: plain TF32 (a_hi*w_hi only, ~2^-11 relative) -- opt-in speed mode, NOT used for parity/bench
     int32_t inkernel_reduce;  // split-K: the last-arriving CTA of a tile reduces it (few splits), no second launch
     int32_t cluster;          // split-K CTAs of a tile form a thread-block cluster and reduce through DSMEM
     long long* dbg;           // optional: CTA (0,0,0) writes globaltimer stamps {entry, setup done, accumulator ready, tile staged, epilogue done}
@@ -126,6 +127,26 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
           "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
           "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
         : "memory");
+}
+// multicast variants for a cluster of MC CTAs along M that share the B (weight) tiles: every CTA loads 1/MC of the tile and
+// the TMA writes it -- and signals the mbarrier at the same offset -- in all MC CTAs; the stage is released with a commit
+// that arrives on every CTA's "empty" barrier.  L2 -> SM traffic for B drops by MC.
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -253,7 +274,8 @@ __device__ __forceinline__ void tc_epi4(const mugd_gemm& g, float4 acc, int m, i
 // AT = true: the converter writes a_hi / a_lo straight into tensor memory (tcgen05.st) and the MMAs take A from TMEM
 // (.kind::tf32 "TS" form).  That removes the converter's 32 KB of shared-memory writes and the 3 x 16 KB of A-operand
 // reads per k-step from the shared-memory port, which is what bounds the all-smem ("SS") variant.
-template <int BN, bool AT>
+// MC > 1: launched as clusters (1, MC, 1) of MC vertically adjacent output tiles that share their weight tiles via TMA multicast.
+template <int BN, bool AT, int MC>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmWhi,
@@ -298,13 +320,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int nit = it_end - it_begin;
 
     pdl_trigger();                      // let the next kernel's launch + prologue overlap this one
+    const uint32_t crank = (MC > 1) ? cluster_rank() : 0u;
     const bool dbg_cta = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
     // ---- one-time setup ------------------------------------------------------------------------------
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(bar_full(s), 1);
             mbar_init(bar_conv(s), 4);        // one arrival per converter warp
-            mbar_init(bar_empty(s), 1);
+            mbar_init(bar_empty(s), MC);      // one commit per CTA of the cluster
         }
         mbar_init(bar_accum, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -315,6 +338,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if constexpr (MC > 1) cluster_sync_all();   // peers' barriers must exist before any multicast can signal them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -333,7 +357,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int it = it_begin + i;
                 const int t = it / p.kblocks;
                 const int kb = it - t * p.kblocks;
-                mbar_expect_tx(bar_full(s), a_tx + 2 * S::B_BYTES);
+                mbar_expect_tx(bar_full(s), a_tx + (p.single_pass ? 1u : 2u) * S::B_BYTES);
                 // row addressing per tap: SAME = l+t-1, TAPS = l+t+shift (zero fill outside the sample by TMA bounds);
                 // DOWN (stride 2, right pad) uses one strided tensor map per tap (row l of map t = source row 2l+t)
                 const CUtensorMap* ma = &tmA;
@@ -342,8 +366,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 else if (g.conv_mode == MUGD_CONV_TAPS) lshift = (t + g.tap_shift) * (g.tap_dilation > 1 ? g.tap_dilation : 1);
                 else if (g.conv_mode == MUGD_CONV_DOWN) ma = (t == 0) ? &tmA : (t == 1 ? &tmA1 : &tmA2);
                 tma_load_3d(a_hi(s), ma, bar_full(s), kb * TC_BK, l_base + lshift, b_base);
-                tma_load_2d(b_hi(s), &tmWhi, bar_full(s), t * g.K + kb * TC_BK, n0);
-                tma_load_2d(b_lo(s), &tmWlo, bar_full(s), t * g.K + kb * TC_BK, n0);
+                if constexpr (MC > 1) {
+                    const int part = BN / MC;                       // this CTA's share of the weight tile rows
+                    const uint32_t doff = crank * (uint32_t)part * (TC_BK * 4);
+                    tma_load_2d_mc(b_hi(s) + doff, &tmWhi, bar_full(s), t * g.K + kb * TC_BK, n0 + (int)crank * part, (uint16_t)((1u << MC) - 1u));
+                    if (!p.single_pass)
+                        tma_load_2d_mc(b_lo(s) + doff, &tmWlo, bar_full(s), t * g.K + kb * TC_BK, n0 + (int)crank * part, (uint16_t)((1u << MC) - 1u));
+                } else {
+                    tma_load_2d(b_hi(s), &tmWhi, bar_full(s), t * g.K + kb * TC_BK, n0);
+                    if (!p.single_pass) tma_load_2d(b_lo(s), &tmWlo, bar_full(s), t * g.K + kb * TC_BK, n0);
+                }
             }
         }
     } else if (warp == 1) {
@@ -363,21 +395,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int kk = 0; kk < TC_BK / 8; ++kk) {
                         const uint64_t ko = (uint64_t)(kk * 2);     // 8 fp32 = 32 bytes = 2 x 16-byte units
-                        umma_tf32_ts(tmem_base, ta_lo + kk * 8, dbh + ko, idesc, (i > 0 || kk > 0) ? 1u : 0u);
-                        umma_tf32_ts(tmem_base, ta_hi + kk * 8, dbl + ko, idesc, 1u);
-                        umma_tf32_ts(tmem_base, ta_hi + kk * 8, dbh + ko, idesc, 1u);
+                        if (p.single_pass) {
+                            umma_tf32_ts(tmem_base, ta_hi + kk * 8, dbh + ko, idesc, (i > 0 || kk > 0) ? 1u : 0u);
+                        } else {
+                            umma_tf32_ts(tmem_base, ta_lo + kk * 8, dbh + ko, idesc, (i > 0 || kk > 0) ? 1u : 0u);
+                            umma_tf32_ts(tmem_base, ta_hi + kk * 8, dbl + ko, idesc, 1u);
+                            umma_tf32_ts(tmem_base, ta_hi + kk * 8, dbh + ko, idesc, 1u);
+                        }
                     }
                 } else {
                     const uint64_t dah = umma_desc(a_hi(s)), dal = umma_desc(a_lo(s));
 #pragma unroll
                     for (int kk = 0; kk < TC_BK / 8; ++kk) {
                         const uint64_t ko = (uint64_t)(kk * 2);
-                        umma_tf32(tmem_base, dal + ko, dbh + ko, idesc, (i > 0 || kk > 0) ? 1u : 0u);
-                        umma_tf32(tmem_base, dah + ko, dbl + ko, idesc, 1u);
-                        umma_tf32(tmem_base, dah + ko, dbh + ko, idesc, 1u);
+                        if (p.single_pass) {
+                            umma_tf32(tmem_base, dah + ko, dbh + ko, idesc, (i > 0 || kk > 0) ? 1u : 0u);
+                        } else {
+                            umma_tf32(tmem_base, dal + ko, dbh + ko, idesc, (i > 0 || kk > 0) ? 1u : 0u);
+                            umma_tf32(tmem_base, dah + ko, dbl + ko, idesc, 1u);
+                            umma_tf32(tmem_base, dah + ko, dbh + ko, idesc, 1u);
+                        }
                     }
                 }
-                umma_commit(bar_empty(s));                            // stage reusable once these MMAs retire
+                if constexpr (MC > 1) umma_commit_mc(bar_empty(s), (uint16_t)((1u << MC) - 1u));
+                else umma_commit(bar_empty(s));                       // stage reusable once these MMAs retire
             }
             umma_commit(bar_accum);
         }
@@ -556,6 +597,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (dbg_cta && threadIdx.x == 0) p.dbg[4] = gtimer();
     }
     // ---- teardown (all tcgen05.ld completed before the phase-2 barrier) ----------------------------------
+    if constexpr (MC > 1) cluster_sync_all();   // trailing multicast commits must not land in an exited CTA
     if (warp == 2) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
@@ -611,6 +653,13 @@ static bool g_tc_a_in_tmem = true;   // A operand of the MMAs from tensor memory
 // SLOWER on B200 (GEMM family 4.17 ms vs 3.01 ms per step at 4; worse at 8/16): one CTA pulling splits x 64 KB out of L2
 // costs more than the ~3 us reduce launch -> 0 (off) by default.
 static int g_tc_inkernel_max = 0;
+static bool g_tc_single_pass = false; // opt-in plain-TF32 mode (one product instead of three)
+// Weight-tile TMA multicast over clusters of 2/4 vertically adjacent tiles: measured on B200 it does not help (B=32 step:
+// GEMM family 11.25 ms unicast, 11.57 ms clusters of 2, 11.74 ms clusters of 4).  The large-GEMM main loop is bound by
+// the chip-wide L2 throughput (~42 B/clk/SM with all SMs pulling), but L2 already merges the requests of the few SMs that
+// read the same weight line at the same time, so multicast at cluster sizes <= 4 saves no L2 bandwidth and only adds
+// the cluster launch/sync cost -> off by default, kept for experiments (MUGD_TC_MC=2|4).
+static int g_tc_multicast = 0;        // max cluster size (along M) for weight-tile TMA multicast; 0/1 = off
 static int g_tc_force_bn = 0;        // experiments: 0 = cost model, 128 / 256 = force the tile width where legal
 // Split-K reduction through a thread-block cluster + DSMEM instead of workspace + reduce kernel.  Works (tests pass)
 // but measured slower on B200: clusters of 197 KB-smem CTAs schedule poorly (8 co-resident SMs of one GPC) and DSMEM
@@ -636,7 +685,7 @@ static EncodeTiledFn get_encode() {
 }
 
 struct TcGeometry {
-    int BN, splits, gx, gy, Lrows, Bs, box_l, box_b, tiles_per_sample, total_it;
+    int BN, splits, gx, gy, Lrows, Bs, box_l, box_b, tiles_per_sample, total_it, mc;
     int64_t ws_floats;
 };
 
@@ -695,6 +744,13 @@ static TcGeometry tc_geometry(const mugd_gemm& g, int sm_count, int forced_split
     }
     t.gx = (g.N + t.BN - 1) / t.BN;
     const int tiles = t.gx * t.gy;
+    // weight-tile multicast: only worth it when the grid oversubscribes the machine (the main loop is then bound by the
+    // L2 -> SM operand stream, ~39 B/clk/SM with all SMs pulling) and the tile rows pair up
+    t.mc = 1;
+    if (g_tc_multicast && g_tc_a_in_tmem && splits == 1 && t.BN >= 128 && tiles >= sm_count) {
+        if (g_tc_multicast >= 4 && t.gy % 4 == 0) t.mc = 4;
+        else if (t.gy % 2 == 0) t.mc = 2;
+    }
     if (splits > t.total_it) splits = t.total_it;
     if (splits < 1) splits = 1;
     t.splits = splits;
@@ -702,16 +758,38 @@ static TcGeometry tc_geometry(const mugd_gemm& g, int sm_count, int forced_split
     return t;
 }
 
-template <int BN, bool AT>
+template <int BN, bool AT, int MC>
 static int tc_launch(const CUtensorMap* tmAs, const CUtensorMap& tmWhi, const CUtensorMap& tmWlo, const TcParams& p,
                      const TcGeometry& t, cudaStream_t st) {
     const CUtensorMap &tmA = tmAs[0], &tmA1 = tmAs[1], &tmA2 = tmAs[2];
     static bool configured = false;
     if (!configured) {
-        MUGD_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, AT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcSmem<BN, AT>::TOTAL));
+        MUGD_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, AT, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcSmem<BN, AT>::TOTAL));
         configured = true;
     }
     dim3 grid(t.gx, t.gy, t.splits);
+    if (MC > 1) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid;
+        cfg.blockDim = dim3(TC_THREADS);
+        cfg.dynamicSmemBytes = TcSmem<BN, AT>::TOTAL;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 1;
+        attr[0].val.clusterDim.y = MC;
+        attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = g_use_pdl ? 2 : 1;
+        MUGD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, AT, MC>, tmA, tmA1, tmA2, tmWhi, tmWlo, p));
+        if (t.splits > 1 && !p.inkernel_reduce) {
+            const long long total = (long long)t.gx * t.gy * TC_BM * (BN / 4);
+            MUGD_CHECK_CUDA(launch_k(gemm_tc_reduce_kernel<BN>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, p, t.gx, t.gy));
+        }
+        return MUGD_OK;
+    }
     if (p.cluster && t.splits > 1) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = grid;
@@ -727,10 +805,10 @@ static int tc_launch(const CUtensorMap* tmAs, const CUtensorMap& tmWhi, const CU
         attr[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = g_use_pdl ? 2 : 1;
-        MUGD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, AT>, tmA, tmA1, tmA2, tmWhi, tmWlo, p));
+        MUGD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, AT, MC>, tmA, tmA1, tmA2, tmWhi, tmWlo, p));
         return MUGD_OK;
     }
-    MUGD_CHECK_CUDA(launch_k(gemm_tc_kernel<BN, AT>, grid, dim3(TC_THREADS), TcSmem<BN, AT>::TOTAL, st, tmA, tmA1, tmA2, tmWhi, tmWlo, p));
+    MUGD_CHECK_CUDA(launch_k(gemm_tc_kernel<BN, AT, MC>, grid, dim3(TC_THREADS), TcSmem<BN, AT>::TOTAL, st, tmA, tmA1, tmA2, tmWhi, tmWlo, p));
     if (t.splits > 1 && !p.inkernel_reduce) {
         const long long total = (long long)t.gx * t.gy * TC_BM * (BN / 4);
         MUGD_CHECK_CUDA(launch_k(gemm_tc_reduce_kernel<BN>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, p, t.gx, t.gy));
@@ -771,7 +849,7 @@ int launch_gemm_tc(const DeviceInfo& dev, const mugd_gemm& g, cudaStream_t st, i
         const cuuint64_t ktot = (cuuint64_t)g.taps * g.K;
         cuuint64_t dims[2] = {ktot, (cuuint64_t)g.N};
         cuuint64_t strides[1] = {ktot * 4};
-        cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)t.BN};
+        cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)(t.BN / t.mc)};
         cuuint32_t estr[2] = {1, 1};
         CUresult r = enc(w == 0 ? &tmWhi : &tmWlo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(w == 0 ? g.W_hi : g.W_lo), dims,
                          strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -791,15 +869,21 @@ int launch_gemm_tc(const DeviceInfo& dev, const mugd_gemm& g, cudaStream_t st, i
     p.box_b = t.box_b;
     p.tiles_per_sample = t.tiles_per_sample;
     p.dbg = g_tc_dbg;
+    p.single_pass = g_tc_single_pass ? 1 : 0;
     p.cluster = use_cluster ? 1 : 0;
     p.inkernel_reduce = (!use_cluster && t.splits > 1 && t.splits <= g_tc_inkernel_max && g.counters && g.n_counters >= t.gx * t.gy) ? 1 : 0;
     int rc;
-    if (g_tc_a_in_tmem)
-        rc = (t.BN == 256) ? tc_launch<256, true>(tmAs, tmWhi, tmWlo, p, t, st)
-             : (t.BN == 128) ? tc_launch<128, true>(tmAs, tmWhi, tmWlo, p, t, st) : tc_launch<64, true>(tmAs, tmWhi, tmWlo, p, t, st);
-    else
-        rc = (t.BN == 256) ? tc_launch<256, false>(tmAs, tmWhi, tmWlo, p, t, st)
-             : (t.BN == 128) ? tc_launch<128, false>(tmAs, tmWhi, tmWlo, p, t, st) : tc_launch<64, false>(tmAs, tmWhi, tmWlo, p, t, st);
+#define TC_GO(BN_, AT_, MC_) rc = tc_launch<BN_, AT_, MC_>(tmAs, tmWhi, tmWlo, p, t, st)
+    if (!g_tc_a_in_tmem) {
+        if (t.BN == 256) TC_GO(256, false, 1); else if (t.BN == 128) TC_GO(128, false, 1); else TC_GO(64, false, 1);
+    } else if (t.mc == 2) {
+        if (t.BN == 256) TC_GO(256, true, 2); else TC_GO(128, true, 2);
+    } else if (t.mc == 4) {
+        if (t.BN == 256) TC_GO(256, true, 4); else TC_GO(128, true, 4);
+    } else {
+        if (t.BN == 256) TC_GO(256, true, 1); else if (t.BN == 128) TC_GO(128, true, 1); else TC_GO(64, true, 1);
+    }
+#undef TC_GO
     if (rc != MUGD_OK) return rc;
     if (launches) *launches += (t.splits > 1 && !use_cluster && !p.inkernel_reduce) ? 2 : 1;
     return MUGD_OK;
@@ -814,6 +898,16 @@ extern "C" int mugd_set_tc_a_in_tmem(int enabled) {
 
 extern "C" int mugd_set_tc_inkernel_reduce_max(int max_splits) {
     mugd::g_tc_inkernel_max = max_splits < 0 ? 0 : max_splits;
+    return MUGD_OK;
+}
+
+extern "C" int mugd_set_tc_single_pass_tf32(int enabled) {
+    mugd::g_tc_single_pass = enabled != 0;
+    return MUGD_OK;
+}
+
+extern "C" int mugd_set_tc_multicast(int max_cluster) {
+    mugd::g_tc_multicast = (max_cluster == 2 || max_cluster == 4) ? max_cluster : 0;
     return MUGD_OK;
 }
 

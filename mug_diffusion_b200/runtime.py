@@ -85,8 +85,11 @@ class MugEngine:
         self.set_gemm_impl(gemm_impl)
 
     def set_gemm_impl(self, impl: str):
-        code = {"auto": L_.GEMM_TC, "simt": L_.GEMM_SIMT, "tc": L_.GEMM_TC}[impl]
+        # "tc_tf32" is an opt-in speed mode: single-pass TF32 tensor-core products (~2^-11 per product) instead of the
+        # fp32-accurate 3xTF32 split.  It is process-wide (library global) and never used by the parity tests or bench.py.
+        code = {"auto": L_.GEMM_TC, "simt": L_.GEMM_SIMT, "tc": L_.GEMM_TC, "tc_tf32": L_.GEMM_TC}[impl]
         L_.check(self.lib.mugd_set_gemm_impl(self.handle, code), "set_gemm_impl")
+        L_.check(self.lib.mugd_set_tc_single_pass_tf32(1 if impl == "tc_tf32" else 0), "set_tc_single_pass_tf32")
         self.gemm_impl = impl
         self.sessions.clear()
         self.dec_sessions.clear()

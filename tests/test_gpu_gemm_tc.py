@@ -162,3 +162,25 @@ def test_upsample_as_two_parity_gemms(R, impl, B, L, C):
     e = rel_err(ncl(out.cpu(), B), ref)
     print(f"upsample parity impl={impl} B={B} L={L} C={C} rel_err={e:.2e}")
     assert e < TOL
+
+
+@pytest.mark.parametrize("kind", ["linear", "conv3"])
+def test_tc_weight_multicast_clusters(R, kind):
+    """grids that oversubscribe the 148 SMs run as clusters of 2 (or 4, MUGD_TC_MC=4) tiles sharing the weight tile by TMA
+    multicast: same numbers as the fp64 reference"""
+    if kind == "linear":
+        M, K, N = 296 * 128, 128, 256
+        x, w, b = g("mcx", (M, K)), g("mcw", (N, K)) / math.sqrt(K), 0.1 * g("mcb", (N,))
+        ref = F.linear(x.double(), w.double(), b.double())
+        xc, bc, out = x.cuda(), b.cuda(), torch.zeros(M, N).cuda()
+        run_tc(R, view(xc), w, N, K, view(out), bias=ptr(bc))
+        assert rel_err(out, ref) < TOL
+    else:
+        B, L, Cin, Cout = 64, 512, 128, 128
+        x, w = g("mcx3", (B, Cin, L)), g("mcw3", (Cout, Cin, 3)) / math.sqrt(3 * Cin)
+        ref = F.conv1d(x.double(), w.double(), None, padding=1)
+        wp = w.permute(0, 2, 1).contiguous().reshape(Cout, 3 * Cin)
+        xc = nlc(x).cuda()
+        out = torch.zeros(B * L, Cout).cuda()
+        run_tc(R, view(xc), wp, Cout, Cin, view(out), taps=3, mode=L_.CONV_SAME, Lin=L, Lout=L)
+        assert rel_err(ncl(out.cpu(), B), ref) < TOL
