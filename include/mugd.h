@@ -223,6 +223,10 @@ int  mugd_set_tc_inkernel_reduce_max(int max_splits);
  * the reference's own GPU path uses for convs); 0 (default) = 3xTF32, fp32-accurate.  Parity tests and bench.py use 0. */
 int  mugd_set_tc_single_pass_tf32(int enabled);
 
+/* attention kernel: 1 (default) = QK^T and PV on the tcgen05 tensor cores (3xTF32, fp32 accuracy); 0 = exact-fp32 FFMA kernel
+ * (the referee of the parity tests).  Replaces the einsum/softmax body of CrossAttention.forward, attention.py:99-121 */
+int  mugd_set_attention_impl(int impl);
+
 /* weight-tile TMA multicast: clusters of up to `max_cluster` (0, 2 or 4) vertically adjacent output tiles load each weight tile
  * once from L2 and multicast it (used only when the grid oversubscribes the SMs).  Default 0 (off): measured no faster on B200. */
 int  mugd_set_tc_multicast(int max_cluster);

@@ -176,9 +176,14 @@ def attn_ref(q, k, v, rel, cg, H, pos_max=64):
     return (attn @ vh).permute(0, 2, 1, 3).reshape(B, Lq, inner)
 
 
+@pytest.mark.parametrize("impl", [1, 0], ids=["tcgen05", "ffma"])
 @pytest.mark.parametrize("B,H,D,Lq,Lk", [(2, 8, 32, 48, 48), (2, 8, 48, 24, 21), (1, 8, 64, 200, 200), (2, 8, 32, 256, 256),
-                                         (1, 8, 64, 124, 124), (3, 8, 48, 130, 21)])
-def test_attention(R, B, H, D, Lq, Lk):
+                                         (1, 8, 64, 124, 124), (3, 8, 48, 130, 21), (1, 8, 32, 496, 496), (1, 8, 48, 300, 300),
+                                         (2, 8, 64, 12, 12), (1, 4, 64, 129, 257)])
+def test_attention(R, B, H, D, Lq, Lk, impl):
+    """both attention kernels (tensor-core 3xTF32 and the exact FFMA referee) against the fp64 formula; covers several key
+    tiles, ragged last tiles (Lk % 16 != 0), Lq < one tile and the 21-token prompt context"""
+    R.lib.mugd_set_attention_impl(impl)
     C = H * D
     q, k, v = g("aq", (B, Lq, C)), g("ak", (B, Lk, C)), g("av", (B, Lk, C))
     rel, cg = 0.5 * g("ar", (129, H)), 1 + 0.1 * g("ac", (129, H))
@@ -190,7 +195,10 @@ def test_attention(R, B, H, D, Lq, Lk):
     relc, cgc = rel.cuda(), cg.cuda()
     ops = OpList()
     ops.attention(view(qkv, 0, C), view(kc), view(vc), view(out), ptr(relc), ptr(cgc), B, H, Lq, Lk, 64)
-    R.run(ops)
+    try:
+        R.run(ops)
+    finally:
+        R.lib.mugd_set_attention_impl(1)
     assert rel_err(out.view(B, Lq, C), ref) < 2e-5
 
 
