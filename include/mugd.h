@@ -227,6 +227,13 @@ int  mugd_set_tc_single_pass_tf32(int enabled);
  * (the referee of the parity tests).  Replaces the einsum/softmax body of CrossAttention.forward, attention.py:99-121 */
 int  mugd_set_attention_impl(int impl);
 
+/* tile-width planning of the tensor-core GEMM: 1 = also consider 64-column tiles for N >= 128 (more, smaller CTAs when the
+ * grid underfills the 148 SMs); kstep_us > 0 overrides the planner's cost per 32-deep k-step of such a tile */
+int  mugd_set_tc_narrow_tiles(int enabled, float kstep_us);
+
+/* split-K reduce kernel as a programmatic dependent launch of its GEMM (scheduled early, waits in griddepcontrol.wait) */
+int  mugd_set_tc_pdl_reduce(int enabled);
+
 /* weight-tile TMA multicast: clusters of up to `max_cluster` (0, 2 or 4) vertically adjacent output tiles load each weight tile
  * once from L2 and multicast it (used only when the grid oversubscribes the SMs).  Default 0 (off): measured no faster on B200. */
 int  mugd_set_tc_multicast(int max_cluster);

@@ -48,6 +48,7 @@ struct TcParams {
     int32_t single_pass;      // 1: plain TF32 (a_hi*w_hi only, ~2^-11 relative) -- opt-in speed mode, NOT used for parity/bench
     int32_t inkernel_reduce;  // split-K: the last-arriving CTA of a tile reduces it (few splits), no second launch
     int32_t cluster;          // split-K CTAs of a tile form a thread-block cluster and reduce through DSMEM
+    int32_t pdl_reduce;       // split-K: the reduce kernel is a programmatic dependent launch (resident and waiting while the GEMM runs)
     long long* dbg;           // optional: CTA (0,0,0) writes globaltimer stamps {entry, setup done, accumulator ready, tile staged, epilogue done}
 };
 
@@ -147,6 +148,18 @@ __device__ __forceinline__ uint32_t cluster_rank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
     return r;
+}
+// One lane of a converged warp.  tcgen05.mma / tcgen05.commit / cp.async.bulk.tensor are uniform-datapath instructions: issued
+// from a lane-divergent branch (`if (lane == 0)`) ptxas wraps every one of them in an elect-and-branch loop (~95 cycles per
+// MMA measured, which starved the tensor pipe); guarded by elect.sync in a converged warp they issue back to back.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, px;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -320,6 +333,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int nit = it_end - it_begin;
 
     pdl_trigger();                      // let the next kernel's launch + prologue overlap this one
+    if (p.pdl_reduce) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the split-K reduce kernel may take its seats now
     const uint32_t crank = (MC > 1) ? cluster_rank() : 0u;
     const bool dbg_cta = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
     // ---- one-time setup ------------------------------------------------------------------------------
@@ -348,12 +362,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     if (warp == 0) {
         // ===================================== TMA producer =====================================
-        if (lane == 0) {
+        // the whole warp walks the loop converged; one elected lane issues the copies
+        {
             const uint32_t a_tx = (uint32_t)(p.box_l * p.box_b) * TC_BK * 4;
             for (int i = 0; i < nit; ++i) {
                 const int s = i % STAGES;
                 const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
                 mbar_wait(bar_empty(s), ph ^ 1u);
+                if (elect_one()) {
+                if (dbg_cta && i < 24) p.dbg[8 + i * 6 + 5] = gtimer();
                 const int it = it_begin + i;
                 const int t = it / p.kblocks;
                 const int kb = it - t * p.kblocks;
@@ -376,11 +393,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     tma_load_2d(b_hi(s), &tmWhi, bar_full(s), t * g.K + kb * TC_BK, n0);
                     if (!p.single_pass) tma_load_2d(b_lo(s), &tmWlo, bar_full(s), t * g.K + kb * TC_BK, n0);
                 }
+                if (dbg_cta && i < 24) p.dbg[8 + i * 6 + 0] = gtimer();
+                }
+                __syncwarp();
             }
         }
     } else if (warp == 1) {
         // ===================================== MMA issuer =======================================
-        if (lane == 0) {
+        {
             // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A=TF32 [7,10)=2, B=TF32 [10,13)=2,
             // A/B K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
@@ -389,6 +409,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
                 mbar_wait(bar_conv(s), ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (elect_one()) {
+                if (dbg_cta && i < 24) p.dbg[8 + i * 6 + 3] = gtimer();
                 const uint64_t dbh = umma_desc(b_hi(s)), dbl = umma_desc(b_lo(s));
                 if constexpr (AT) {
                     const uint32_t ta_hi = tmem_base + (uint32_t)(BN + s * 64), ta_lo = ta_hi + 32u;
@@ -419,8 +441,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 if constexpr (MC > 1) umma_commit_mc(bar_empty(s), (uint16_t)((1u << MC) - 1u));
                 else umma_commit(bar_empty(s));                       // stage reusable once these MMAs retire
+                if (dbg_cta && i < 24) p.dbg[8 + i * 6 + 4] = gtimer();
+                }
+                __syncwarp();
             }
-            umma_commit(bar_accum);
+            if (elect_one()) umma_commit(bar_accum);
         }
     } else if (warp >= 4) {
         // ===================================== converter ========================================
@@ -429,6 +454,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int s = i % STAGES;
             const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
             mbar_wait(bar_full(s), ph);
+            if (dbg_cta && ct == 0 && i < 24) p.dbg[8 + i * 6 + 1] = gtimer();
             if constexpr (AT) {
                 // thread = tile row (= TMEM lane): read the row's 128 bytes out of the 128B-swizzled tile (16-byte chunk c
                 // of row r sits at chunk c ^ (r & 7)), split, and store hi / lo to this stage's TMEM columns
@@ -466,6 +492,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_conv(s));
+            if (dbg_cta && ct == 0 && i < 24) p.dbg[8 + i * 6 + 2] = gtimer();
         }
         // ===================================== epilogue =========================================
         mbar_wait(bar_accum, 0);
@@ -659,6 +686,10 @@ static bool g_tc_single_pass = false; // opt-in plain-TF32 mode (one product ins
 // the chip-wide L2 throughput (~42 B/clk/SM with all SMs pulling), but L2 already merges the requests of the few SMs that
 // read the same weight line at the same time, so multicast at cluster sizes <= 4 saves no L2 bandwidth and only adds
 // the cluster launch/sync cost -> off by default, kept for experiments (MUGD_TC_MC=2|4).
+// 64-wide tiles for GEMMs that could use 128 (more, smaller CTAs for the grids that underfill the machine)
+static int g_tc_pdl_reduce = 0;
+static int g_tc_narrow_tiles = 0;
+static float g_tc_kstep64 = 0.4f;
 static int g_tc_multicast = 0;        // max cluster size (along M) for weight-tile TMA multicast; 0/1 = off
 static int g_tc_force_bn = 0;        // experiments: 0 = cost model, 128 / 256 = force the tile width where legal
 // Split-K reduction through a thread-block cluster + DSMEM instead of workspace + reduce kernel.  Works (tests pass)
@@ -722,15 +753,16 @@ static TcGeometry tc_geometry(const mugd_gemm& g, int sm_count, int forced_split
     // Candidates: tile width 128 (or 64 for narrow N), 256 when N allows it, each with its best K split.
     int splits = 1;
     float best = 1e30f;
-    const int bn_lo = (g.N >= 128) ? 128 : 64;
     const int tc_bn_env = g_tc_force_bn;
-    for (int cand = 0; cand < 2; ++cand) {
-        const int bn = cand == 0 ? bn_lo : 256;
-        if (cand == 1 && g.N < 256) break;
-        if (tc_bn_env && bn != tc_bn_env && !(tc_bn_env == 256 && g.N < 256 && cand == 0)) continue;
+    static const int cands[3] = {64, 128, 256};
+    for (int cand = 0; cand < 3; ++cand) {
+        const int bn = cands[cand];
+        if (bn > 64 && g.N < bn) break;
+        if (bn == 64 && g.N >= 128 && !g_tc_narrow_tiles && tc_bn_env != 64) continue;
+        if (tc_bn_env && bn != tc_bn_env && !(tc_bn_env > g.N && bn == (g.N >= 128 ? 128 : 64))) continue;
         const int gx = (g.N + bn - 1) / bn;
         const int tiles = gx * t.gy;
-        const float kstep = bn == 256 ? 1.05f : (bn == 128 ? 0.7f : 0.5f);
+        const float kstep = bn == 256 ? 1.05f : (bn == 128 ? 0.7f : g_tc_kstep64);
         // 256-wide tiles only pay off unsplit (measured: l1/l2 FF1 and the B=64 convs gain 15-25 %, split cases lose)
         const int sp_max = forced_split > 0 ? forced_split : ((tiles < sm_count && bn != 256) ? (g_tc_cluster ? 8 : 16) : 1);
         for (int sp = forced_split > 0 ? forced_split : 1; sp <= sp_max && sp <= t.total_it; ++sp) {
@@ -738,7 +770,9 @@ static TcGeometry tc_geometry(const mugd_gemm& g, int sm_count, int forced_split
             if (forced_split <= 0 && sp > 1 && per < 2) break;
             if (forced_split <= 0 && sp > 1 && tiles * sp > 2 * sm_count) break;   // bounds the workspace: < 2*SMs partial tiles
             const int waves = (tiles * sp + sm_count - 1) / sm_count;
-            const float est = waves * (1.0f + kstep * per) + (sp > 1 ? (g_tc_cluster ? 2.0f : (sp <= g_tc_inkernel_max ? 1.0f + 0.6f * sp : 5.0f)) : 0.0f);
+            // narrower tiles also shorten the epilogue (fewer columns per CTA): ~1 us per 64 columns on top of the fill
+            const float fill = 1.0f + (g_tc_narrow_tiles ? 0.9f * (bn / 64 - 1) : 0.0f);
+            const float est = waves * (fill + kstep * per) + (sp > 1 ? (g_tc_cluster ? 2.0f : (sp <= g_tc_inkernel_max ? 1.0f + 0.6f * sp : 5.0f)) : 0.0f);
             if (est < best - 0.25f) { best = est; splits = sp; t.BN = bn; }
         }
     }
@@ -811,7 +845,22 @@ static int tc_launch(const CUtensorMap* tmAs, const CUtensorMap& tmWhi, const CU
     MUGD_CHECK_CUDA(launch_k(gemm_tc_kernel<BN, AT, MC>, grid, dim3(TC_THREADS), TcSmem<BN, AT>::TOTAL, st, tmA, tmA1, tmA2, tmWhi, tmWlo, p));
     if (t.splits > 1 && !p.inkernel_reduce) {
         const long long total = (long long)t.gx * t.gy * TC_BM * (BN / 4);
-        MUGD_CHECK_CUDA(launch_k(gemm_tc_reduce_kernel<BN>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, p, t.gx, t.gy));
+        if (p.pdl_reduce) {
+            // programmatic dependent launch: the reduce grid is scheduled while the GEMM still runs and sits in
+            // griddepcontrol.wait until the GEMM grid has completed and flushed -> no launch gap between the two
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)((total + 255) / 256));
+            cfg.blockDim = dim3(256);
+            cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            MUGD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_reduce_kernel<BN>, p, t.gx, t.gy));
+        } else {
+            MUGD_CHECK_CUDA(launch_k(gemm_tc_reduce_kernel<BN>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, p, t.gx, t.gy));
+        }
     }
     return MUGD_OK;
 }
@@ -869,6 +918,7 @@ int launch_gemm_tc(const DeviceInfo& dev, const mugd_gemm& g, cudaStream_t st, i
     p.box_b = t.box_b;
     p.tiles_per_sample = t.tiles_per_sample;
     p.dbg = g_tc_dbg;
+    p.pdl_reduce = (g_tc_pdl_reduce && t.splits > 1 && t.mc == 1 && !(g_tc_cluster && t.splits > 1)) ? 1 : 0;
     p.single_pass = g_tc_single_pass ? 1 : 0;
     p.cluster = use_cluster ? 1 : 0;
     p.inkernel_reduce = (!use_cluster && t.splits > 1 && t.splits <= g_tc_inkernel_max && g.counters && g.n_counters >= t.gx * t.gy) ? 1 : 0;
@@ -906,13 +956,24 @@ extern "C" int mugd_set_tc_single_pass_tf32(int enabled) {
     return MUGD_OK;
 }
 
+extern "C" int mugd_set_tc_narrow_tiles(int enabled, float kstep_us) {
+    mugd::g_tc_narrow_tiles = enabled ? 1 : 0;
+    if (kstep_us > 0.f) mugd::g_tc_kstep64 = kstep_us;
+    return MUGD_OK;
+}
+
+extern "C" int mugd_set_tc_pdl_reduce(int enabled) {
+    mugd::g_tc_pdl_reduce = enabled ? 1 : 0;
+    return MUGD_OK;
+}
+
 extern "C" int mugd_set_tc_multicast(int max_cluster) {
     mugd::g_tc_multicast = (max_cluster == 2 || max_cluster == 4) ? max_cluster : 0;
     return MUGD_OK;
 }
 
 extern "C" int mugd_debug_set_tc_tile_n(int bn) {
-    mugd::g_tc_force_bn = (bn == 128 || bn == 256) ? bn : 0;
+    mugd::g_tc_force_bn = (bn == 64 || bn == 128 || bn == 256) ? bn : 0;
     return MUGD_OK;
 }
 
