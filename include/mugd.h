@@ -231,6 +231,10 @@ int  mugd_set_attention_impl(int impl);
  * grid underfills the 148 SMs); kstep_us > 0 overrides the planner's cost per 32-deep k-step of such a tile */
 int  mugd_set_tc_narrow_tiles(int enabled, float kstep_us);
 
+/* planner cost constants of the tensor-core GEMM (us per 32-deep k-step of a 128- and a 256-column tile, us per split-K
+ * round trip); values <= 0 keep the current one.  For tuning sweeps (tools/), not needed in production. */
+int  mugd_debug_set_tc_cost(float kstep128_us, float kstep256_us, float split_us);
+
 /* split-K reduce kernel as a programmatic dependent launch of its GEMM (scheduled early, waits in griddepcontrol.wait) */
 int  mugd_set_tc_pdl_reduce(int enabled);
 

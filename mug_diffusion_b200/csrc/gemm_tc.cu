@@ -687,6 +687,9 @@ static bool g_tc_single_pass = false; // opt-in plain-TF32 mode (one product ins
 // read the same weight line at the same time, so multicast at cluster sizes <= 4 saves no L2 bandwidth and only adds
 // the cluster launch/sync cost -> off by default, kept for experiments (MUGD_TC_MC=2|4).
 // 64-wide tiles for GEMMs that could use 128 (more, smaller CTAs for the grids that underfill the machine)
+// planner constants, re-measured after the elect.sync issue fix (tools/bench_gemm.py, tools/gpu_cost.sh sweep):
+// us per k-step of a 128- / 256-wide tile, us per split-K round trip (workspace + reduce launch)
+static float g_tc_cost[3] = {0.55f, 1.1f, 4.0f};
 static int g_tc_pdl_reduce = 0;
 static int g_tc_narrow_tiles = 0;
 static float g_tc_kstep64 = 0.4f;
@@ -762,7 +765,7 @@ static TcGeometry tc_geometry(const mugd_gemm& g, int sm_count, int forced_split
         if (tc_bn_env && bn != tc_bn_env && !(tc_bn_env > g.N && bn == (g.N >= 128 ? 128 : 64))) continue;
         const int gx = (g.N + bn - 1) / bn;
         const int tiles = gx * t.gy;
-        const float kstep = bn == 256 ? 1.05f : (bn == 128 ? 0.7f : g_tc_kstep64);
+        const float kstep = bn == 256 ? g_tc_cost[1] : (bn == 128 ? g_tc_cost[0] : g_tc_kstep64);
         // 256-wide tiles only pay off unsplit (measured: l1/l2 FF1 and the B=64 convs gain 15-25 %, split cases lose)
         const int sp_max = forced_split > 0 ? forced_split : ((tiles < sm_count && bn != 256) ? (g_tc_cluster ? 8 : 16) : 1);
         for (int sp = forced_split > 0 ? forced_split : 1; sp <= sp_max && sp <= t.total_it; ++sp) {
@@ -772,7 +775,7 @@ static TcGeometry tc_geometry(const mugd_gemm& g, int sm_count, int forced_split
             const int waves = (tiles * sp + sm_count - 1) / sm_count;
             // narrower tiles also shorten the epilogue (fewer columns per CTA): ~1 us per 64 columns on top of the fill
             const float fill = 1.0f + (g_tc_narrow_tiles ? 0.9f * (bn / 64 - 1) : 0.0f);
-            const float est = waves * (fill + kstep * per) + (sp > 1 ? (g_tc_cluster ? 2.0f : (sp <= g_tc_inkernel_max ? 1.0f + 0.6f * sp : 5.0f)) : 0.0f);
+            const float est = waves * (fill + kstep * per) + (sp > 1 ? (g_tc_cluster ? 2.0f : (sp <= g_tc_inkernel_max ? 1.0f + 0.6f * sp : g_tc_cost[2])) : 0.0f);
             if (est < best - 0.25f) { best = est; splits = sp; t.BN = bn; }
         }
     }
@@ -959,6 +962,13 @@ extern "C" int mugd_set_tc_single_pass_tf32(int enabled) {
 extern "C" int mugd_set_tc_narrow_tiles(int enabled, float kstep_us) {
     mugd::g_tc_narrow_tiles = enabled ? 1 : 0;
     if (kstep_us > 0.f) mugd::g_tc_kstep64 = kstep_us;
+    return MUGD_OK;
+}
+
+extern "C" int mugd_debug_set_tc_cost(float kstep128_us, float kstep256_us, float split_us) {
+    if (kstep128_us > 0.f) mugd::g_tc_cost[0] = kstep128_us;
+    if (kstep256_us > 0.f) mugd::g_tc_cost[1] = kstep256_us;
+    if (split_us > 0.f) mugd::g_tc_cost[2] = split_us;
     return MUGD_OK;
 }
 
