@@ -49,18 +49,23 @@ def measured_peaks():
 
 
 def ncu_traffic_per_launch():
-    """DRAM bytes (read+write) per launch of the dominant kernel from the committed ncu --set full capture, or None."""
+    """DRAM bytes (read+write) per launch of the dominant kernel (gemm_tc_kernel) from the committed ncu --set full
+    capture of this workload's representative ops (profiles/r01d_families_ncu_raw.csv, tools/ncu_families.py), or None."""
     import csv
-    p = os.path.join(ROOT, "profiles", "r01c_tc_gemm_ncu_raw.csv")
-    try:
-        rows = list(csv.reader(open(p)))
-        hdr, units = rows[0], rows[1]
-        ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
-        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-        vals = [float(r[ir]) * scale.get(units[ir], 1.0) + float(r[iw]) * scale.get(units[iw], 1.0) for r in rows[2:] if len(r) > iw]
-        return sum(vals) / len(vals) if vals else None
-    except Exception:
-        return None
+    for name in ("r01d_families_ncu_raw.csv", "r01c_tc_gemm_ncu_raw.csv"):
+        p = os.path.join(ROOT, "profiles", name)
+        try:
+            rows = list(csv.reader(l for l in open(p) if not l.startswith("==")))
+            hdr, units = rows[0], rows[1]
+            ir, iw, ik = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("Kernel Name")
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            vals = [float(r[ir]) * scale.get(units[ir], 1.0) + float(r[iw]) * scale.get(units[iw], 1.0)
+                    for r in rows[2:] if len(r) > iw and "gemm_tc_kernel" in r[ik]]
+            if vals:
+                return sum(vals) / len(vals), name, len(vals)
+        except Exception:
+            continue
+    return None, None, 0
 
 
 class ClockSampler:
@@ -331,13 +336,13 @@ def main():
             fam_ms[kind] = a0.elapsed_time(a1) / 5
             fam_n[kind] = pl.launches
         pk = measured_peaks()
-        traffic = ncu_traffic_per_launch()
+        traffic, traffic_src, traffic_n = ncu_traffic_per_launch()
         gemm_ms, gemm_n = fam_ms[L_.OP_GEMM], fam_n[L_.OP_GEMM]
         ach = gemm_flops / (gemm_ms * 1e-3) / 1e12
         roof = dict(bound="tensor", kernel=f"gemm_tc_kernel (tcgen05 3xTF32; impl={eng.gemm_impl})", achieved=ach, peak=pk["tflops"],
                     unit="TFLOP/s", frac=ach / pk["tflops"], traffic=traffic, peak_source=pk["src"], launches=gemm_n,
-                    traffic_note="mean dram__bytes_read+write per gemm_tc_kernel launch in profiles/r01c_tc_gemm_ncu_raw.csv "
-                                 "(ncu --set full, 3 launches of this workload)",
+                    traffic_note=f"mean dram__bytes_read+write per gemm_tc_kernel launch in profiles/{traffic_src} "
+                                 f"(ncu --set full, {traffic_n} representative launches of the L512_B4 plan, cold cache)",
                     avg_launch_us=1000.0 * gemm_ms / max(gemm_n, 1), algorithmic_gflop_per_step=gemm_flops / 1e9,
                     note="3xTF32 issues 3 tensor-core products per fp32 product and TF32 runs at half the bf16 rate: "
                          "the fp32-exact ceiling is peak/6",

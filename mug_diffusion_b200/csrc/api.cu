@@ -9,7 +9,7 @@
 namespace mugd {
 
 static thread_local char g_err[1024] = "";
-bool g_use_pdl = false;   // measured on B200: 5.12 ms/step with PDL edges vs 4.46 without (L512_B4_cfg5) -> off by default
+bool g_use_pdl = true;    // programmatic launch edges with the implicit (grid-completion) trigger: 3.97 vs 4.02 ms/step; explicit triggers are slower (common.cuh)
 
 void set_error(const char* fmt, ...) {
     va_list ap;

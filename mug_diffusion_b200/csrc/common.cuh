@@ -78,11 +78,24 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
     cfg.numAttrs = g_use_pdl ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
-// Early trigger (dependents become resident while this grid still runs) measured SLOWER on B200 for this launch
-// mix (5.12 vs 4.46 ms/step); without it the trigger is implicit at grid completion and PDL only overlaps the
-// dependent's launch with this grid's memory flush.  Kept behind a macro for experiments.
+// Trigger placement experiments (all measured on B200, none kept on: DESIGN.md 4 "tried and measured slower"):
+//   MUGD_PDL_EARLY_TRIGGER  every kernel signals at entry (dependents become resident while this grid still runs): 5.12 vs 4.46 ms/step
+//   MUGD_PDL_SHORT_ENTRY    only the short kernels (norms, attention, S4, elementwise, reduce) signal at entry
+//   MUGD_PDL_LATE_TRIGGER   the GEMM signals once its accumulator tile is staged, so the next launch overlaps the store phase
+// Without a trigger the signal is implicit at grid completion and PDL only overlaps the dependent's launch with this
+// grid's memory flush.
 __device__ __forceinline__ void pdl_trigger() {
-#ifdef MUGD_PDL_EARLY_TRIGGER
+#if defined(MUGD_PDL_EARLY_TRIGGER) || defined(MUGD_PDL_SHORT_ENTRY)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_trigger_gemm_entry() {
+#if defined(MUGD_PDL_EARLY_TRIGGER)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_trigger_late() {
+#if defined(MUGD_PDL_LATE_TRIGGER)
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 #endif
 }

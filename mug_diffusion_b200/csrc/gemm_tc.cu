@@ -55,7 +55,7 @@ struct TcParams {
 // ---- raw PTX helpers ---------------------------------------------------------------------------------
 __device__ __forceinline__ long long gtimer() {
     long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t) :: "memory");
     return t;
 }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -332,7 +332,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int it_end = (int)(((long long)p.total_it * (blockIdx.z + 1)) / p.splits);
     const int nit = it_end - it_begin;
 
-    pdl_trigger();                      // let the next kernel's launch + prologue overlap this one
+    pdl_trigger_gemm_entry();           // (experiment switch, off: see common.cuh)
     if (p.pdl_reduce) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the split-K reduce kernel may take its seats now
     const uint32_t crank = (MC > 1) ? cluster_rank() : 0u;
     const bool dbg_cta = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
@@ -521,6 +521,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // MMA / allocator warps have nothing left to do and join in.
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    pdl_trigger_late();                 // (experiment switch, off) only the store phase is left
+    if (dbg_cta && threadIdx.x == 0) p.dbg[5] = gtimer();
     {
         const int step = g.step ? *g.step : 0;
         const float* rowvec = g.rowvec ? g.rowvec + (int64_t)step * g.rowvec_step_stride : nullptr;

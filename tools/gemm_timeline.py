@@ -17,6 +17,8 @@ from mug_diffusion_b200.packer import tf32_split  # noqa: E402
 
 # (label, B, L, Cin, Cout, taps, split, force_bn)
 SHAPES = [
+    ("tiny 1x1 128->128 M4096 bn128", 8, 512, 128, 128, 1, 1, 128),
+    ("tiny 1x1 128->128 M4096 bn128 split2", 8, 512, 128, 128, 1, 2, 128),
     ("1x1 256->256 M2048 bn128", 8, 256, 256, 256, 1, 1, 128),
     ("1x1 256->256 M2048 bn64", 8, 256, 256, 256, 1, 1, 64),
     ("1x1 384->384 M1024 bn128 unsplit", 8, 128, 384, 384, 1, 1, 128),
@@ -50,7 +52,7 @@ def main():
         R.lib.mugd_debug_set_tc_tile_n(0)
         t = buf.cpu().tolist()
         t0 = t[0]
-        print(f"\n== {label}: M={M} N={Cout} K={taps*Cin}  accum ready {t[2]-t0} ns, staged {t[3]-t0}, done {t[4]-t0}")
+        print(f"\n== {label}: M={M} N={Cout} K={taps*Cin}  accum ready {t[2]-t0} ns, staged {t[3]-t0}, phase-2 start {t[5]-t0}, done {t[4]-t0}")
         print("   k | tma issued  full seen  conv done  mma start  mma commit | empty seen (producer)")
         nk = min(24, taps * Cin // 32)
         for i in range(nk):

@@ -8,3 +8,7 @@ timeout 900 ncu --profile-from-start off --set full --clock-control none --impor
 tail -25 gpurun_out/families.txt
 ncu -i gpurun_out/families.ncu-rep --page raw --csv > gpurun_out/families_raw.csv 2>/dev/null
 ls -la gpurun_out/ | head -30
+for wl in L512_B32_cfg5_S50 L992_B8_cfg5_S100; do
+  timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --workload $wl > gpurun_out/bench_$wl.log 2>gpurun_out/bench_$wl.err; tail -c 1500 gpurun_out/bench_$wl.log | head -c 400; echo
+done
+timeout 120 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; tail -2 gpurun_out/smoke.log
