@@ -235,8 +235,17 @@ int  mugd_set_tc_narrow_tiles(int enabled, float kstep_us);
  * round trip); values <= 0 keep the current one.  For tuning sweeps (tools/), not needed in production. */
 int  mugd_debug_set_tc_cost(float kstep128_us, float kstep256_us, float split_us);
 
+/* split-K reduction inside the GEMM kernel: cooperative launch (grid <= one CTA per SM, co-residency guaranteed by the driver),
+ * the splits of a tile rendezvous on a device counter and each reduces + finishes its band of rows; no second launch.
+ * split_cost_us > 0 sets the planner's cost of a split in this mode. */
+int  mugd_set_tc_coop_reduce(int enabled, float split_cost_us);
+
 /* split-K reduce kernel as a programmatic dependent launch of its GEMM (scheduled early, waits in griddepcontrol.wait) */
 int  mugd_set_tc_pdl_reduce(int enabled);
+
+/* debugging aid: CTA (0,0,0) of the tensor-core attention kernel dumps 40 floats per query row of its first key tile
+ * (raw logits, O tile, running max / sum, first operand words) into buf[128*40]; NULL switches it off */
+int  mugd_debug_set_attention_dump(float* buf);
 
 /* weight-tile TMA multicast: clusters of up to `max_cluster` (0, 2 or 4) vertically adjacent output tiles load each weight tile
  * once from L2 and multicast it (used only when the grid oversubscribes the SMs).  Default 0 (off): measured no faster on B200. */

@@ -578,7 +578,51 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                 for (int u = 0; u < U; ++u) st_f4(wsp + (i0 + u * TC_THREADS + (int)threadIdx.x) * 4, acc[u]);   // [row][BN] dense
             }
-            if (p.inkernel_reduce) {
+            if (p.inkernel_reduce == 2) {
+                // Cooperative launch (all CTAs of the grid are co-resident, guaranteed by the driver): the `splits` CTAs of a
+                // tile meet at the tile's counter once their partial tiles are in L2, then each sums ITS band of rows over all
+                // partials in fixed split order (deterministic) and finishes it with the fused epilogue.  The reduction is
+                // spread over the same CTAs that produced it: no second launch and no serial tail.
+                int* cnt = p.counters + tile_lin;
+                __threadfence();
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    atomicAdd(cnt, 1);
+                    const long long t0 = clock64();
+                    int seen;
+                    do {
+                        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(cnt) : "memory");
+                        if (clock64() - t0 > 4000000000LL) __trap();      // a protocol bug traps instead of hanging the GPU
+                    } while (seen < p.splits);
+                }
+                __syncthreads();
+                __threadfence();
+                const int rows_per = (TC_BM + p.splits - 1) / p.splits;
+                const int r0 = (int)blockIdx.z * rows_per;
+                const int r1 = min(TC_BM, r0 + rows_per);
+                const int n4 = max(0, r1 - r0) * C4;
+                const float* wst = p.ws + ((int64_t)tile_lin * p.splits) * (TC_BM * BN);
+                for (int i = (int)threadIdx.x; i < n4; i += TC_THREADS) {
+                    const int row = r0 + i / C4, c4 = i % C4;
+                    const float* src = wst + (int64_t)row * BN + c4 * 4;
+                    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+                    for (int z = 0; z < p.splits; ++z) {
+                        const float4 t4 = __ldcg(reinterpret_cast<const float4*>(src + (int64_t)z * (TC_BM * BN)));
+                        sum.x += t4.x; sum.y += t4.y; sum.z += t4.z; sum.w += t4.w;
+                    }
+                    const int m = m_base + row, nn = n0 + c4 * 4;
+                    if (row < rows_valid && m < g.M && nn < g.N) {
+#define TC_CALL_EPI(A_, G_) tc_epi4<A_, G_>(g, sum, m, nn, rowvec)
+                        TC_DISPATCH_EPI(g, TC_CALL_EPI);
+#undef TC_CALL_EPI
+                    }
+                }
+                __syncthreads();
+                // second round of tickets: the CTA that completes it puts the counter back to rest (nobody can still be
+                // polling: every CTA left the wait above before taking its second ticket)
+                if (threadIdx.x == 0 && atomicAdd(cnt, 1) == 2 * p.splits - 1) atomicExch(cnt, 0);
+            } else if (p.inkernel_reduce) {
                 // Few splits: the CTA that arrives last at the tile's ticket sums all partial tiles (fixed split order ->
                 // deterministic) straight out of L2 and runs the epilogue; nobody waits, so there is no co-residency
                 // requirement, and the second launch is saved.  Many splits keep the fully parallel reduce kernel.
@@ -692,6 +736,8 @@ static bool g_tc_single_pass = false; // opt-in plain-TF32 mode (one product ins
 // planner constants, re-measured after the elect.sync issue fix (tools/bench_gemm.py, tools/gpu_cost.sh sweep):
 // us per k-step of a 128- / 256-wide tile, us per split-K round trip (workspace + reduce launch)
 static float g_tc_cost[3] = {0.55f, 1.1f, 4.0f};
+static int g_tc_coop_reduce = 0;         // split-K: cooperative launch + per-tile rendezvous, reduction spread over the split CTAs
+static float g_tc_coop_cost = 2.0f;      // planner: us per split round trip in that mode
 static int g_tc_pdl_reduce = 0;
 static int g_tc_narrow_tiles = 0;
 static float g_tc_kstep64 = 0.4f;
@@ -774,10 +820,11 @@ static TcGeometry tc_geometry(const mugd_gemm& g, int sm_count, int forced_split
             const int per = (t.total_it + sp - 1) / sp;
             if (forced_split <= 0 && sp > 1 && per < 2) break;
             if (forced_split <= 0 && sp > 1 && tiles * sp > 2 * sm_count) break;   // bounds the workspace: < 2*SMs partial tiles
+            if (g_tc_coop_reduce && sp > 1 && tiles * sp > sm_count) break;          // cooperative reduce: the whole grid must be co-resident
             const int waves = (tiles * sp + sm_count - 1) / sm_count;
             // narrower tiles also shorten the epilogue (fewer columns per CTA): ~1 us per 64 columns on top of the fill
             const float fill = 1.0f + (g_tc_narrow_tiles ? 0.9f * (bn / 64 - 1) : 0.0f);
-            const float est = waves * (fill + kstep * per) + (sp > 1 ? (g_tc_cluster ? 2.0f : (sp <= g_tc_inkernel_max ? 1.0f + 0.6f * sp : g_tc_cost[2])) : 0.0f);
+            const float est = waves * (fill + kstep * per) + (sp > 1 ? (g_tc_cluster ? 2.0f : (g_tc_coop_reduce ? g_tc_coop_cost : (sp <= g_tc_inkernel_max ? 1.0f + 0.6f * sp : g_tc_cost[2]))) : 0.0f);
             if (est < best - 0.25f) { best = est; splits = sp; t.BN = bn; }
         }
     }
@@ -844,6 +891,20 @@ static int tc_launch(const CUtensorMap* tmAs, const CUtensorMap& tmWhi, const CU
         attr[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = g_use_pdl ? 2 : 1;
+        MUGD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, AT, MC>, tmA, tmA1, tmA2, tmWhi, tmWlo, p));
+        return MUGD_OK;
+    }
+    if (p.inkernel_reduce == 2) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid;
+        cfg.blockDim = dim3(TC_THREADS);
+        cfg.dynamicSmemBytes = TcSmem<BN, AT>::TOTAL;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeCooperative;
+        attr[0].val.cooperative = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
         MUGD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, AT, MC>, tmA, tmA1, tmA2, tmWhi, tmWlo, p));
         return MUGD_OK;
     }
@@ -927,6 +988,9 @@ int launch_gemm_tc(const DeviceInfo& dev, const mugd_gemm& g, cudaStream_t st, i
     p.single_pass = g_tc_single_pass ? 1 : 0;
     p.cluster = use_cluster ? 1 : 0;
     p.inkernel_reduce = (!use_cluster && t.splits > 1 && t.splits <= g_tc_inkernel_max && g.counters && g.n_counters >= t.gx * t.gy) ? 1 : 0;
+    if (g_tc_coop_reduce && !use_cluster && t.splits > 1 && t.mc == 1 && g.counters && g.n_counters >= t.gx * t.gy &&
+        t.gx * t.gy * t.splits <= dev.sm_count)
+        p.inkernel_reduce = 2;
     int rc;
 #define TC_GO(BN_, AT_, MC_) rc = tc_launch<BN_, AT_, MC_>(tmAs, tmWhi, tmWlo, p, t, st)
     if (!g_tc_a_in_tmem) {
@@ -971,6 +1035,12 @@ extern "C" int mugd_debug_set_tc_cost(float kstep128_us, float kstep256_us, floa
     if (kstep128_us > 0.f) mugd::g_tc_cost[0] = kstep128_us;
     if (kstep256_us > 0.f) mugd::g_tc_cost[1] = kstep256_us;
     if (split_us > 0.f) mugd::g_tc_cost[2] = split_us;
+    return MUGD_OK;
+}
+
+extern "C" int mugd_set_tc_coop_reduce(int enabled, float split_cost_us) {
+    mugd::g_tc_coop_reduce = enabled ? 1 : 0;
+    if (split_cost_us > 0.f) mugd::g_tc_coop_cost = split_cost_us;
     return MUGD_OK;
 }
 
