@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MUGD_ABI_VERSION 6
+#define MUGD_ABI_VERSION 7
 
 typedef struct mugd_handle mugd_handle;   /* one device + scratch state            */
 typedef struct mugd_plan mugd_plan;       /* validated launch plan (+ CUDA graph)  */
@@ -51,7 +51,8 @@ enum mugd_op_kind {
     MUGD_OP_TRANSPOSE = 7,     /* [B,C,L] <-> [B,L,C] with leading dimensions                                */
     MUGD_OP_COPY2D = 8,        /* strided row copy                                                           */
     MUGD_OP_STEP_ADVANCE = 9,  /* *step += 1                                                                 */
-    MUGD_OP_NOTES = 10         /* decoder logits -> ordered note list (OsuManiaConvertor.array_to_objects)   */
+    MUGD_OP_NOTES = 10,        /* decoder logits -> ordered note list (OsuManiaConvertor.array_to_objects)   */
+    MUGD_OP_EMBED = 11         /* prompt ids -> [B, H, F] embedding (BeatmapFeatureEmbedder.forward)         */
 };
 
 /* A-operand row addressing of MUGD_OP_GEMM (rows are tokens of B samples, Lout output rows each) */
@@ -158,12 +159,22 @@ typedef struct mugd_notes {
     int32_t B, T, K;
 } mugd_notes;
 
+/* Prompt embedding, mug/cond/feature.py:15-21 (BeatmapFeatureEmbedder.forward): out[b][h][f] = table[ids[b][f]][h], the
+ * nn.Embedding lookup followed by rearrange "b f h -> b h f".  ids must lie in [0, n_embed) (the host checks, like torch). */
+typedef struct mugd_embed {
+    const float* table;                    /* [n_embed, H] row-major                                         */
+    const int32_t* ids;                    /* [B, F]                                                         */
+    float* out;                            /* [B, H, F]                                                      */
+    int32_t B, F, H, n_embed;
+} mugd_embed;
+
 typedef struct mugd_op {
     int32_t kind;
     int32_t tag;                           /* free for the host (profiling labels)                          */
     union {
         mugd_gemm gemm; mugd_groupnorm gn; mugd_layernorm ln; mugd_attention attn; mugd_s4conv s4;
         mugd_ddim_update ddim; mugd_transpose tr; mugd_copy2d cp; mugd_step_advance adv; mugd_notes notes;
+        mugd_embed embed;
     } u;
 } mugd_op;
 
@@ -261,7 +272,7 @@ int  mugd_debug_set_tc_timing(long long* device_buf4);
 /* ---- utility ---------------------------------------------------------------------------------- */
 int  mugd_fill_i32(int32_t* dst, int32_t value, void* stream);
 /* sizeof() of {mugd_op, mugd_gemm, mugd_groupnorm, mugd_layernorm, mugd_attention, mugd_s4conv,
- * mugd_ddim_update, mugd_transpose, mugd_copy2d, mugd_notes} so a foreign-language mirror can verify its layout */
+ * mugd_ddim_update, mugd_transpose, mugd_copy2d, mugd_notes, mugd_embed} so a foreign-language mirror can verify its layout */
 int  mugd_abi_sizes(int32_t* out, int32_t n);
 
 #ifdef __cplusplus

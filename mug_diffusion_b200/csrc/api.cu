@@ -47,6 +47,7 @@ static int dispatch(mugd_handle* h, const mugd_op& op, cudaStream_t st, int* lau
         case MUGD_OP_COPY2D: return launch_copy2d(h->dev, op.u.cp, st, launches);
         case MUGD_OP_STEP_ADVANCE: return launch_step_advance(h->dev, op.u.adv, st, launches);
         case MUGD_OP_NOTES: return launch_notes(h->dev, op.u.notes, st, launches);
+        case MUGD_OP_EMBED: return launch_embed(h->dev, op.u.embed, st, launches);
         default:
             set_error("unknown op kind %d", op.kind);
             return MUGD_ERR_INVALID;
@@ -173,11 +174,11 @@ int mugd_plan_replay(mugd_plan* p, int32_t times, void* stream) {
 }
 
 int mugd_abi_sizes(int32_t* out, int32_t n) {
-    MUGD_REQUIRE(out && n >= 10, "abi_sizes: need room for 10 entries");
+    MUGD_REQUIRE(out && n >= 11, "abi_sizes: need room for 11 entries");
     out[0] = sizeof(mugd_op); out[1] = sizeof(mugd_gemm); out[2] = sizeof(mugd_groupnorm);
     out[3] = sizeof(mugd_layernorm); out[4] = sizeof(mugd_attention); out[5] = sizeof(mugd_s4conv);
     out[6] = sizeof(mugd_ddim_update); out[7] = sizeof(mugd_transpose); out[8] = sizeof(mugd_copy2d);
-    out[9] = sizeof(mugd_notes);
+    out[9] = sizeof(mugd_notes); out[10] = sizeof(mugd_embed);
     return MUGD_OK;
 }
 

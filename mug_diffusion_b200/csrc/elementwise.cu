@@ -198,6 +198,29 @@ int launch_notes(const DeviceInfo&, const mugd_notes& n, cudaStream_t st, int* l
     return MUGD_OK;
 }
 
+// ---- prompt embedding (mug/cond/feature.py:15-21): gather + "b f h -> b h f" ------------------------------------------
+// One CTA per (sample, feature slot): the table row is read coalesced, the store is strided by F (21 slots x 128 channels per
+// sample: 10 KB per request, latency only).
+__global__ void __launch_bounds__(128)
+embed_kernel(const mugd_embed e) {
+    pdl_trigger();
+    pdl_wait();
+    const int f = blockIdx.x, b = blockIdx.y;
+    const int id = e.ids[b * e.F + f];
+    const float* row = e.table + (int64_t)id * e.H;
+    float* out = e.out + (int64_t)b * e.H * e.F + f;
+    for (int h = threadIdx.x; h < e.H; h += blockDim.x) out[(int64_t)h * e.F] = row[h];
+}
+
+int launch_embed(const DeviceInfo&, const mugd_embed& e, cudaStream_t st, int* launches) {
+    MUGD_REQUIRE(e.B > 0 && e.F > 0 && e.H > 0 && e.n_embed > 0, "embed: bad shape B=%d F=%d H=%d n=%d", e.B, e.F, e.H, e.n_embed);
+    MUGD_REQUIRE(e.table && e.ids && e.out, "embed: null argument");
+    MUGD_REQUIRE(e.B <= 65535, "embed: B=%d too large for one launch", e.B);
+    MUGD_CHECK_CUDA(launch_k(embed_kernel, dim3(e.F, e.B), dim3(128), 0, st, e));
+    if (launches) *launches += 1;
+    return MUGD_OK;
+}
+
 }  // namespace mugd
 
 extern "C" int mugd_fill_i32(int32_t* dst, int32_t value, void* stream) {

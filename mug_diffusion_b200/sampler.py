@@ -19,6 +19,7 @@ import torch
 from . import lib as L_
 from .config import DecoderConfig, ModelConfig, UNetConfig
 from .engine import OpList
+from .prompt import PromptEmbedder
 from .runtime import MugEngine, Session, _ptr
 
 try:  # the reference falls back to tqdm when no tqdm_class is given (ddim.py:133-135)
@@ -60,6 +61,9 @@ def ddim_parameters(alphas_cumprod: torch.Tensor, ts: np.ndarray, eta: float):
 # --------------------------------------------------------------------------------------------------
 # model holder with the attributes the callers read
 # --------------------------------------------------------------------------------------------------
+PROMPT_TABLE_KEY = "model.cond_stage_model.embedding.weight"
+
+
 class _Wrapper:
     """Stands where ``MugDiffusionWrapper`` stands: ``.forward(x, t, c, w)`` and ``.decode(z)``."""
 
@@ -90,6 +94,16 @@ class _Wrapper:
             B, _, Lz = z.shape
             return o.engine.decoder_session(B, Lz).decode(z)
 
+
+    @torch.no_grad()
+    def cond_stage_model(self, feature: torch.Tensor) -> torch.Tensor:
+        """Stands where ``model.model.cond_stage_model`` stands (webui.py:186-193): BeatmapFeatureEmbedder.forward,
+        ids ``[B, F]`` -> conditioning ``[B, 128, F]`` (mug/cond/feature.py:15-21), one gather kernel."""
+        o = self._o
+        if o.prompt_embedder is None:
+            raise RuntimeError("this model was built without the prompt embedding table "
+                               "(state_dict key 'model.cond_stage_model.embedding.weight')")
+        return o.prompt_embedder(feature)
 
     @torch.no_grad()
     def wave_model(self, mel: torch.Tensor):
@@ -129,7 +143,13 @@ class MugDiffusionB200:
         sch = register_schedule(self.cfg.timesteps, self.cfg.linear_start, self.cfg.linear_end)
         for k, v in sch.items():
             setattr(self, k, v.to(self.device))
+        emb = None if state_dict is None else state_dict.get(PROMPT_TABLE_KEY)
+        self.prompt_embedder = PromptEmbedder(self.engine, emb) if emb is not None else None
         self.model = _Wrapper(self)
+
+    def set_prompt_table(self, weight: torch.Tensor):
+        """attach / replace the [n_embed, 128] prompt embedding table (``cond_stage_model.embedding.weight``)"""
+        self.prompt_embedder = PromptEmbedder(self.engine, weight)
 
     @classmethod
     def from_state_dict(cls, sd, cfg=None, z_length=512, device=None, gemm_impl="auto"):

@@ -414,3 +414,43 @@ def array_to_objects(note_array: np.ndarray, key_count: int, frame_ms: float) ->
             out.append((line, start))
     out.sort(key=lambda t: t[1])
     return [t[0] for t in out]
+
+
+# ---------------------------------------------------------------------------------------------------
+# Prompt path.  TEST INFRASTRUCTURE like the rest of this file.
+# ---------------------------------------------------------------------------------------------------
+def feature_rows(x):
+    """mug/util.py:50-60 count_beatmap_features_embedding"""
+    import math
+    if x["type"] == "numeric":
+        return int(math.ceil((x["max"] - x["min"]) / x["interval"])) + 1
+    if x["type"] == "category":
+        return len(x["category"]) + 1
+    if x["type"] == "bool":
+        return 3
+    raise ValueError(str(x))
+
+
+def feature_ids(feature_dict, feature_yaml):
+    """mug/util.py:62-84 feature_dict_to_embedding_ids, restated as (offset of the slot's row block) + (bin within it)"""
+    out, offset = [], 0
+    for spec in feature_yaml:
+        v = feature_dict.get(spec["name"])
+        if v is None:
+            b = 0                                                       # :67-68 missing
+        elif spec["type"] == "numeric":
+            v = max(spec["min"], min(spec["max"], v))                   # :71
+            b = int((v - spec["min"]) / spec["interval"]) + 1           # :72, :80
+        elif spec["type"] == "bool":
+            b = v + 1                                                   # :74, :80
+        else:
+            b = spec["category"].index(v) + 1                           # :77 (ValueError for an unknown value), :80
+        for _ in range(spec.get("count", 1)):                           # :81-83
+            out.append(offset + b)
+            offset += feature_rows(spec)
+    return out
+
+
+def prompt_embed(table: torch.Tensor, ids: torch.Tensor) -> torch.Tensor:
+    """mug/cond/feature.py:15-21: embedding(x.long()) then 'b f h -> b h f'"""
+    return table[ids.long()].permute(0, 2, 1).contiguous()

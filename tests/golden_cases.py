@@ -90,3 +90,17 @@ def synthetic_note_logits(B: int = 3, T: int = 700, seed: int = 9) -> torch.Tens
     x[1, 9, T - 39:] = 2.0
     x[2, 2, 10:20] = 1.0                   # back-to-back starts
     return x
+
+
+# ---- prompt path: feature dicts whose ids / embeddings are pinned to the reference in tests/golden/prompt.json
+PROMPT_DICTS = [
+    {},                                                        # the unconditional prompt (webui uc)
+    {"sr": 6.4, "ln_ratio": 0.0, "rc": True},                  # the reference's own examples, mug/util.py:164-179
+    {"sr": 6.2, "ln_ratio": 0.5, "rc": False},
+    {"sr": 0, "ln_ratio": 0.5, "rc": True},                    # below min -> clamped
+    {"sr": 0.6, "hb": True},
+    {"sr": 99.0, "ln_ratio": 1.0, "ett": 35, "stamina_ett": 5},      # above max / at the edges
+    {"sr": 3, "rank_status": "ranked", "rc": 1, "ln_ratio": 0},      # the SURVEY 8d bench prompt
+    {"sr": 4.19999, "rank_status": "graveyard", "ln": False, "stamina": True, "stream_ett": 17.9},
+    {"sr": 7.999, "rank_status": "loved", "hb": 0, "ln_ratio": 0.95},
+]

@@ -139,6 +139,29 @@ def make_wave():
     print([tuple(h.shape) for h in hs])
 
 
+def make_prompt():
+    """Prompt path: the reference's feature_dict_to_embedding_ids on a set of feature dicts (its own examples,
+    mug/util.py:164-179, plus clamping / missing / count>1 / category cases) and BeatmapFeatureEmbedder.forward on those ids
+    with a seeded table.  The parsed feature spec travels with the golden (the GPU box has no /root/reference)."""
+    import json
+    import yaml
+    ref_shim.install_shims()
+    from mug.cond.feature import BeatmapFeatureEmbedder
+    from mug.util import count_beatmap_features, feature_dict_to_embedding_ids
+    ypath = os.path.join(ref_shim.REF_ROOT, "configs", "mug", "mania_beatmap_features.yaml")
+    spec = yaml.safe_load(open(ypath))
+    ids = [feature_dict_to_embedding_ids(d, spec) for d in gc.PROMPT_DICTS]
+    emb = BeatmapFeatureEmbedder(ypath, 128)
+    g = torch.Generator().manual_seed(77)
+    with torch.no_grad():
+        emb.embedding.weight.copy_(torch.randn(emb.embedding.weight.shape, generator=g))
+        out = emb(torch.tensor(np.asarray(ids), dtype=torch.float32))       # float ids, as webui.py:191 passes them
+    json.dump(dict(spec=spec, dicts=gc.PROMPT_DICTS, ids=ids, n_embed=count_beatmap_features(spec)),
+              open(os.path.join(GOLD, "prompt.json"), "w"), indent=1)
+    save("prompt_embed", table=emb.embedding.weight.detach().numpy(), out=out.numpy())
+    print("prompt:", len(ids), "dicts,", len(ids[0]), "slots, table", tuple(emb.embedding.weight.shape))
+
+
 def make_hit_objects():
     """OsuManiaConvertor.array_to_objects of the UNMODIFIED reference on the golden decoder logits (and on a synthetic
     logit array that exercises long notes running to the last frame, back-to-back starts and clipped offsets)."""
@@ -177,5 +200,7 @@ if __name__ == "__main__":
         make_wave()
     if a.only in (None, "notes"):
         make_hit_objects()
+    if a.only in (None, "prompt"):
+        make_prompt()
 
 
