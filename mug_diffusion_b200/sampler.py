@@ -234,18 +234,20 @@ class DDIMSampler(object):
         return self.ddim_sampling(w, c, size, callback=callback, img_callback=img_callback, mask=mask, x0=x0,
                                   noise_dropout=noise_dropout, temperature=temperature, x_T=x_T, log_every_t=log_every_t,
                                   unconditional_guidance_scale=unconditional_guidance_scale,
-                                  unconditional_conditioning=unconditional_conditioning, tqdm_class=tqdm_class)
+                                  unconditional_conditioning=unconditional_conditioning, tqdm_class=tqdm_class,
+                                  match_reference_rng=bool(kwargs.get("match_reference_rng", False)))
 
     @torch.no_grad()
     def ddim_sampling(self, w, c, shape, x_T=None, callback=None, mask=None, x0=None, img_callback=None,
                       log_every_t=100, temperature=1., noise_dropout=0., unconditional_guidance_scale=1.,
-                      unconditional_conditioning=None, tqdm_class=None, progress=True):
+                      unconditional_conditioning=None, tqdm_class=None, progress=True, match_reference_rng=False):
         model = self.model
         eng = model.engine
         dev = self.device
         B, Cz, Lz = shape
-        if noise_dropout > 0.:
-            raise NotImplementedError("noise_dropout > 0 is not supported by the B200 sampler")
+        # the reference draws (and, with noise_dropout, masks) noise every step even when sigma == 0 (ddim.py:192-194); the
+        # draw is skipped here unless it can change the result or the caller asks for the same global-RNG consumption
+        match_rng = bool(match_reference_rng)
         with eng.lock:
             x = torch.randn(shape, device=dev) if x_T is None else x_T.to(dev, torch.float32)
             cfg_on = not (unconditional_conditioning is None or unconditional_guidance_scale == 1.)
@@ -317,8 +319,12 @@ class DDIMSampler(object):
                     x_orig = model.q_sample(x0.to(dev), tsb)
                     xm = x_orig * mask + (1. - mask) * current_x()
                     sess.load_x(xm, dup=cfg_on)
-                if has_noise:
+                if has_noise or match_rng:
                     nz = torch.randn(shape, device=dev)                      # ddim.py:192
+                    if noise_dropout > 0.:
+                        # dropout(sigma * n * T) == sigma * T * dropout(n): same Bernoulli draw, same 1/(1-p) scale (:193-194)
+                        nz = torch.nn.functional.dropout(nz, p=noise_dropout)
+                if has_noise:
                     ops = OpList()
                     ops.transpose(_ptr(nz), _ptr(noise_nlc), 0, Cz, B, Cz, Lz, True)
                     eng.run_ops(ops)

@@ -347,8 +347,10 @@ def make_schedule(S: int, eta: float = 0.0, timesteps: int = 1000, linear_start:
 def ddim_sample(p: Params, S: int, c: torch.Tensor, w: Sequence[torch.Tensor], x_T: torch.Tensor,
                 scale: float = 1.0, uc: Optional[torch.Tensor] = None, eta: float = 0.0,
                 cfg: dict = DEFAULT_UNET, noise_gen: Optional[torch.Generator] = None,
-                return_eps: bool = False):
-    """DDIMSampler.ddim_sampling + p_sample_ddim  -- mug/diffusion/ddim.py:110-196 (mask=None path)."""
+                return_eps: bool = False, noise_seq: Optional[Sequence[torch.Tensor]] = None, temperature: float = 1.0):
+    """DDIMSampler.ddim_sampling + p_sample_ddim  -- mug/diffusion/ddim.py:110-196 (mask=None path).
+    ``noise_seq[i]`` replaces the i-th ``noise_like`` draw (:192), already passed through ``dropout`` (:193-194) if any, so a
+    test can hand the exact per-step noise of another RNG stream to this restatement."""
     sch = make_schedule(S, eta)
     ts = sch["timesteps"]
     x = x_T
@@ -373,7 +375,8 @@ def ddim_sample(p: Params, S: int, c: torch.Tensor, w: Sequence[torch.Tensor], x
         s1m = torch.full((B, 1, 1), float(sch["sqrt_one_minus_alphas"][index]))
         pred_x0 = (x - s1m * e_t) / a_t.sqrt()
         dir_xt = (1.0 - a_prev - sigma_t ** 2).sqrt() * e_t
-        noise = sigma_t * torch.randn(x.shape, generator=noise_gen)
+        raw = noise_seq[i] if noise_seq is not None else torch.randn(x.shape, generator=noise_gen)
+        noise = sigma_t * raw * temperature                                  # :192
         x = a_prev.sqrt() * pred_x0 + dir_xt + noise
     if return_eps:
         return x, eps_list

@@ -157,6 +157,58 @@ def test_eta_noise_path_runs_and_is_seeded():
     assert torch.isfinite(outs[0]).all() and torch.equal(outs[0], outs[1])
 
 
+@pytest.mark.parametrize("dropout", [0.0, 0.25])
+def test_eta_noise_and_noise_dropout_match_oracle(dropout):
+    """eta = 1 (sigma > 0), temperature != 1 and noise_dropout (ddim.py:192-194) against the CPU oracle fed with the very noise
+    the GPU run draws: the sampler's only RNG calls are randn(shape) [+ dropout] per step on the CUDA generator, so re-seeding
+    and repeating them here reproduces the sequence"""
+    L, B, S = 96, 2, 5
+    m = model_for(L)
+    inp = synth.synthetic_inputs(B, L)
+    sampler = DDIMSampler(m)
+    torch.cuda.manual_seed(123)
+    z, _ = sampler.sample(S=S, c=inp["c"].cuda(), w=[w.cuda() for w in inp["w"]], batch_size=B, verbose=False, x_T=inp["x_T"].cuda(),
+                          eta=1.0, shape=(16, L), temperature=0.8, noise_dropout=dropout, unconditional_guidance_scale=3.0,
+                          unconditional_conditioning=inp["uc"].cuda())
+    torch.cuda.manual_seed(123)
+    seq = []
+    for _ in range(S):
+        nz = torch.randn((B, 16, L), device="cuda")
+        if dropout > 0:
+            nz = torch.nn.functional.dropout(nz, p=dropout)
+        seq.append(nz.cpu())
+    with torch.no_grad():
+        ref = orc.ddim_sample(synth.synthetic_state_dict(L), S, inp["c"], inp["w"], inp["x_T"], scale=3.0, uc=inp["uc"], eta=1.0,
+                              noise_seq=seq, temperature=0.8)
+    assert rel_err(z, ref) < 2e-4
+    if dropout > 0:
+        assert any((t == 0).any() for t in seq)
+
+
+def test_match_reference_rng_consumes_the_generator_like_the_reference():
+    """at eta = 0 the reference still draws randn(shape) every step (ddim.py:192); with match_reference_rng the CUDA generator
+    ends where S draws leave it, without it the generator is untouched -- and the samples are identical either way"""
+    L, B, S = 96, 1, 4
+    m = model_for(L)
+    inp = synth.synthetic_inputs(B, L)
+    sampler = DDIMSampler(m)
+    kw = dict(S=S, c=inp["c"].cuda(), w=[w.cuda() for w in inp["w"]], batch_size=B, verbose=False, x_T=inp["x_T"].cuda(), shape=(16, L))
+    torch.cuda.manual_seed(5)
+    z0, _ = sampler.sample(**kw)
+    after_plain = torch.randn(4, device="cuda")
+    torch.cuda.manual_seed(5)
+    z1, _ = sampler.sample(match_reference_rng=True, **kw)
+    after_match = torch.randn(4, device="cuda")
+    torch.cuda.manual_seed(5)
+    for _ in range(S):
+        torch.randn((B, 16, L), device="cuda")
+    want = torch.randn(4, device="cuda")
+    torch.cuda.manual_seed(5)
+    untouched = torch.randn(4, device="cuda")
+    assert torch.equal(z0, z1)
+    assert torch.equal(after_match, want) and torch.equal(after_plain, untouched)
+
+
 def test_mask_branch_with_zero_mask_is_identity():
     """ddim.py:141-144 inpainting blend x = q_sample(x0,t)*mask + (1-mask)*x : with mask == 0 the trajectory must equal
     the unmasked one bit for bit (the noisy x0 is multiplied by zero), which exercises the per-step host round trip"""
