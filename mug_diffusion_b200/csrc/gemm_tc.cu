@@ -30,6 +30,9 @@
 
 namespace mugd {
 
+#ifndef MUGD_TC_DECOUPLED
+#define MUGD_TC_DECOUPLED 1      // measured: Beff=64 step 14.43 -> 13.90 ms, conv3 640->256 k-step 1.10 -> 1.02 us (0 = coupled stages)
+#endif
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;                 // fp32 elements per k-step = 128 bytes = one swizzle row
 constexpr int TC_THREADS = 256;
@@ -197,7 +200,13 @@ struct TcSmem {
     static constexpr uint32_t A_BUFS = AT ? 1 : 2;            // AT: only the raw tile lives in smem (hi/lo go to TMEM)
     static constexpr uint32_t STAGE_BYTES = A_BUFS * TC_A_BYTES + 2 * B_BYTES;
     static constexpr int STAGES = AT ? ((BN == 256) ? 2 : (BN == 128 ? 4 : 6)) : ((BN == 256) ? 2 : (BN == 128 ? 3 : 4));
-    static constexpr uint32_t TILE_BYTES = STAGES * STAGE_BYTES;
+    // Decoupled rings (256-wide tiles): only two 64 KB weight stages fit, and tied to the A tile they sat idle while the
+    // activations were fetched and split.  With its own 4-deep ring (16 KB per stage + a TMEM slot) the A side runs ahead and a
+    // weight stage is occupied only from its TMA to the retirement of its MMAs.
+    static constexpr bool DEC = AT && BN == 256 && (MUGD_TC_DECOUPLED != 0);
+    static constexpr int SA = DEC ? 4 : STAGES;
+    static constexpr int SW = DEC ? 2 : STAGES;
+    static constexpr uint32_t TILE_BYTES = DEC ? SA * TC_A_BYTES + SW * 2 * B_BYTES : STAGES * STAGE_BYTES;
     static constexpr uint32_t TOTAL = TILE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -296,22 +305,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     using S = TcSmem<BN, AT>;
     constexpr int STAGES = S::STAGES;
     // TMEM columns: accumulator [0, BN), then (AT) per stage 32 columns a_hi + 32 columns a_lo
-    constexpr int TMEM_NEED = AT ? BN + STAGES * 64 : BN;
+    constexpr bool DEC = S::DEC && MC == 1;
+    constexpr int SA = DEC ? S::SA : STAGES;            // A ring = TMEM operand slots
+    constexpr int SW = DEC ? S::SW : STAGES;            // weight ring
+    constexpr int TMEM_NEED = AT ? BN + SA * 64 : BN;
     constexpr int TMEM_COLS = TMEM_NEED <= 64 ? 64 : (TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512));
     static_assert(TMEM_NEED <= 512, "tensor memory budget");
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // SWIZZLE_128B needs 1024-B alignment
     const uint32_t bars = base + S::TILE_BYTES;                          // barrier block (8-byte aligned)
     // barrier addresses: full[s], conv[s], empty[s], accum ; tmem ptr slot after them
+    // decoupled rings add: afree[s] (A smem slot read by the converter), wfull[s] / wfree[s] (weight stage landed / retired);
+    // bar_empty[s] then means "TMEM operand slot s retired"
     auto bar_full = [&](int s) { return bars + 8u * s; };
-    auto bar_conv = [&](int s) { return bars + 8u * (STAGES + s); };
-    auto bar_empty = [&](int s) { return bars + 8u * (2 * STAGES + s); };
-    const uint32_t bar_accum = bars + 8u * (3 * STAGES);
-    const uint32_t tmem_slot = bars + 8u * (3 * STAGES + 1);
-    auto a_hi = [&](int s) { return base + s * S::STAGE_BYTES; };
+    auto bar_conv = [&](int s) { return bars + 8u * (SA + s); };
+    auto bar_empty = [&](int s) { return bars + 8u * (2 * SA + s); };
+    auto bar_afree = [&](int s) { return bars + 8u * (3 * SA + s); };
+    auto bar_wfull = [&](int s) { return bars + 8u * (4 * SA + s); };
+    auto bar_wfree = [&](int s) { return bars + 8u * (4 * SA + SW + s); };
+    const uint32_t bar_accum = bars + 8u * (DEC ? 4 * SA + 2 * SW : 3 * STAGES);
+    const uint32_t tmem_slot = bar_accum + 8u;
+    static_assert(8 * (DEC ? 4 * SA + 2 * SW + 2 : 3 * STAGES + 2) <= 256, "barrier block");
+    auto a_hi = [&](int s) { return DEC ? base + s * TC_A_BYTES : base + s * S::STAGE_BYTES; };
     auto a_lo = [&](int s) { return base + s * S::STAGE_BYTES + TC_A_BYTES; };
-    auto b_hi = [&](int s) { return base + s * S::STAGE_BYTES + S::A_BUFS * TC_A_BYTES; };
-    auto b_lo = [&](int s) { return base + s * S::STAGE_BYTES + S::A_BUFS * TC_A_BYTES + S::B_BYTES; };
+    auto b_hi = [&](int s) { return DEC ? base + SA * TC_A_BYTES + s * 2 * S::B_BYTES : base + s * S::STAGE_BYTES + S::A_BUFS * TC_A_BYTES; };
+    auto b_lo = [&](int s) { return b_hi(s) + S::B_BYTES; };
 
     const mugd_gemm& g = p.g;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -338,10 +356,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool dbg_cta = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
     // ---- one-time setup ------------------------------------------------------------------------------
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) {
+        for (int s = 0; s < SA; ++s) {
             mbar_init(bar_full(s), 1);
             mbar_init(bar_conv(s), 4);        // one arrival per converter warp
             mbar_init(bar_empty(s), MC);      // one commit per CTA of the cluster
+            if constexpr (DEC) mbar_init(bar_afree(s), 4);
+        }
+        if constexpr (DEC) {
+            for (int s = 0; s < SW; ++s) {
+                mbar_init(bar_wfull(s), 1);
+                mbar_init(bar_wfree(s), 1);
+            }
         }
         mbar_init(bar_accum, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -366,15 +391,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         {
             const uint32_t a_tx = (uint32_t)(p.box_l * p.box_b) * TC_BK * 4;
             for (int i = 0; i < nit; ++i) {
-                const int s = i % STAGES;
-                const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
-                mbar_wait(bar_empty(s), ph ^ 1u);
+                const int s = i % SA;
+                const uint32_t ph = (uint32_t)(i / SA) & 1u;
+                if constexpr (DEC) mbar_wait(bar_afree(s), ph ^ 1u);
+                else mbar_wait(bar_empty(s), ph ^ 1u);
                 if (elect_one()) {
                 if (dbg_cta && i < 24) p.dbg[8 + i * 6 + 5] = gtimer();
                 const int it = it_begin + i;
                 const int t = it / p.kblocks;
                 const int kb = it - t * p.kblocks;
-                mbar_expect_tx(bar_full(s), a_tx + (p.single_pass ? 1u : 2u) * S::B_BYTES);
+                mbar_expect_tx(bar_full(s), DEC ? a_tx : a_tx + (p.single_pass ? 1u : 2u) * S::B_BYTES);
                 // row addressing per tap: SAME = l+t-1, TAPS = l+t+shift (zero fill outside the sample by TMA bounds);
                 // DOWN (stride 2, right pad) uses one strided tensor map per tap (row l of map t = source row 2l+t)
                 const CUtensorMap* ma = &tmA;
@@ -389,11 +415,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     tma_load_2d_mc(b_hi(s) + doff, &tmWhi, bar_full(s), t * g.K + kb * TC_BK, n0 + (int)crank * part, (uint16_t)((1u << MC) - 1u));
                     if (!p.single_pass)
                         tma_load_2d_mc(b_lo(s) + doff, &tmWlo, bar_full(s), t * g.K + kb * TC_BK, n0 + (int)crank * part, (uint16_t)((1u << MC) - 1u));
-                } else {
+                } else if constexpr (!DEC) {
                     tma_load_2d(b_hi(s), &tmWhi, bar_full(s), t * g.K + kb * TC_BK, n0);
                     if (!p.single_pass) tma_load_2d(b_lo(s), &tmWlo, bar_full(s), t * g.K + kb * TC_BK, n0);
                 }
                 if (dbg_cta && i < 24) p.dbg[8 + i * 6 + 0] = gtimer();
+                }
+                __syncwarp();
+            }
+        }
+    } else if (DEC && warp == 3) {
+        // ===================================== weight producer (decoupled rings) ================
+        if constexpr (DEC) {
+            for (int i = 0; i < nit; ++i) {
+                const int s = i % SW;
+                const uint32_t ph = (uint32_t)(i / SW) & 1u;
+                mbar_wait(bar_wfree(s), ph ^ 1u);
+                if (elect_one()) {
+                    const int it = it_begin + i;
+                    const int t = it / p.kblocks;
+                    const int kb = it - t * p.kblocks;
+                    mbar_expect_tx(bar_wfull(s), (p.single_pass ? 1u : 2u) * S::B_BYTES);
+                    tma_load_2d(b_hi(s), &tmWhi, bar_wfull(s), t * g.K + kb * TC_BK, n0);
+                    if (!p.single_pass) tma_load_2d(b_lo(s), &tmWlo, bar_wfull(s), t * g.K + kb * TC_BK, n0);
                 }
                 __syncwarp();
             }
@@ -405,13 +449,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // A/B K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
             for (int i = 0; i < nit; ++i) {
-                const int s = i % STAGES;
-                const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+                const int s = i % SA;
+                const uint32_t ph = (uint32_t)(i / SA) & 1u;
+                const int sw = DEC ? i % SW : s;
                 mbar_wait(bar_conv(s), ph);
+                if constexpr (DEC) mbar_wait(bar_wfull(sw), (uint32_t)(i / SW) & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (elect_one()) {
                 if (dbg_cta && i < 24) p.dbg[8 + i * 6 + 3] = gtimer();
-                const uint64_t dbh = umma_desc(b_hi(s)), dbl = umma_desc(b_lo(s));
+                const uint64_t dbh = umma_desc(b_hi(sw)), dbl = umma_desc(b_lo(sw));
                 if constexpr (AT) {
                     const uint32_t ta_hi = tmem_base + (uint32_t)(BN + s * 64), ta_lo = ta_hi + 32u;
 #pragma unroll
@@ -440,7 +486,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 }
                 if constexpr (MC > 1) umma_commit_mc(bar_empty(s), (uint16_t)((1u << MC) - 1u));
-                else umma_commit(bar_empty(s));                       // stage reusable once these MMAs retire
+                else umma_commit(bar_empty(s));                       // stage (decoupled: TMEM operand slot) reusable once these MMAs retire
+                if constexpr (DEC) umma_commit(bar_wfree(sw));        // ... and the weight stage
                 if (dbg_cta && i < 24) p.dbg[8 + i * 6 + 4] = gtimer();
                 }
                 __syncwarp();
@@ -451,9 +498,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ===================================== converter ========================================
         const int ct = threadIdx.x - 128;                             // 0..127
         for (int i = 0; i < nit; ++i) {
-            const int s = i % STAGES;
-            const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+            const int s = i % SA;
+            const uint32_t ph = (uint32_t)(i / SA) & 1u;
             mbar_wait(bar_full(s), ph);
+            if constexpr (DEC) {
+                mbar_wait(bar_empty(s), ph ^ 1u);                     // the MMAs that read TMEM slot s last time have retired
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            }
             if (dbg_cta && ct == 0 && i < 24) p.dbg[8 + i * 6 + 1] = gtimer();
             if constexpr (AT) {
                 // thread = tile row (= TMEM lane): read the row's 128 bytes out of the 128B-swizzled tile (16-byte chunk c
@@ -491,7 +542,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA (async proxy)
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_conv(s));
+            if (lane == 0) {
+                mbar_arrive(bar_conv(s));
+                if constexpr (DEC) mbar_arrive(bar_afree(s));         // the raw tile has been read: its smem slot may be refilled
+            }
             if (dbg_cta && ct == 0 && i < 24) p.dbg[8 + i * 6 + 2] = gtimer();
         }
         // ===================================== epilogue =========================================
