@@ -201,12 +201,14 @@ struct TcSmem {
     static constexpr uint32_t STAGE_BYTES = A_BUFS * TC_A_BYTES + 2 * B_BYTES;
     static constexpr int STAGES = AT ? ((BN == 256) ? 2 : (BN == 128 ? 4 : 6)) : ((BN == 256) ? 2 : (BN == 128 ? 3 : 4));
     // Decoupled rings (256-wide tiles): only two 64 KB weight stages fit, and tied to the A tile they sat idle while the
-    // activations were fetched and split.  With its own 4-deep ring (16 KB per stage + a TMEM slot) the A side runs ahead and a
-    // weight stage is occupied only from its TMA to the retirement of its MMAs.
+    // activations were fetched and split.  Decoupled, the A side is a 2-deep smem ring feeding a 4-deep ring of TMEM operand
+    // slots and runs ahead, and the freed shared memory holds a THIRD weight stage; a weight stage is occupied only from its TMA
+    // to the retirement of its MMAs.
     static constexpr bool DEC = AT && BN == 256 && (MUGD_TC_DECOUPLED != 0);
-    static constexpr int SA = DEC ? 4 : STAGES;
-    static constexpr int SW = DEC ? 2 : STAGES;
-    static constexpr uint32_t TILE_BYTES = DEC ? SA * TC_A_BYTES + SW * 2 * B_BYTES : STAGES * STAGE_BYTES;
+    static constexpr int SAS = DEC ? 2 : STAGES;           // raw activation tiles in shared memory
+    static constexpr int SA = DEC ? 4 : STAGES;            // split activation tiles in tensor memory
+    static constexpr int SW = DEC ? 3 : STAGES;            // weight stages (hi + lo)
+    static constexpr uint32_t TILE_BYTES = DEC ? SAS * TC_A_BYTES + SW * 2 * B_BYTES : STAGES * STAGE_BYTES;
     static constexpr uint32_t TOTAL = TILE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -306,7 +308,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int STAGES = S::STAGES;
     // TMEM columns: accumulator [0, BN), then (AT) per stage 32 columns a_hi + 32 columns a_lo
     constexpr bool DEC = S::DEC && MC == 1;
-    constexpr int SA = DEC ? S::SA : STAGES;            // A ring = TMEM operand slots
+    constexpr int SAS = DEC ? S::SAS : STAGES;          // raw A tiles in smem
+    constexpr int SA = DEC ? S::SA : STAGES;            // TMEM operand slots
     constexpr int SW = DEC ? S::SW : STAGES;            // weight ring
     constexpr int TMEM_NEED = AT ? BN + SA * 64 : BN;
     constexpr int TMEM_COLS = TMEM_NEED <= 64 ? 64 : (TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512));
@@ -317,18 +320,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // barrier addresses: full[s], conv[s], empty[s], accum ; tmem ptr slot after them
     // decoupled rings add: afree[s] (A smem slot read by the converter), wfull[s] / wfree[s] (weight stage landed / retired);
     // bar_empty[s] then means "TMEM operand slot s retired"
-    auto bar_full = [&](int s) { return bars + 8u * s; };
-    auto bar_conv = [&](int s) { return bars + 8u * (SA + s); };
-    auto bar_empty = [&](int s) { return bars + 8u * (2 * SA + s); };
-    auto bar_afree = [&](int s) { return bars + 8u * (3 * SA + s); };
-    auto bar_wfull = [&](int s) { return bars + 8u * (4 * SA + s); };
-    auto bar_wfree = [&](int s) { return bars + 8u * (4 * SA + SW + s); };
-    const uint32_t bar_accum = bars + 8u * (DEC ? 4 * SA + 2 * SW : 3 * STAGES);
+    auto bar_full = [&](int s) { return bars + 8u * s; };                              // [SAS] raw A tile landed
+    auto bar_conv = [&](int s) { return bars + 8u * (SAS + s); };                      // [SA]  split A in its TMEM slot
+    auto bar_empty = [&](int s) { return bars + 8u * (SAS + SA + s); };                // [SA]  coupled: stage free; decoupled: TMEM slot retired
+    auto bar_afree = [&](int s) { return bars + 8u * (SAS + 2 * SA + s); };            // [SAS] raw A tile consumed
+    auto bar_wfull = [&](int s) { return bars + 8u * (2 * SAS + 2 * SA + s); };        // [SW]
+    auto bar_wfree = [&](int s) { return bars + 8u * (2 * SAS + 2 * SA + SW + s); };   // [SW]
+    const uint32_t bar_accum = bars + 8u * (DEC ? 2 * SAS + 2 * SA + 2 * SW : 3 * STAGES);
     const uint32_t tmem_slot = bar_accum + 8u;
-    static_assert(8 * (DEC ? 4 * SA + 2 * SW + 2 : 3 * STAGES + 2) <= 256, "barrier block");
+    static_assert(8 * (DEC ? 2 * SAS + 2 * SA + 2 * SW + 2 : 3 * STAGES + 2) <= 256, "barrier block");
     auto a_hi = [&](int s) { return DEC ? base + s * TC_A_BYTES : base + s * S::STAGE_BYTES; };
     auto a_lo = [&](int s) { return base + s * S::STAGE_BYTES + TC_A_BYTES; };
-    auto b_hi = [&](int s) { return DEC ? base + SA * TC_A_BYTES + s * 2 * S::B_BYTES : base + s * S::STAGE_BYTES + S::A_BUFS * TC_A_BYTES; };
+    auto b_hi = [&](int s) { return DEC ? base + SAS * TC_A_BYTES + s * 2 * S::B_BYTES : base + s * S::STAGE_BYTES + S::A_BUFS * TC_A_BYTES; };
     auto b_lo = [&](int s) { return b_hi(s) + S::B_BYTES; };
 
     const mugd_gemm& g = p.g;
@@ -357,9 +360,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ---- one-time setup ------------------------------------------------------------------------------
     if (threadIdx.x == 0) {
         for (int s = 0; s < SA; ++s) {
-            mbar_init(bar_full(s), 1);
             mbar_init(bar_conv(s), 4);        // one arrival per converter warp
             mbar_init(bar_empty(s), MC);      // one commit per CTA of the cluster
+        }
+        for (int s = 0; s < SAS; ++s) {
+            mbar_init(bar_full(s), 1);
             if constexpr (DEC) mbar_init(bar_afree(s), 4);
         }
         if constexpr (DEC) {
@@ -391,8 +396,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         {
             const uint32_t a_tx = (uint32_t)(p.box_l * p.box_b) * TC_BK * 4;
             for (int i = 0; i < nit; ++i) {
-                const int s = i % SA;
-                const uint32_t ph = (uint32_t)(i / SA) & 1u;
+                const int s = i % SAS;
+                const uint32_t ph = (uint32_t)(i / SAS) & 1u;
                 if constexpr (DEC) mbar_wait(bar_afree(s), ph ^ 1u);
                 else mbar_wait(bar_empty(s), ph ^ 1u);
                 if (elect_one()) {
@@ -498,11 +503,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ===================================== converter ========================================
         const int ct = threadIdx.x - 128;                             // 0..127
         for (int i = 0; i < nit; ++i) {
-            const int s = i % SA;
-            const uint32_t ph = (uint32_t)(i / SA) & 1u;
-            mbar_wait(bar_full(s), ph);
+            const int s = i % SA;                                     // TMEM operand slot
+            const int sm = i % SAS;                                   // raw tile in shared memory
+            mbar_wait(bar_full(sm), (uint32_t)(i / SAS) & 1u);
             if constexpr (DEC) {
-                mbar_wait(bar_empty(s), ph ^ 1u);                     // the MMAs that read TMEM slot s last time have retired
+                mbar_wait(bar_empty(s), ((uint32_t)(i / SA) & 1u) ^ 1u);   // the MMAs that read TMEM slot s last time have retired
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             }
             if (dbg_cta && ct == 0 && i < 24) p.dbg[8 + i * 6 + 1] = gtimer();
@@ -510,7 +515,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 // thread = tile row (= TMEM lane): read the row's 128 bytes out of the 128B-swizzled tile (16-byte chunk c
                 // of row r sits at chunk c ^ (r & 7)), split, and store hi / lo to this stage's TMEM columns
                 const int r = (warp & 3) * 32 + lane;
-                const uint32_t rowaddr = a_hi(s) + (uint32_t)r * 128u;
+                const uint32_t rowaddr = a_hi(sm) + (uint32_t)r * 128u;
                 float hi[32], lo[32];
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
@@ -544,7 +549,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             __syncwarp();
             if (lane == 0) {
                 mbar_arrive(bar_conv(s));
-                if constexpr (DEC) mbar_arrive(bar_afree(s));         // the raw tile has been read: its smem slot may be refilled
+                if constexpr (DEC) mbar_arrive(bar_afree(sm));        // the raw tile has been read: its smem slot may be refilled
             }
             if (dbg_cta && ct == 0 && i < 24) p.dbg[8 + i * 6 + 2] = gtimer();
         }
@@ -789,7 +794,7 @@ static bool g_tc_single_pass = false; // opt-in plain-TF32 mode (one product ins
 // 64-wide tiles for GEMMs that could use 128 (more, smaller CTAs for the grids that underfill the machine)
 // planner constants, re-measured after the elect.sync issue fix (tools/bench_gemm.py, tools/gpu_cost.sh sweep):
 // us per k-step of a 128- / 256-wide tile, us per split-K round trip (workspace + reduce launch)
-static float g_tc_cost[3] = {0.55f, 1.1f, 4.0f};
+static float g_tc_cost[3] = {0.55f, 0.9f, 4.0f};
 static int g_tc_coop_reduce = 0;         // split-K: cooperative launch + per-tile rendezvous, reduction spread over the split CTAs
 static float g_tc_coop_cost = 2.0f;      // planner: us per split round trip in that mode
 static int g_tc_pdl_reduce = 0;

@@ -231,7 +231,7 @@ def test_full_size_batch32_is_consistent_with_batch4_chunks():
         small = run(slice(b0, b0 + 4))
         assert rel_err(big[b0:b0 + 4], small) < 1e-4
     # guidance scale 1 takes the Beff = B path (ddim.py:170-171): identical to passing no unconditional prompt at all
-    kw = dict(S=3, c=inp["c"][:4].cuda(), w=[w[:4].cuda() for w in inp["w"]], batch_size=4, verbose=False, x_T=inp["x_T"][:4].cuda(),
+    kw = dict(S=4, c=inp["c"][:4].cuda(), w=[w[:4].cuda() for w in inp["w"]], batch_size=4, verbose=False, x_T=inp["x_T"][:4].cuda(),
               eta=0.0, shape=(16, L))
     z_a, _ = sampler.sample(unconditional_guidance_scale=1.0, unconditional_conditioning=inp["uc"][:4].cuda(), **kw)
     z_b, _ = sampler.sample(**kw)
