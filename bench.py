@@ -363,15 +363,30 @@ def main():
     h2d = sum(t.numel() * 4 for t in [host["x_T"], host["c"], host["uc"]] + host["w"])
     K = min(args.steps, 1000)
 
+    trace = os.environ.get("BENCH_E2E_TRACE") == "1"      # phase wall times (adds syncs: not for the reported number)
+
     def request():
+        tt = [time.perf_counter()]
+
+        def mark():
+            if trace:
+                torch.cuda.synchronize()
+                tt.append(time.perf_counter())
         c = host["c"].to(dev, non_blocking=True)
         uc = host["uc"].to(dev, non_blocking=True)
         w = [t.to(dev, non_blocking=True) for t in host["w"]]
         xT = host["x_T"].to(dev, non_blocking=True)
+        mark()
         z, _ = sampler.sample(S=K, c=c, w=w, batch_size=B, shape=(16, L), verbose=False, x_T=xT, eta=0.0,
                               unconditional_guidance_scale=wl["scale"], unconditional_conditioning=uc, tqdm_class=_NoBar)
+        mark()
         logits = model.model.decode(z)
-        return logits.to("cpu", non_blocking=False)
+        mark()
+        out = logits.to("cpu", non_blocking=False)
+        mark()
+        if trace and rank == 0:
+            print("e2e phases ms (h2d, sample, decode, d2h):", [round(1e3 * (b - a), 2) for a, b in zip(tt, tt[1:])], file=sys.stderr)
+        return out
 
     request()                                   # warm (decoder plan, graph already captured)
     torch.cuda.synchronize()
