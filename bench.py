@@ -62,7 +62,8 @@ def ncu_traffic_per_launch():
             vals = [float(r[ir]) * scale.get(units[ir], 1.0) + float(r[iw]) * scale.get(units[iw], 1.0)
                     for r in rows[2:] if len(r) > iw and "gemm_tc_kernel" in r[ik]]
             if vals:
-                return sum(vals) / len(vals), name, len(vals)
+                vals.sort()                  # median: one replayed launch of a capture can show a spurious DRAM count
+                return vals[len(vals) // 2], name, len(vals)
         except Exception:
             continue
     return None, None, 0
@@ -349,7 +350,7 @@ def main():
         ach = gemm_flops / (gemm_ms * 1e-3) / 1e12
         roof = dict(bound="tensor", kernel=f"gemm_tc_kernel (tcgen05 3xTF32; impl={eng.gemm_impl})", achieved=ach, peak=pk["tflops"],
                     unit="TFLOP/s", frac=ach / pk["tflops"], traffic=traffic, peak_source=pk["src"], launches=gemm_n,
-                    traffic_note=f"mean dram__bytes_read+write per gemm_tc_kernel launch in profiles/{traffic_src} "
+                    traffic_note=f"median dram__bytes_read+write per gemm_tc_kernel launch in profiles/{traffic_src} "
                                  f"(ncu --set full, {traffic_n} representative launches of the L512_B4 plan, cold cache)",
                     avg_launch_us=1000.0 * gemm_ms / max(gemm_n, 1), algorithmic_gflop_per_step=gemm_flops / 1e9,
                     note="3xTF32 issues 3 tensor-core products per fp32 product and TF32 runs at half the bf16 rate: "
