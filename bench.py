@@ -373,10 +373,11 @@ def main():
             if trace:
                 torch.cuda.synchronize()
                 tt.append(time.perf_counter())
-        c = host["c"].to(dev, non_blocking=True)
-        uc = host["uc"].to(dev, non_blocking=True)
-        w = [t.to(dev, non_blocking=True) for t in host["w"]]
-        xT = host["x_T"].to(dev, non_blocking=True)
+        # plain blocking copies from pinned memory, as a caller writes them (webui.py builds its inputs with .to(device))
+        c = host["c"].to(dev)
+        uc = host["uc"].to(dev)
+        w = [t.to(dev) for t in host["w"]]
+        xT = host["x_T"].to(dev)
         mark()
         z, _ = sampler.sample(S=K, c=c, w=w, batch_size=B, shape=(16, L), verbose=False, x_T=xT, eta=0.0,
                               unconditional_guidance_scale=wl["scale"], unconditional_conditioning=uc, tqdm_class=_NoBar)
