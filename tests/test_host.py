@@ -139,3 +139,46 @@ def test_synthetic_streams_are_stable():
     assert abs(float(w.double().sum()) - (-17.870057)) < 1e-3, float(w.double().sum())
     x = synth.synthetic_inputs(1, 96)["x_T"]
     assert abs(float(x.double().sum()) - -30.42121) < 1e-3, float(x.double().sum())
+
+
+@pytest.mark.parametrize("Beff,Lz", [(2, 96), (8, 512), (64, 512), (16, 992)])
+def test_tensor_core_planner_invariants(packed, Beff, Lz):
+    """tile / split-K planning of the tcgen05 GEMM (pure host code in libmugd, no GPU needed) over every GEMM of real plans:
+    what it takes it must be able to run with the engine's fixed 32 MB workspace and 4096 tile counters."""
+    import ctypes as C
+    cfg, sd, blob = packed
+    lib = L_.load()
+    comp = UNetCompiler(cfg.unet, blob, 1 << 30)
+    res = comp.compile(Arena(1 << 32), Beff, Lz, _fake_ext(comp, Beff, Lz), False)
+    n_tc = n_split = 0
+    for o in res["ops"].ops:
+        if o.kind != L_.OP_GEMM:
+            continue
+        g = o.u.gemm
+        ok, sp, nt, ws = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int64()
+        assert lib.mugd_gemm_tc_query(None, C.byref(g), 148, C.byref(ok), C.byref(sp), C.byref(ws), C.byref(nt)) == 0
+        small = g.K % 32 != 0 or g.N < 64                       # conv_in (K = 16) and the 16-channel output conv stay on the FFMA kernel
+        assert bool(ok.value) == (not small), (g.M, g.N, g.K)
+        if not ok.value:
+            assert sp.value == 0 and ws.value == 0
+            continue
+        n_tc += 1
+        ksteps = g.taps * (g.K // 32)
+        assert 1 <= sp.value <= ksteps and 1 <= nt.value <= 4096
+        if sp.value > 1:
+            n_split += 1
+            assert nt.value * sp.value <= 2 * 148               # bounds the workspace: fewer than 2 partial tiles per SM
+            assert ksteps // sp.value >= 2                       # a split never leaves a CTA with a single k-step
+            assert 0 < ws.value <= 32 << 20
+            assert ws.value % (128 * 64 * 4) == 0                # whole 128-row partial tiles
+        else:
+            assert ws.value == 0
+        # a machine with fewer SMs never gets more CTAs than twice its size out of a split either
+        sp2, nt2 = C.c_int32(), C.c_int32()
+        lib.mugd_gemm_tc_query(None, C.byref(g), 64, None, C.byref(sp2), None, C.byref(nt2))
+        assert sp2.value == 1 or nt2.value * sp2.value <= 2 * 64
+    assert n_tc >= 220
+    if Beff <= 8:
+        assert n_split > 100                                     # small batches underfill 148 SMs: most GEMMs are split
+    if Beff == 64:
+        assert n_split < n_tc // 2
