@@ -251,6 +251,9 @@ int  mugd_debug_set_tc_cost(float kstep128_us, float kstep256_us, float split_us
  * split_cost_us > 0 sets the planner's cost of a split in this mode. */
 int  mugd_set_tc_coop_reduce(int enabled, float split_cost_us);
 
+/* measurement aid: GEMMs without bias / row vector / residual / activation store their tile with the bare split-K store loop */
+int  mugd_debug_set_tc_plain_store(int enabled);
+
 /* split-K reduce kernel as a programmatic dependent launch of its GEMM (scheduled early, waits in griddepcontrol.wait) */
 int  mugd_set_tc_pdl_reduce(int enabled);
 

@@ -51,6 +51,7 @@ struct TcParams {
     int32_t single_pass;      // 1: plain TF32 (a_hi*w_hi only, ~2^-11 relative) -- opt-in speed mode, NOT used for parity/bench
     int32_t inkernel_reduce;  // split-K: the last-arriving CTA of a tile reduces it (few splits), no second launch
     int32_t cluster;          // split-K CTAs of a tile form a thread-block cluster and reduce through DSMEM
+    int32_t dbg_plain_store;  // measurement aid: bare store loop for epilogue-free GEMMs
     int32_t pdl_reduce;       // split-K: the reduce kernel is a programmatic dependent launch (resident and waiting while the GEMM runs)
     long long* dbg;           // optional: CTA (0,0,0) writes globaltimer stamps {entry, setup done, accumulator ready, tile staged, epilogue done}
 };
@@ -721,6 +722,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (threadIdx.x == 0) p.counters[tile_lin] = 0;          // ticket back to rest for the next launch / replay
                 }
             }
+        } else if (p.dbg_plain_store && !g.bias && !rowvec && !g.residual && g.act == MUGD_ACT_NONE && g.gate == MUGD_GATE_NONE) {
+            // measurement aid (mugd_debug_set_tc_plain_store): the split-K path's bare store loop writing C rows -- 1.4 us per
+            // 128x128 tile against 3.1 us for tc_store_tile with nothing to add
+            constexpr int SP = BN + 4;
+            constexpr int C4 = BN / 4;
+            constexpr int U = 8;
+#pragma unroll 1
+            for (int i0 = 0; i0 < TC_BM * C4; i0 += TC_THREADS * U) {
+                float4 acc[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int idx = i0 + u * TC_THREADS + (int)threadIdx.x;
+                    const int row = idx / C4, c4 = idx - row * C4;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(acc[u].x), "=f"(acc[u].y), "=f"(acc[u].z), "=f"(acc[u].w)
+                                 : "r"(stage + (uint32_t)(row * SP + c4 * 4) * 4u));
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int idx = i0 + u * TC_THREADS + (int)threadIdx.x;
+                    const int row = idx / C4, c4 = idx - row * C4;
+                    const int m = m_base + row, nn = n0 + c4 * 4;
+                    if (row < rows_valid && m < g.M && nn < g.N) st_f4(g.C + (int64_t)m * g.ldc + nn, acc[u]);
+                }
+            }
         } else {
 #define TC_CALL_STORE(A_, G_) tc_store_tile<BN, A_, G_>(g, stage, m_base, n0, rows_valid, rowvec)
             TC_DISPATCH_EPI(g, TC_CALL_STORE);
@@ -797,6 +822,7 @@ static bool g_tc_single_pass = false; // opt-in plain-TF32 mode (one product ins
 static float g_tc_cost[3] = {0.55f, 0.9f, 4.0f};
 static int g_tc_coop_reduce = 0;         // split-K: cooperative launch + per-tile rendezvous, reduction spread over the split CTAs
 static float g_tc_coop_cost = 2.0f;      // planner: us per split round trip in that mode
+static int g_tc_plain_store = 0;
 static int g_tc_pdl_reduce = 0;
 static int g_tc_narrow_tiles = 0;
 static float g_tc_kstep64 = 0.4f;
@@ -1043,6 +1069,7 @@ int launch_gemm_tc(const DeviceInfo& dev, const mugd_gemm& g, cudaStream_t st, i
     p.box_b = t.box_b;
     p.tiles_per_sample = t.tiles_per_sample;
     p.dbg = g_tc_dbg;
+    p.dbg_plain_store = g_tc_plain_store;
     p.pdl_reduce = (g_tc_pdl_reduce && t.splits > 1 && t.mc == 1 && !(g_tc_cluster && t.splits > 1)) ? 1 : 0;
     p.single_pass = g_tc_single_pass ? 1 : 0;
     p.cluster = use_cluster ? 1 : 0;
@@ -1100,6 +1127,11 @@ extern "C" int mugd_debug_set_tc_cost(float kstep128_us, float kstep256_us, floa
 extern "C" int mugd_set_tc_coop_reduce(int enabled, float split_cost_us) {
     mugd::g_tc_coop_reduce = enabled ? 1 : 0;
     if (split_cost_us > 0.f) mugd::g_tc_coop_cost = split_cost_us;
+    return MUGD_OK;
+}
+
+extern "C" int mugd_debug_set_tc_plain_store(int enabled) {
+    mugd::g_tc_plain_store = enabled ? 1 : 0;
     return MUGD_OK;
 }
 

@@ -203,5 +203,5 @@ def check(rc: int, what: str = ""):
 EXPORTED_SYMBOLS = [
     "mugd_abi_version", "mugd_last_error", "mugd_create", "mugd_destroy", "mugd_device_info", "mugd_set_gemm_impl",
     "mugd_op_run", "mugd_plan_create", "mugd_plan_run", "mugd_plan_capture", "mugd_plan_replay",
-    "mugd_plan_launch_count", "mugd_plan_destroy", "mugd_s4_kernel_gen", "mugd_fill_i32", "mugd_abi_sizes", "mugd_gemm_tc_query", "mugd_set_pdl", "mugd_set_tc_cluster_reduce", "mugd_debug_set_tc_tile_n", "mugd_set_tc_a_in_tmem", "mugd_set_tc_inkernel_reduce_max", "mugd_set_tc_single_pass_tf32", "mugd_set_tc_multicast", "mugd_debug_set_attention_dump", "mugd_set_tc_coop_reduce", "mugd_debug_set_tc_cost", "mugd_set_tc_pdl_reduce", "mugd_set_tc_narrow_tiles", "mugd_set_attention_impl", "mugd_debug_set_tc_timing",
+    "mugd_plan_launch_count", "mugd_plan_destroy", "mugd_s4_kernel_gen", "mugd_fill_i32", "mugd_abi_sizes", "mugd_gemm_tc_query", "mugd_set_pdl", "mugd_set_tc_cluster_reduce", "mugd_debug_set_tc_tile_n", "mugd_set_tc_a_in_tmem", "mugd_set_tc_inkernel_reduce_max", "mugd_set_tc_single_pass_tf32", "mugd_set_tc_multicast", "mugd_debug_set_tc_plain_store", "mugd_debug_set_attention_dump", "mugd_set_tc_coop_reduce", "mugd_debug_set_tc_cost", "mugd_set_tc_pdl_reduce", "mugd_set_tc_narrow_tiles", "mugd_set_attention_impl", "mugd_debug_set_tc_timing",
 ]
