@@ -3,6 +3,7 @@ from __future__ import annotations
 
 import ctypes as C
 import threading
+from collections import OrderedDict
 from typing import Dict, List, Optional, Sequence
 
 import numpy as np
@@ -63,7 +64,8 @@ class MugEngine:
     re-entrant either: webui.py:355-356 mutates model.z_length per request)."""
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], cfg: Optional[ModelConfig] = None,
-                 device: Optional[torch.device] = None, gemm_impl: str = "auto", blob: Optional[WeightBlob] = None):
+                 device: Optional[torch.device] = None, gemm_impl: str = "auto", blob: Optional[WeightBlob] = None,
+                 max_sessions: int = 4):
         if not torch.cuda.is_available():
             raise L_.MugdError("mug_diffusion_b200 needs an sm_100 (B200) GPU; there is no CPU fallback")
         self.cfg = cfg or ModelConfig()
@@ -80,8 +82,14 @@ class MugEngine:
         # (bound: tiles*splits < 2*SMs tiles of 128x128 fp32)
         self.tc_ws = torch.zeros(8 * 1024 * 1024, device=self.device)          # 32 MB
         self.tc_counters = torch.zeros(4096, dtype=torch.int32, device=self.device)
-        self.sessions: Dict[tuple, "Session"] = {}
-        self.dec_sessions: Dict[tuple, "DecoderSession"] = {}
+        # Compiled shapes are cached in small LRUs: webui derives z_length from each audio's duration (any multiple of
+        # 32, webui.py:349-356), so an unbounded cache would grow by one ~1.5 GB arena + CUDA graph per new shape.
+        self.sessions: "OrderedDict[tuple, Session]" = OrderedDict()
+        self.dec_sessions: "OrderedDict[tuple, object]" = OrderedDict()
+        self.max_sessions = max_sessions
+        # internal S4 kernel length per layer (SSKernelNPLR's `L` buffer, s4.py:557-584).  It is ENGINE state: lengthening
+        # rewrites this engine's device copy of C~, so the length that goes with it must not live in the shared host blob.
+        self.s4_L: Dict[str, int] = {k: int(v) for k, v in self.blob.meta.items() if k.endswith("kernel.kernel.L")}
         self.set_gemm_impl(gemm_impl)
 
     def set_gemm_impl(self, impl: str):
@@ -107,33 +115,32 @@ class MugEngine:
         for op in ops.ops:
             L_.check(self.lib.mugd_op_run(self.handle, C.byref(op), st), f"op kind {op.kind}")
 
-    def session(self, Beff: int, Lz: int, per_sample_t: bool = False) -> "Session":
-        key = (Beff, Lz, per_sample_t)
-        s = self.sessions.get(key)
+    def _lru_get(self, cache: OrderedDict, key, make):
+        s = cache.get(key)
         if s is None:
-            s = Session(self, Beff, Lz, per_sample_t)
-            self.sessions[key] = s
+            while len(cache) >= max(1, self.max_sessions):
+                _, old = cache.popitem(last=False)          # least recently used: frees its arena, plan and graph
+                if hasattr(old, "release"):
+                    old.release()
+                del old
+            s = make()
+            cache[key] = s
+        else:
+            cache.move_to_end(key)
         return s
+
+    def session(self, Beff: int, Lz: int, per_sample_t: bool = False) -> "Session":
+        return self._lru_get(self.sessions, (Beff, Lz, per_sample_t), lambda: Session(self, Beff, Lz, per_sample_t))
 
     def wave_session(self, B: int, T: int):
         """Audio encoder plan for B mel-spectrograms of T frames; needs wave weights in the blob."""
         if "wave_cfg" not in self.blob.meta:
             raise L_.MugdError("this engine was packed without model.wave_model.* weights")
         from .wave import WaveSession
-        key = ("wave", B, T)
-        s = self.dec_sessions.get(key)
-        if s is None:
-            s = WaveSession(self, B, T)
-            self.dec_sessions[key] = s
-        return s
+        return self._lru_get(self.dec_sessions, ("wave", B, T), lambda: WaveSession(self, B, T))
 
     def decoder_session(self, B: int, Lz: int) -> "DecoderSession":
-        key = (B, Lz)
-        s = self.dec_sessions.get(key)
-        if s is None:
-            s = DecoderSession(self, B, Lz)
-            self.dec_sessions[key] = s
-        return s
+        return self._lru_get(self.dec_sessions, (B, Lz), lambda: DecoderSession(self, B, Lz))
 
     def __del__(self):
         try:
@@ -181,7 +188,7 @@ class Session:
         ws = None
         for b in s4b:
             k = b.prefix + "s4_model.kernel.kernel."
-            L_int = int(eng.blob.meta[k + "L"])
+            L_int = int(eng.s4_L[k + "L"])
             L_req = self.Lz // b.ds
             if L_req > L_int:
                 # same one-time, persistent mutation the reference performs in SSKernelNPLR._setup_C (s4.py:557-584):
@@ -197,7 +204,7 @@ class Session:
                 C_new, L_int = s4_setup.lengthen(params, L_int, L_req)
                 e = eng.blob.entries[k + "C"]
                 eng.weights[e.offset:e.offset + C_new.numel()].copy_(C_new.reshape(-1).to(eng.device))
-                eng.blob.meta[k + "L"] = L_int
+                eng.s4_L[k + "L"] = L_int
             need = 16 * b.cin * (L_int // 2 + 1)
             if ws is None or ws.numel() * 8 < need:
                 ws = torch.empty(need // 8 + 2, dtype=torch.float64, device=eng.device)
