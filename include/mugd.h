@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MUGD_ABI_VERSION 7
+#define MUGD_ABI_VERSION 8
 
 typedef struct mugd_handle mugd_handle;   /* one device + scratch state            */
 typedef struct mugd_plan mugd_plan;       /* validated launch plan (+ CUDA graph)  */
@@ -92,7 +92,13 @@ typedef struct mugd_gemm {
     int32_t tap_shift;                     /* MUGD_CONV_TAPS: source row of tap t is l + (t + tap_shift) * dilation */
     int32_t tap_dilation;                  /* MUGD_CONV_TAPS: 0/1 = dense taps; d = dilated conv (wave.py:425-433)  */
     void* workspace; int64_t workspace_bytes; /* split-K partial tiles (see mugd_gemm_tc_query)            */
-    int32_t* counters;                     /* zero-initialised tile tickets, left zero by every launch     */
+    int32_t* counters;                     /* unused since ABI 8 (kept for layout stability)               */
+    /* optional SECOND activation source: K2 more channels read at the output row itself (a 1x1 term), weights in columns
+     * taps*K .. taps*K+K2 of every W row.  One GEMM then computes  conv3(A) + conv1(A2):  out_layers conv + skip_connection
+     * of a TimestepResBlock (unet.py:187-193,237-239), and  proj_out(ff.net.2(ff) + h) = (Wp Wf) ff + Wp h  of the transformer
+     * block (attention.py:57-65,194-199) with the packer-composed weight.  NULL / 0 = single source. */
+    const float* A2; int64_t lda2;         /* [B*Lout, K2]                                                 */
+    int32_t K2; int32_t reserved_;
 } mugd_gemm;
 
 typedef struct mugd_groupnorm {
@@ -185,7 +191,7 @@ int  mugd_create(int device, mugd_handle** out);           /* MUGD_ERR_NO_DEVICE
 void mugd_destroy(mugd_handle* h);
 int  mugd_device_info(mugd_handle* h, int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
 int  mugd_set_gemm_impl(mugd_handle* h, int impl);         /* default for ops with impl == AUTO         */
-int  mugd_set_pdl(int enabled);                            /* programmatic dependent launch (default off) */
+int  mugd_set_pdl(int enabled);                            /* programmatic launch edges (default on; process-wide A/B switch) */
 
 /* ---- single op (parity tests call every kernel through this) ---------------------------------- */
 int  mugd_op_run(mugd_handle* h, const mugd_op* op, void* stream);
@@ -218,59 +224,31 @@ int  mugd_s4_kernel_gen(mugd_handle* h,
 int  mugd_gemm_tc_query(mugd_handle* h, const mugd_gemm* g, int32_t sm_count, int32_t* supported, int32_t* splits,
                         int64_t* workspace_bytes, int32_t* n_tiles);
 
-/* split-K reduction of the tensor-core GEMM: 0 (default) = partial tiles through the workspace + a reduce kernel;
- * 1 = the splits of a tile run as one thread-block cluster and reduce through distributed shared memory (slower on B200) */
-int  mugd_set_tc_cluster_reduce(int enabled);
-
-/* tensor-core GEMM variant: 1 (default) = split activations go to tensor memory and the MMAs read A from TMEM (TS form);
- * 0 = both operands from shared memory (SS form) */
-int  mugd_set_tc_a_in_tmem(int enabled);
-
-/* split-K with at most `max_splits` parts is reduced inside the GEMM kernel by the last-arriving CTA of each tile (needs the
- * `counters` of mugd_gemm); larger splits use the parallel reduce kernel.  0 (default) disables: measured slower on B200. */
-int  mugd_set_tc_inkernel_reduce_max(int max_splits);
-
-/* OPT-IN speed mode: 1 = plain TF32 products (a_hi*w_hi only, ~2^-11 relative error per product, like cuDNN's allow_tf32 that
- * the reference's own GPU path uses for convs); 0 (default) = 3xTF32, fp32-accurate.  Parity tests and bench.py use 0. */
-int  mugd_set_tc_single_pass_tf32(int enabled);
+/* ---- per-handle switches -------------------------------------------------------------------------
+ * OPT-IN speed mode of the tensor-core GEMM: 1 = plain TF32 products (a_hi*w_hi only, ~2^-11 relative error per product, like
+ * cuDNN's allow_tf32 that the reference's own GPU path uses for convs); 0 (default) = 3xTF32, fp32-accurate.  Parity tests and
+ * bench.py use 0.  Plans created (and graphs captured) earlier keep the mode they were created with. */
+int  mugd_set_tc_single_pass_tf32(mugd_handle* h, int enabled);
 
 /* attention kernel: 1 (default) = QK^T and PV on the tcgen05 tensor cores (3xTF32, fp32 accuracy); 0 = exact-fp32 FFMA kernel
  * (the referee of the parity tests).  Replaces the einsum/softmax body of CrossAttention.forward, attention.py:99-121 */
-int  mugd_set_attention_impl(int impl);
+int  mugd_set_attention_impl(mugd_handle* h, int impl);
 
-/* tile-width planning of the tensor-core GEMM: 1 = also consider 64-column tiles for N >= 128 (more, smaller CTAs when the
- * grid underfills the 148 SMs); kstep_us > 0 overrides the planner's cost per 32-deep k-step of such a tile */
-int  mugd_set_tc_narrow_tiles(int enabled, float kstep_us);
-
-/* planner cost constants of the tensor-core GEMM (us per 32-deep k-step of a 128- and a 256-column tile, us per split-K
- * round trip); values <= 0 keep the current one.  For tuning sweeps (tools/), not needed in production. */
+/* ---- measurement aids (process-wide, not needed in production) -------------------------------------
+ * planner cost constants of the tensor-core GEMM (us per 32-deep k-step of a 128- and a 256-column tile, us per split-K
+ * round trip); values <= 0 keep the current one.  For tuning sweeps (tools/). */
 int  mugd_debug_set_tc_cost(float kstep128_us, float kstep256_us, float split_us);
 
-/* split-K reduction inside the GEMM kernel: cooperative launch (grid <= one CTA per SM, co-residency guaranteed by the driver),
- * the splits of a tile rendezvous on a device counter and each reduces + finishes its band of rows; no second launch.
- * split_cost_us > 0 sets the planner's cost of a split in this mode. */
-int  mugd_set_tc_coop_reduce(int enabled, float split_cost_us);
+/* force the tensor-core tile width (64, 128 or 256) where legal; 0 = cost model */
+int  mugd_debug_set_tc_tile_n(int bn);
 
-/* measurement aid: GEMMs without bias / row vector / residual / activation store their tile with the bare split-K store loop */
-int  mugd_debug_set_tc_plain_store(int enabled);
-
-/* split-K reduce kernel as a programmatic dependent launch of its GEMM (scheduled early, waits in griddepcontrol.wait) */
-int  mugd_set_tc_pdl_reduce(int enabled);
-
-/* debugging aid: CTA (0,0,0) of the tensor-core attention kernel dumps 40 floats per query row of its first key tile
+/* CTA (0,0,0) of the tensor-core attention kernel dumps 40 floats per query row of its first key tile
  * (raw logits, O tile, running max / sum, first operand words) into buf[128*40]; NULL switches it off */
 int  mugd_debug_set_attention_dump(float* buf);
 
-/* weight-tile TMA multicast: clusters of up to `max_cluster` (0, 2 or 4) vertically adjacent output tiles load each weight tile
- * once from L2 and multicast it (used only when the grid oversubscribes the SMs).  Default 0 (off): measured no faster on B200. */
-int  mugd_set_tc_multicast(int max_cluster);
-
-/* experiments: force the tensor-core tile width (128 or 256) where legal; 0 = cost model */
-int  mugd_debug_set_tc_tile_n(int bn);
-
-/* debugging aid: when set (device pointer to 8 x int64), CTA (0,0,0) of every tensor-core GEMM launch writes
- * %globaltimer stamps {kernel entry, setup done, accumulator ready, tile staged in smem, epilogue done}; pass NULL to disable */
-int  mugd_debug_set_tc_timing(long long* device_buf4);
+/* builds with -DMUGD_TC_TIMELINE only (tools/build_variant.py): CTA (0,0,0) of every tensor-core GEMM launch writes
+ * %globaltimer stamps into the device buffer (tools/gemm_timeline.py); otherwise returns MUGD_ERR_INVALID */
+int  mugd_debug_set_tc_timing(long long* device_buf);
 
 /* ---- utility ---------------------------------------------------------------------------------- */
 int  mugd_fill_i32(int32_t* dst, int32_t value, void* stream);

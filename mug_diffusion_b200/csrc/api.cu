@@ -9,7 +9,9 @@
 namespace mugd {
 
 static thread_local char g_err[1024] = "";
-bool g_use_pdl = true;    // programmatic launch edges with the implicit (grid-completion) trigger: 3.97 vs 4.02 ms/step; explicit triggers are slower (common.cuh)
+// Programmatic launch edges with the implicit (grid-completion) trigger: graph edge 0.57 vs 0.69 us, 3.97 vs 4.02 ms/step.  This is a
+// launch attribute without numerical effect; it is process-wide because launch_k() has no handle (mugd_set_pdl is an A/B switch).
+bool g_use_pdl = true;
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -105,6 +107,18 @@ int mugd_set_gemm_impl(mugd_handle* h, int impl) {
     MUGD_REQUIRE(h, "null handle");
     MUGD_REQUIRE(impl == MUGD_GEMM_SIMT || impl == MUGD_GEMM_TC, "set_gemm_impl: %d", impl);
     h->default_gemm_impl = impl;
+    return MUGD_OK;
+}
+
+int mugd_set_tc_single_pass_tf32(mugd_handle* h, int enabled) {
+    MUGD_REQUIRE(h, "null handle");
+    h->dev.tc_single_pass = enabled ? 1 : 0;
+    return MUGD_OK;
+}
+
+int mugd_set_attention_impl(mugd_handle* h, int impl) {
+    MUGD_REQUIRE(h, "null handle");
+    h->dev.attention_impl = impl ? 1 : 0;
     return MUGD_OK;
 }
 

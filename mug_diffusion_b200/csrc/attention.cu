@@ -182,8 +182,6 @@ static int attention_launch(const mugd_attention& a, cudaStream_t st) {
 
 int launch_attention_tc(const DeviceInfo& dev, const mugd_attention& a, cudaStream_t st);   // attention_tc.cu
 // 1 (default): both contractions on the tcgen05 tensor cores (attention_tc.cu); 0: the FFMA kernel above
-static int g_attention_impl = 1;
-
 int launch_attention(const DeviceInfo& dev, const mugd_attention& a, cudaStream_t st, int* launches) {
     MUGD_REQUIRE(a.B > 0 && a.H > 0 && a.Lq > 0 && a.Lk > 0, "attention: empty shape");
     MUGD_REQUIRE(a.D == 32 || a.D == 48 || a.D == 64, "attention: head dim %d not in {32,48,64}", a.D);
@@ -193,7 +191,7 @@ int launch_attention(const DeviceInfo& dev, const mugd_attention& a, cudaStream_
     MUGD_REQUIRE(a.ldq >= a.H * a.D && a.ldk >= a.H * a.D && a.ldv >= a.H * a.D && a.ldo >= a.H * a.D, "attention: ld < H*D");
     MUGD_REQUIRE(a.relpos && a.cgain, "attention: tables missing");
     int rc;
-    if (g_attention_impl == 1) rc = launch_attention_tc(dev, a, st);
+    if (dev.attention_impl == 1) rc = launch_attention_tc(dev, a, st);
     else rc = (a.D == 32) ? attention_launch<32>(a, st) : (a.D == 48) ? attention_launch<48>(a, st) : attention_launch<64>(a, st);
     if (rc != MUGD_OK) return rc;
     if (launches) *launches += 1;
@@ -202,7 +200,3 @@ int launch_attention(const DeviceInfo& dev, const mugd_attention& a, cudaStream_
 
 }  // namespace mugd
 
-extern "C" int mugd_set_attention_impl(int impl) {
-    mugd::g_attention_impl = impl ? 1 : 0;
-    return MUGD_OK;
-}

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 #include <string>
 #include <utility>
 
@@ -39,6 +40,9 @@ struct DeviceInfo {
     int sm_count = 148;
     int cc_major = 0, cc_minor = 0;
     int max_smem_optin = 0;
+    // per-handle switches (round 1 kept these as process globals)
+    int tc_single_pass = 0;     // opt-in plain-TF32 tensor-core products (NOT fp32-accurate; never used by parity tests / bench)
+    int attention_impl = 1;     // 1 = tcgen05 attention, 0 = exact-fp32 FFMA referee
 };
 
 // per-family launchers (each validates its descriptor and enqueues kernels on `st`);
@@ -79,27 +83,10 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
     cfg.numAttrs = g_use_pdl ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
-// Trigger placement experiments (all measured on B200, none kept on: DESIGN.md 4 "tried and measured slower"):
-//   MUGD_PDL_EARLY_TRIGGER  every kernel signals at entry (dependents become resident while this grid still runs): 5.12 vs 4.46 ms/step
-//   MUGD_PDL_SHORT_ENTRY    only the short kernels (norms, attention, S4, elementwise, reduce) signal at entry
-//   MUGD_PDL_LATE_TRIGGER   the GEMM signals once its accumulator tile is staged, so the next launch overlaps the store phase
-// Without a trigger the signal is implicit at grid completion and PDL only overlaps the dependent's launch with this
-// grid's memory flush.
-__device__ __forceinline__ void pdl_trigger() {
-#if defined(MUGD_PDL_EARLY_TRIGGER) || defined(MUGD_PDL_SHORT_ENTRY)
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-#endif
-}
-__device__ __forceinline__ void pdl_trigger_gemm_entry() {
-#if defined(MUGD_PDL_EARLY_TRIGGER)
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-#endif
-}
-__device__ __forceinline__ void pdl_trigger_late() {
-#if defined(MUGD_PDL_LATE_TRIGGER)
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-#endif
-}
+// No kernel signals launch_dependents explicitly: the trigger is implicit at grid completion, so PDL only overlaps the dependent's
+// launch with this grid's memory flush (graph edge 0.57 us instead of 0.69 us, tools/experiments/sync_probe.cu).  Explicit triggers
+// (at entry, in the short kernels only, after the GEMM main loop) were measured slower in round 1 and removed.
+__device__ __forceinline__ void pdl_trigger() {}
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ---- device helpers ---------------------------------------------------------------------------

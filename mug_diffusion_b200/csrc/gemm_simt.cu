@@ -19,7 +19,7 @@ constexpr int SG_BK = 16;
 
 struct GemmParams {
     mugd_gemm g;
-    int nk;  // total k-steps = taps*K/16
+    int nk;  // total k-steps = (taps*K + K2)/16
 };
 
 __device__ __forceinline__ int conv_src_row(int mode, int l, int t, int Lin, int Lout, int tap_shift, int dil) {
@@ -75,19 +75,25 @@ gemm_simt_kernel(const GemmParams p) {
         w_row[r] = (tid >> 2) + r * 64;
         w_ok[r] = (n0 + w_row[r]) < g.N;
     }
-    const int64_t wld = (int64_t)g.taps * g.K;
+    const int64_t wld = (int64_t)g.taps * g.K + g.K2;
+    const int k_main = g.taps * g.K;
 
     float4 ra[RM], rw[RN];
     auto load_tile = [&](int kt) {
         const int kk = kt * SG_BK;
-        const int t = kk / g.K;
-        const int k0 = kk - t * g.K;
+        const bool second = kk >= k_main;         // k-steps of the second source (1x1 term at the output row)
+        const int t = second ? 0 : kk / g.K;
+        const int k0 = second ? kk - k_main : kk - t * g.K;
 #pragma unroll
         for (int r = 0; r < RM; ++r) {
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (a_b[r] >= 0) {
-                const int src = conv_src_row(g.conv_mode, a_l[r], t, g.Lin, g.Lout, g.tap_shift, g.tap_dilation > 1 ? g.tap_dilation : 1);
-                if (src >= 0) v = ld_f4(g.A + ((int64_t)a_b[r] * g.Lin + src) * g.lda + k0 + a_kq * 4);
+                if (second) {
+                    v = ld_f4(g.A2 + ((int64_t)a_b[r] * g.Lout + a_l[r]) * g.lda2 + k0 + a_kq * 4);
+                } else {
+                    const int src = conv_src_row(g.conv_mode, a_l[r], t, g.Lin, g.Lout, g.tap_shift, g.tap_dilation > 1 ? g.tap_dilation : 1);
+                    if (src >= 0) v = ld_f4(g.A + ((int64_t)a_b[r] * g.Lin + src) * g.lda + k0 + a_kq * 4);
+                }
             }
             ra[r] = v;
         }
@@ -222,6 +228,10 @@ static int validate_gemm(const mugd_gemm& g) {
     if (g.conv_mode == MUGD_CONV_DOWN) MUGD_REQUIRE(g.Lin == 2 * g.Lout, "gemm: Downsample needs Lin == 2*Lout");
     if (g.conv_mode == MUGD_CONV_UP) MUGD_REQUIRE(g.Lout == 2 * g.Lin, "gemm: Upsample needs Lout == 2*Lin");
     MUGD_REQUIRE(g.A && g.W && g.C, "gemm: null operand");
+    MUGD_REQUIRE(g.K2 >= 0 && (g.K2 == 0) == (g.A2 == nullptr), "gemm: A2 / K2 inconsistent");
+    if (g.K2 > 0)
+        MUGD_REQUIRE(g.K2 % 16 == 0 && aligned16(g.A2) && g.lda2 % 4 == 0 && g.lda2 >= g.K2 && g.conv_mode != MUGD_CONV_DOWN &&
+                         g.conv_mode != MUGD_CONV_UP, "gemm: second source needs K2 %% 16 == 0, aligned A2 and an unstrided conv mode");
     MUGD_REQUIRE(aligned16(g.A) && aligned16(g.W) && g.lda % 4 == 0 && g.lda >= g.K, "gemm: A/W alignment or lda");
     MUGD_REQUIRE(!g.bias || aligned16(g.bias), "gemm: bias alignment");
     MUGD_REQUIRE(!g.rowvec || (aligned16(g.rowvec) && g.rowvec_b_stride % 4 == 0 && g.rowvec_step_stride % 4 == 0), "gemm: rowvec alignment");
@@ -243,7 +253,7 @@ int launch_gemm(const DeviceInfo& dev, const mugd_gemm& g, int default_impl, cud
     }
     GemmParams p;
     p.g = g;
-    p.nk = g.taps * g.K / SG_BK;
+    p.nk = (g.taps * g.K + g.K2) / SG_BK;
     // big tiles only when they still fill the machine
     const long tiles128 = (long)((g.M + 127) / 128) * ((g.N + 127) / 128);
     if (tiles128 >= 2L * dev.sm_count) {

@@ -1,0 +1,585 @@
+// Device side of the tcgen05 (5th-generation tensor core) implicit GEMM, shared by the stand-alone kernels of gemm_tc.cu and any
+// kernel that embeds GEMM tiles.  fp32 in / fp32 out with the 3xTF32 split so results stay at fp32 accuracy
+// (DESIGN.md §4 "Precision"):
+//
+//     a = a_hi + a_lo (both exactly representable in TF32, round-to-nearest),   w = w_hi + w_lo
+//     acc += a_lo*w_hi + a_hi*w_lo + a_hi*w_hi          (fp32 accumulation in TMEM, dropped term ~2^-22)
+//
+// One call of gemm_tc_tile<BN>() computes one 128 x BN output tile (or its split-K partial) with the 8 warps of a CTA:
+//   warp 0      TMA producer : per k-step (32 fp32 = one 128-byte swizzle row) loads the raw A tile through a 3-D tensor map
+//                              (k, l, b) -- the conv k=3 halo is the TMA out-of-bounds zero fill on the l axis, so no im2col /
+//                              padding copy exists -- plus the pre-split W_hi / W_lo tiles; completion on an mbarrier.
+//   warp 3      second producer (256-wide tiles only: the weight ring is decoupled from the activation ring)
+//   warps 4-7   converter    : thread = tile row = TMEM lane; splits the raw row into a_hi / a_lo (cvt.rna.tf32) and writes them
+//                              straight into tensor memory (tcgen05.st); the MMAs take A from TMEM (".kind::tf32" TS form).
+//   warp 1      MMA issuer   : one elected lane issues 12 tcgen05.mma.kind::tf32 (M128 x BN x K8) per k-step; tcgen05.commit
+//                              releases the stage and, after the last k-step, hands the accumulator to the epilogue.
+//   warps 4-7   epilogue 1   : tcgen05.ld 32x32b -> shared memory (row pitch BN+4)
+//   all warps   epilogue 2   : bias / time-embedding row / SiLU / GELU / GEGLU / GLU / residual, row-contiguous coalesced stores;
+//                              with split-K the partial tile goes to an L2-resident workspace and tc_reduce_item() sums the
+//                              splits in fixed order (deterministic) and runs the same fused epilogue.
+//
+// Variants that were built and measured slower on B200 in round 1 (operands both from shared memory, weight-tile TMA multicast over
+// clusters, split-K reduction through DSMEM / by the last-arriving CTA / by a cooperative rendezvous, explicit PDL triggers) were
+// removed in round 2; their numbers stay in DESIGN.md §4.
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace mugd {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 32;                 // fp32 elements per k-step = 128 bytes = one swizzle row
+constexpr int TC_THREADS = 256;
+constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
+
+struct TcParams {
+    mugd_gemm g;
+    float* ws;                // split-K partial tiles [tile][split][128][BN]
+    int32_t splits;
+    int32_t total_it;         // (taps * K + K2) / 32
+    int32_t kblocks;          // K / 32
+    int32_t it_main;          // taps * K / 32: k-steps >= it_main read the second source (A2, 1x1 term)
+    int32_t Lrows, Bs;        // row structure of the A tensor map (Lrows = rows per sample, Bs samples)
+    int32_t box_l, box_b;     // TMA box: box_l rows of box_b consecutive samples (box_l*box_b <= 128)
+    int32_t tiles_per_sample; // when Lrows >= 128
+    int32_t single_pass;      // 1: plain TF32 (a_hi*w_hi only, ~2^-11 relative) -- opt-in speed mode, NOT used for parity/bench
+    int32_t BN, gx, gy;       // tile width and tile grid (gx column tiles x gy row tiles x splits)
+#ifdef MUGD_TC_TIMELINE
+    long long* dbg;           // CTA (0,0,0) writes globaltimer stamps (tools/gemm_timeline.py)
+#endif
+};
+
+#ifdef __CUDACC__
+// ---- raw PTX helpers ---------------------------------------------------------------------------------
+__device__ __forceinline__ long long gtimer() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t) :: "memory");
+    return t;
+}
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_inval(uint32_t bar) {
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// bounded wait: a protocol bug traps (CUDA error) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    const long long t0 = clock64();
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) break;
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+// A operand from tensor memory (lane = row, one 32-bit column per K element), B from shared memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+          "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+          "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+          "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
+          "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
+          "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
+          "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
+          "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+        : "memory");
+}
+// One lane of a converged warp.  tcgen05.mma / tcgen05.commit / cp.async.bulk.tensor are uniform-datapath instructions: issued
+// from a lane-divergent branch (`if (lane == 0)`) ptxas wraps every one of them in an elect-and-branch loop (~95 cycles per
+// MMA measured, which starved the tensor pipe); guarded by elect.sync in a converged warp they issue back to back.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, px;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// start>>4 [0,14) | LBO>>4 [16,30) (unused for swizzled K-major, 1) | SBO>>4 [32,46) = 1024 B between 8-row
+// groups | version=1 [46,48) | layout_type=SWIZZLE_128B(2) [61,64)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+template <int BN>
+struct TcSmem {
+    static constexpr uint32_t B_BYTES = BN * TC_BK * 4;
+    static constexpr uint32_t STAGE_BYTES = TC_A_BYTES + 2 * B_BYTES;     // raw A tile + W_hi + W_lo (a_hi / a_lo live in TMEM)
+    static constexpr int STAGES = (BN == 256) ? 2 : (BN == 128 ? 4 : 6);
+    // Decoupled rings (256-wide tiles): only two 80 KB coupled stages would fit, and tied to the A tile the weight tile sat idle
+    // while the activations were fetched and split.  Decoupled, the A side is a 2-deep smem ring feeding a 4-deep ring of TMEM
+    // operand slots and runs ahead, and the freed shared memory holds a THIRD weight stage; a weight stage is occupied only from
+    // its TMA to the retirement of its MMAs (k-step 1.10 -> 1.00 us on the Beff=64 convs).
+    static constexpr bool DEC = BN == 256;
+    static constexpr int SAS = DEC ? 2 : STAGES;           // raw activation tiles in shared memory
+    static constexpr int SA = DEC ? 4 : STAGES;            // split activation tiles in tensor memory
+    static constexpr int SW = DEC ? 3 : STAGES;            // weight stages (hi + lo)
+    static constexpr uint32_t TILE_BYTES = DEC ? SAS * TC_A_BYTES + SW * 2 * B_BYTES : STAGES * STAGE_BYTES;
+    static constexpr uint32_t BAR_BYTES = 256;
+    static constexpr uint32_t TOTAL = TILE_BYTES + 1024 /*align slack*/ + BAR_BYTES;
+    static constexpr int TMEM_NEED = BN + SA * 64;         // accumulator + per slot 32 columns a_hi + 32 columns a_lo
+    static constexpr int TMEM_COLS = TMEM_NEED <= 64 ? 64 : (TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512));
+    static_assert(TMEM_NEED <= 512, "tensor memory budget");
+    static_assert(128u * (BN + 4) * 4u <= TILE_BYTES, "the staged accumulator tile must fit the pipeline buffers");
+};
+
+// Fused epilogue math on 4 consecutive accumulator columns.  ACT / GATE are compile-time so that the compiler
+// cannot if-convert the branches into "compute SiLU, GELU and both gates for every element, then select"
+// (which it did, costing ~4 us per tile); callers dispatch once per tile on the (uniform) act/gate values.
+template <int ACT, int GATE>
+__device__ __forceinline__ void tc_finish4(const mugd_gemm& g, float4 acc, float4 bia, float4 rvv, float4 res, int m, int nn) {
+    float x[4] = {acc.x + bia.x + rvv.x, acc.y + bia.y + rvv.y, acc.z + bia.z + rvv.z, acc.w + bia.w + rvv.w};
+    if constexpr (ACT == MUGD_ACT_SILU) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) x[j] = silu_f(x[j]);
+    } else if constexpr (ACT == MUGD_ACT_GELU) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) x[j] = gelu_f(x[j]);
+    }
+    if constexpr (GATE == MUGD_GATE_NONE) {
+        st_f4(g.C + (int64_t)m * g.ldc + nn, make_float4(x[0] + res.x, x[1] + res.y, x[2] + res.z, x[3] + res.w));
+    } else {
+        float o0, o1;
+        if constexpr (GATE == MUGD_GATE_GEGLU) { o0 = x[0] * gelu_f(x[1]); o1 = x[2] * gelu_f(x[3]); }
+        else { o0 = x[0] * sigmoid_f(x[1]); o1 = x[2] * sigmoid_f(x[3]); }
+        const int no = nn >> 1;
+        if (g.residual) {
+            const float2 rr = *reinterpret_cast<const float2*>(g.residual + (int64_t)m * g.ldr + no);
+            o0 += rr.x; o1 += rr.y;
+        }
+        *reinterpret_cast<float2*>(g.C + (int64_t)m * g.ldc + no) = make_float2(o0, o1);
+    }
+}
+
+// phase 2 of the epilogue for one CTA: read the staged accumulator tile from shared memory (row pitch BN+4) and
+// finish it with coalesced global traffic; U float4 per thread in flight, every global load issued before any use.
+template <int BN, int ACT, int GATE>
+__device__ __forceinline__ void tc_store_tile(const mugd_gemm& g, uint32_t stage, int m_base, int n0, int rows_valid, const float* rowvec) {
+    constexpr int SP = BN + 4;
+    constexpr int C4 = BN / 4;
+    constexpr int U = 8;
+#pragma unroll 1
+    for (int i0 = 0; i0 < TC_BM * C4; i0 += TC_THREADS * U) {
+        float4 acc[U], bia[U], rvv[U], res[U];
+        bool ok[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int idx = i0 + u * TC_THREADS + (int)threadIdx.x;
+            const int row = idx / C4, c4 = idx - row * C4;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(acc[u].x), "=f"(acc[u].y), "=f"(acc[u].z), "=f"(acc[u].w)
+                         : "r"(stage + (uint32_t)(row * SP + c4 * 4) * 4u));
+            const int m = m_base + row, nn = n0 + c4 * 4;
+            ok[u] = row < rows_valid && m < g.M && nn < g.N;
+            bia[u] = rvv[u] = res[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok[u]) {
+                if (g.bias) bia[u] = ld_f4(g.bias + nn);
+                if (rowvec) rvv[u] = ld_f4(rowvec + (int64_t)(m / g.Lout) * g.rowvec_b_stride + nn);
+                if (GATE == MUGD_GATE_NONE && g.residual) res[u] = ld_f4(g.residual + (int64_t)m * g.ldr + nn);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (!ok[u]) continue;
+            const int idx = i0 + u * TC_THREADS + (int)threadIdx.x;
+            const int row = idx / C4, c4 = idx - row * C4;
+            tc_finish4<ACT, GATE>(g, acc[u], bia[u], rvv[u], res[u], m_base + row, n0 + c4 * 4);
+        }
+    }
+}
+
+// single float4 variant used by the split-K reduce
+template <int ACT, int GATE>
+__device__ __forceinline__ void tc_epi4(const mugd_gemm& g, float4 acc, int m, int nn, const float* rowvec) {
+    float4 bia = make_float4(0.f, 0.f, 0.f, 0.f), rvv = bia, res = bia;
+    if (g.bias) bia = ld_f4(g.bias + nn);
+    if (rowvec) rvv = ld_f4(rowvec + (int64_t)(m / g.Lout) * g.rowvec_b_stride + nn);
+    if (GATE == MUGD_GATE_NONE && g.residual) res = ld_f4(g.residual + (int64_t)m * g.ldr + nn);
+    tc_finish4<ACT, GATE>(g, acc, bia, rvv, res, m, nn);
+}
+
+#define TC_DISPATCH_EPI(g, CALL)                                                                      \
+    do {                                                                                              \
+        if ((g).gate == MUGD_GATE_GEGLU) { CALL(MUGD_ACT_NONE, MUGD_GATE_GEGLU); }                    \
+        else if ((g).gate == MUGD_GATE_GLU) { CALL(MUGD_ACT_NONE, MUGD_GATE_GLU); }                   \
+        else if ((g).act == MUGD_ACT_SILU) { CALL(MUGD_ACT_SILU, MUGD_GATE_NONE); }                   \
+        else if ((g).act == MUGD_ACT_GELU) { CALL(MUGD_ACT_GELU, MUGD_GATE_NONE); }                   \
+        else { CALL(MUGD_ACT_NONE, MUGD_GATE_NONE); }                                                 \
+    } while (0)
+
+// rows of output tile `by`
+__device__ __forceinline__ void tc_tile_rows(const TcParams& p, int by, int& b_base, int& l_base, int& rows_valid) {
+    if (p.Lrows >= TC_BM) {
+        b_base = by / p.tiles_per_sample;
+        l_base = (by % p.tiles_per_sample) * TC_BM;
+        rows_valid = min(TC_BM, p.Lrows - l_base);
+    } else {
+        b_base = by * p.box_b;
+        l_base = 0;
+        rows_valid = min(p.box_b, p.Bs - b_base) * p.Lrows;
+    }
+}
+
+// Barrier block of one CTA (at base + TILE_BYTES): full[SAS] conv[SA] empty[SA], decoupled rings add afree[SAS] wfull[SW]
+// wfree[SW]; then accum and the tmem-pointer slot.
+template <int BN>
+struct TcBars {
+    using S = TcSmem<BN>;
+    static constexpr int N_DEC = S::DEC ? S::SAS + 2 * S::SW : 0;
+    static constexpr int COUNT = S::SAS + 2 * S::SA + N_DEC + 1;
+    static_assert(8 * (COUNT + 1) <= (int)S::BAR_BYTES, "barrier block");
+    uint32_t bars;
+    __device__ __forceinline__ explicit TcBars(uint32_t base) : bars(base + S::TILE_BYTES) {}
+    __device__ __forceinline__ uint32_t full(int s) const { return bars + 8u * s; }                                    // raw A tile (coupled: + W) landed
+    __device__ __forceinline__ uint32_t conv(int s) const { return bars + 8u * (S::SAS + s); }                         // split A in its TMEM slot
+    __device__ __forceinline__ uint32_t empty(int s) const { return bars + 8u * (S::SAS + S::SA + s); }                // coupled: stage free; decoupled: TMEM slot retired
+    __device__ __forceinline__ uint32_t afree(int s) const { return bars + 8u * (S::SAS + 2 * S::SA + s); }            // decoupled: raw A tile consumed
+    __device__ __forceinline__ uint32_t wfull(int s) const { return bars + 8u * (2 * S::SAS + 2 * S::SA + s); }        // decoupled: weight stage landed
+    __device__ __forceinline__ uint32_t wfree(int s) const { return bars + 8u * (2 * S::SAS + 2 * S::SA + S::SW + s); }
+    __device__ __forceinline__ uint32_t accum() const { return bars + 8u * (COUNT - 1); }
+    __device__ __forceinline__ uint32_t tmem_slot() const { return bars + 8u * COUNT; }
+    // (re-)arm every barrier for one tile; called by ONE thread between two CTA-wide barriers
+    __device__ __forceinline__ void init(bool reinit) const {
+        if (reinit) {
+            for (int i = 0; i < COUNT; ++i) mbar_inval(bars + 8u * i);
+        }
+        for (int s = 0; s < S::SA; ++s) { mbar_init(conv(s), 4); mbar_init(empty(s), 1); }
+        for (int s = 0; s < S::SAS; ++s) mbar_init(full(s), 1);
+        if constexpr (S::DEC) {
+            for (int s = 0; s < S::SAS; ++s) mbar_init(afree(s), 4);
+            for (int s = 0; s < S::SW; ++s) { mbar_init(wfull(s), 1); mbar_init(wfree(s), 1); }
+        }
+        mbar_init(accum(), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+};
+
+// One 128 x BN output tile (bx, by) of split bz.  `base` = 1024-byte aligned shared-memory address of the CTA's tile pool
+// (TcSmem<BN>::TILE_BYTES + barrier block), `tmem_base` = allocated tensor memory (>= TcSmem<BN>::TMEM_NEED columns), barriers
+// armed by the caller (TcBars::init) and visible to all threads.  All 256 threads call it; on return every TMA has landed, every
+// MMA has retired and been observed, and the tile (or its partial) is on its way to global memory.
+// PDL: stand-alone launches pass true -- the producer side executes griddepcontrol.wait before touching activations.
+template <int BN, bool PDL>
+__device__ __forceinline__ void gemm_tc_tile(const CUtensorMap* tmA, const CUtensorMap* tmA1, const CUtensorMap* tmA2, const CUtensorMap* tmB,
+                                             const CUtensorMap* tmWhi, const CUtensorMap* tmWlo, const TcParams& p, int bx, int by, int bz,
+                                             uint32_t base, uint32_t tmem_base) {
+    using S = TcSmem<BN>;
+    constexpr bool DEC = S::DEC;
+    constexpr int SAS = S::SAS, SA = S::SA, SW = S::SW;
+    const TcBars<BN> B(base);
+    auto a_raw = [&](int s) { return DEC ? base + s * TC_A_BYTES : base + s * S::STAGE_BYTES; };
+    auto b_hi = [&](int s) { return DEC ? base + SAS * TC_A_BYTES + s * 2 * S::B_BYTES : base + s * S::STAGE_BYTES + TC_A_BYTES; };
+    auto b_lo = [&](int s) { return b_hi(s) + S::B_BYTES; };
+
+    const mugd_gemm& g = p.g;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = bx * BN;
+    int b_base, l_base, rows_valid;
+    tc_tile_rows(p, by, b_base, l_base, rows_valid);
+    const int m_base = b_base * p.Lrows + l_base;
+    const int it_begin = (int)(((long long)p.total_it * bz) / p.splits);
+    const int it_end = (int)(((long long)p.total_it * (bz + 1)) / p.splits);
+    const int nit = it_end - it_begin;
+#ifdef MUGD_TC_TIMELINE
+    const bool dbg_cta = p.dbg && bx == 0 && by == 0 && bz == 0;
+#define TC_STAMP(cond, slot) do { if (dbg_cta && (cond)) p.dbg[slot] = gtimer(); } while (0)
+#else
+#define TC_STAMP(cond, slot) do { } while (0)
+#endif
+    TC_STAMP(threadIdx.x == 0, 1);
+
+    if (warp == 0) {
+        // ===================================== TMA producer =====================================
+        // the whole warp walks the loop converged; one elected lane issues the copies
+        const uint32_t a_tx = (uint32_t)(p.box_l * p.box_b) * TC_BK * 4;
+        const uint32_t w_tx = (p.single_pass ? 1u : 2u) * S::B_BYTES;
+        for (int i = 0; i < nit; ++i) {
+            const int s = i % SAS;
+            const uint32_t ph = (uint32_t)(i / SAS) & 1u;
+            if constexpr (DEC) mbar_wait(B.afree(s), ph ^ 1u);
+            else mbar_wait(B.empty(s), ph ^ 1u);
+            if (elect_one()) {
+                TC_STAMP(i < 24, 8 + i * 6 + 5);
+                const int it = it_begin + i;
+                mbar_expect_tx(B.full(s), DEC ? a_tx : a_tx + w_tx);
+                if constexpr (!DEC) {
+                    // weights first: they do not depend on the previous kernel / op.  W columns are in k-step order.
+                    tma_load_2d(b_hi(s), tmWhi, B.full(s), it * TC_BK, n0);
+                    if (!p.single_pass) tma_load_2d(b_lo(s), tmWlo, B.full(s), it * TC_BK, n0);
+                }
+                if (PDL && i == 0) pdl_wait();      // activations written by the previous kernel are touched from here on
+                if (it < p.it_main) {
+                    const int t = it / p.kblocks;
+                    const int kb = it - t * p.kblocks;
+                    // row addressing per tap: SAME = l+t-1, TAPS = l+(t+shift)*dilation (zero fill outside the sample by TMA
+                    // bounds); DOWN (stride 2, right pad) uses one strided tensor map per tap (row l of map t = source row 2l+t)
+                    const CUtensorMap* ma = tmA;
+                    int lshift = 0;
+                    if (g.conv_mode == MUGD_CONV_SAME) lshift = t - 1;
+                    else if (g.conv_mode == MUGD_CONV_TAPS) lshift = (t + g.tap_shift) * (g.tap_dilation > 1 ? g.tap_dilation : 1);
+                    else if (g.conv_mode == MUGD_CONV_DOWN) ma = (t == 0) ? tmA : (t == 1 ? tmA1 : tmA2);
+                    tma_load_3d(a_raw(s), ma, B.full(s), kb * TC_BK, l_base + lshift, b_base);
+                } else {
+                    tma_load_3d(a_raw(s), tmB, B.full(s), (it - p.it_main) * TC_BK, l_base, b_base);   // second source: 1x1 term
+                }
+                TC_STAMP(i < 24, 8 + i * 6 + 0);
+            }
+            __syncwarp();
+        }
+    } else if (DEC && warp == 3) {
+        // ===================================== weight producer (decoupled rings) ================
+        for (int i = 0; i < nit; ++i) {
+            const int s = i % SW;
+            const uint32_t ph = (uint32_t)(i / SW) & 1u;
+            mbar_wait(B.wfree(s), ph ^ 1u);
+            if (elect_one()) {
+                const int it = it_begin + i;
+                mbar_expect_tx(B.wfull(s), (p.single_pass ? 1u : 2u) * S::B_BYTES);
+                tma_load_2d(b_hi(s), tmWhi, B.wfull(s), it * TC_BK, n0);
+                if (!p.single_pass) tma_load_2d(b_lo(s), tmWlo, B.wfull(s), it * TC_BK, n0);
+            }
+            __syncwarp();
+        }
+    } else if (warp == 1) {
+        // ===================================== MMA issuer =======================================
+        // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A=TF32 [7,10)=2, B=TF32 [10,13)=2,
+        // A/B K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+        for (int i = 0; i < nit; ++i) {
+            const int s = i % SA;
+            const uint32_t ph = (uint32_t)(i / SA) & 1u;
+            const int sw = DEC ? i % SW : s;
+            mbar_wait(B.conv(s), ph);
+            if constexpr (DEC) mbar_wait(B.wfull(sw), (uint32_t)(i / SW) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (elect_one()) {
+                TC_STAMP(i < 24, 8 + i * 6 + 3);
+                const uint64_t dbh = umma_desc(b_hi(sw)), dbl = umma_desc(b_lo(sw));
+                const uint32_t ta_hi = tmem_base + (uint32_t)(BN + s * 64), ta_lo = ta_hi + 32u;
+#pragma unroll
+                for (int kk = 0; kk < TC_BK / 8; ++kk) {
+                    const uint64_t ko = (uint64_t)(kk * 2);     // 8 fp32 = 32 bytes = 2 x 16-byte units
+                    if (p.single_pass) {
+                        umma_tf32_ts(tmem_base, ta_hi + kk * 8, dbh + ko, idesc, (i > 0 || kk > 0) ? 1u : 0u);
+                    } else {
+                        umma_tf32_ts(tmem_base, ta_lo + kk * 8, dbh + ko, idesc, (i > 0 || kk > 0) ? 1u : 0u);
+                        umma_tf32_ts(tmem_base, ta_hi + kk * 8, dbl + ko, idesc, 1u);
+                        umma_tf32_ts(tmem_base, ta_hi + kk * 8, dbh + ko, idesc, 1u);
+                    }
+                }
+                umma_commit(B.empty(s));                      // stage (decoupled: TMEM operand slot) reusable once these MMAs retire
+                if constexpr (DEC) umma_commit(B.wfree(sw));  // ... and the weight stage
+                TC_STAMP(i < 24, 8 + i * 6 + 4);
+            }
+            __syncwarp();
+        }
+        if (elect_one()) umma_commit(B.accum());
+        __syncwarp();
+        // drain: observe the release of the last use of every stage, so that no commit is still on its way to a barrier when the
+        // caller re-arms them for the next tile (persistent kernel) or the CTA exits
+        for (int i = (nit > SA ? nit - SA : 0); i < nit; ++i) mbar_wait(B.empty(i % SA), (uint32_t)(i / SA) & 1u);
+        if constexpr (DEC) {
+            for (int i = (nit > SW ? nit - SW : 0); i < nit; ++i) mbar_wait(B.wfree(i % SW), (uint32_t)(i / SW) & 1u);
+        }
+    } else if (warp >= 4) {
+        // ===================================== converter ========================================
+        for (int i = 0; i < nit; ++i) {
+            const int s = i % SA;                                     // TMEM operand slot
+            const int sm = i % SAS;                                   // raw tile in shared memory
+            mbar_wait(B.full(sm), (uint32_t)(i / SAS) & 1u);
+            if constexpr (DEC) {
+                mbar_wait(B.empty(s), ((uint32_t)(i / SA) & 1u) ^ 1u);   // the MMAs that read TMEM slot s last time have retired
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            }
+            TC_STAMP(threadIdx.x == 128 && i < 24, 8 + i * 6 + 1);
+            // thread = tile row (= TMEM lane): read the row's 128 bytes out of the 128B-swizzled tile (16-byte chunk c
+            // of row r sits at chunk c ^ (r & 7)), split, and store hi / lo to this slot's TMEM columns
+            const int r = (warp & 3) * 32 + lane;
+            const uint32_t rowaddr = a_raw(sm) + (uint32_t)r * 128u;
+            float hi[32], lo[32];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                float4 x;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
+                             : "r"(rowaddr + (uint32_t)((c ^ (r & 7)) * 16)));
+                hi[c * 4] = to_tf32(x.x); hi[c * 4 + 1] = to_tf32(x.y); hi[c * 4 + 2] = to_tf32(x.z); hi[c * 4 + 3] = to_tf32(x.w);
+                lo[c * 4] = to_tf32(x.x - hi[c * 4]); lo[c * 4 + 1] = to_tf32(x.y - hi[c * 4 + 1]);
+                lo[c * 4 + 2] = to_tf32(x.z - hi[c * 4 + 2]); lo[c * 4 + 3] = to_tf32(x.w - hi[c * 4 + 3]);
+            }
+            const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(BN + s * 64);
+            tmem_st32(ta, hi);
+            tmem_st32(ta + 32u, lo);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(B.conv(s));
+                if constexpr (DEC) mbar_arrive(B.afree(sm));          // the raw tile has been read: its smem slot may be refilled
+            }
+            TC_STAMP(threadIdx.x == 128 && i < 24, 8 + i * 6 + 2);
+        }
+        // ===================================== epilogue, phase 1 ================================
+        mbar_wait(B.accum(), 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        TC_STAMP(threadIdx.x == 128, 2);
+        const int q = warp & 3;                                        // TMEM lane quarter this warp may read
+        const int r = q * 32 + lane;                                   // tile row == TMEM lane
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+        // TMEM -> registers -> shared (the pipeline buffers are free: every TMA landed, every MMA retired).
+        // Row pitch BN+4 floats keeps the per-row float4 stores and the row-contiguous reads below conflict-free.
+        constexpr int SP = BN + 4;
+        float v[32];
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            tmem_ld32(trow + (uint32_t)c0, v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(base + (uint32_t)(r * SP + c0 + j * 4) * 4u), "f"(v[j * 4]),
+                             "f"(v[j * 4 + 1]), "f"(v[j * 4 + 2]), "f"(v[j * 4 + 3]) : "memory");
+        }
+        TC_STAMP(threadIdx.x == 128, 3);
+    }
+    // ---- phase 2 (all 8 warps): consecutive threads take consecutive float4 of a row -> coalesced global traffic.
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    TC_STAMP(threadIdx.x == 0, 5);
+    {
+        const int step = g.step ? *g.step : 0;
+        const float* rowvec = g.rowvec ? g.rowvec + (int64_t)step * g.rowvec_step_stride : nullptr;
+        if (p.splits > 1) {
+            const int tile_lin = by * p.gx + bx;
+            float* wsp = p.ws + ((int64_t)tile_lin * p.splits + bz) * (TC_BM * BN);
+            constexpr int SP = BN + 4;
+            constexpr int C4 = BN / 4;
+            constexpr int U = 8;
+#pragma unroll 1
+            for (int i0 = 0; i0 < TC_BM * C4; i0 += TC_THREADS * U) {
+                float4 acc[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int idx = i0 + u * TC_THREADS + (int)threadIdx.x;
+                    const int row = idx / C4, c4 = idx - row * C4;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(acc[u].x), "=f"(acc[u].y), "=f"(acc[u].z), "=f"(acc[u].w)
+                                 : "r"(base + (uint32_t)(row * SP + c4 * 4) * 4u));
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) st_f4(wsp + (i0 + u * TC_THREADS + (int)threadIdx.x) * 4, acc[u]);   // [row][BN] dense
+            }
+        } else {
+#define TC_CALL_STORE(A_, G_) tc_store_tile<BN, A_, G_>(g, base, m_base, n0, rows_valid, rowvec)
+            TC_DISPATCH_EPI(g, TC_CALL_STORE);
+#undef TC_CALL_STORE
+        }
+    }
+    TC_STAMP(threadIdx.x == 0, 4);
+#undef TC_STAMP
+}
+
+// split-K second pass, one float4 of the output per call: sum the partial tiles in fixed split order (deterministic) and run
+// the fused epilogue.  idx enumerates (tile, row, 4-column group) over the whole tile grid.
+template <int BN>
+__device__ __forceinline__ void tc_reduce_item(const TcParams& p, long long idx) {
+    const mugd_gemm& g = p.g;
+    constexpr int C4 = BN / 4;
+    const int c4 = (int)(idx % C4);
+    const int r = (int)((idx / C4) % TC_BM);
+    const int tile_lin = (int)(idx / ((long long)C4 * TC_BM));
+    const int bx = tile_lin % p.gx, by = tile_lin / p.gx;
+    int b_base, l_base, rows_valid;
+    tc_tile_rows(p, by, b_base, l_base, rows_valid);
+    const int m = b_base * p.Lrows + l_base + r;
+    const int n = bx * BN + c4 * 4;
+    if (r >= rows_valid || m >= g.M || n >= g.N) return;
+    const float* src = p.ws + ((long long)tile_lin * p.splits) * (TC_BM * BN) + (long long)r * BN + c4 * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int z = 0; z < p.splits; ++z) {                                   // fixed order -> deterministic
+        const float4 t4 = __ldcg(reinterpret_cast<const float4*>(src + (long long)z * (TC_BM * BN)));
+        acc.x += t4.x; acc.y += t4.y; acc.z += t4.z; acc.w += t4.w;
+    }
+    const int step = g.step ? *g.step : 0;
+    const float* rowvec = g.rowvec ? g.rowvec + (int64_t)step * g.rowvec_step_stride : nullptr;
+#define TC_CALL_EPI(A_, G_) tc_epi4<A_, G_>(g, acc, m, n, rowvec)
+    TC_DISPATCH_EPI(g, TC_CALL_EPI);
+#undef TC_CALL_EPI
+}
+#endif  // __CUDACC__
+
+// ---- host side (gemm_tc.cu) -------------------------------------------------------------------------
+struct TcGeometry {
+    int BN, splits, gx, gy, Lrows, Bs, box_l, box_b, tiles_per_sample, total_it;
+    int64_t ws_floats;
+};
+// one planned tensor-core GEMM: kernel parameters + its six tensor maps (A taps 0..2, second source, W_hi, W_lo)
+struct alignas(64) TcPlanned {
+    CUtensorMap maps[6];
+    TcParams p;
+};
+TcGeometry tc_geometry(const mugd_gemm& g, int sm_count, int forced_split);
+int tc_plan(const DeviceInfo& dev, const mugd_gemm& g, TcPlanned* out);     // validates, picks the geometry, encodes the maps
+
+}  // namespace mugd

@@ -90,7 +90,8 @@ class OpList:
              mode: int = L_.CONV_NONE, Lin: int = 0, Lout: int = 0, act: int = L_.ACT_NONE,
              gate: int = L_.GATE_NONE, residual: Optional[View] = None, rowvec: int = 0,
              rowvec_b_stride: int = 0, rowvec_step_stride: int = 0, step: int = 0, impl: int = L_.GEMM_AUTO,
-             W_hi: int = 0, W_lo: int = 0, split_k: int = 0, tap_shift: int = 0, dilation: int = 1, tag: int = 0):
+             W_hi: int = 0, W_lo: int = 0, split_k: int = 0, tap_shift: int = 0, dilation: int = 1, tag: int = 0,
+             A2: Optional[View] = None):
         g = L_.Gemm()
         M = out.rows
         g.A, g.lda = A.ptr, A.ld
@@ -104,6 +105,9 @@ class OpList:
         g.step = step or None
         if residual is not None:
             g.residual, g.ldr = residual.ptr, residual.ld
+        if A2 is not None:                     # second activation source: K2 more channels at the output row (1x1 term)
+            assert A2.rows == out.rows, (A2.rows, out.rows)
+            g.A2, g.lda2, g.K2 = A2.ptr, A2.ld, A2.cols
         g.C, g.ldc = out.ptr, out.ld
         g.M, g.N, g.K = M, N, K
         g.taps, g.conv_mode = taps, mode
@@ -276,14 +280,13 @@ class UNetCompiler:
                      rowvec_step_stride=0 if per_sample_t else emb_total, step=0 if per_sample_t else step, tag=TAG_RES)
             t3 = arena.alloc(x.rows, b.cout)
             ops.groupnorm(t2, t3, self.w(p + "out_layers.0.weight"), self.w(p + "out_layers.0.bias"), Bq, Lr, cfg.gn_groups, True, TAG_RES)
-            res = x
             if b.has_skip_conv:
-                t4 = arena.alloc(x.rows, b.cout)
-                ops.gemm(x, self.w(p + "skip_connection.weight"), b.cout, b.cin, t4, bias=self.w(p + "skip_connection.bias"),
-                         Lout=Lr, tag=TAG_RES)
-                res = t4
-            ops.gemm(t3, self.w(p + "out_layers.3.weight"), b.cout, b.cout, out, bias=self.w(p + "out_layers.3.bias"), taps=3,
-                     mode=L_.CONV_SAME, Lin=Lr, Lout=Lr, residual=res, tag=TAG_RES)
+                # conv3(t3) + skip_connection(x) as ONE GEMM: the 1x1 skip runs as extra k-steps on a second source
+                ops.gemm(t3, self.w(p + "out_skip.weight"), b.cout, b.cout, out, bias=self.w(p + "out_skip.bias"), taps=3,
+                         mode=L_.CONV_SAME, Lin=Lr, Lout=Lr, A2=x, tag=TAG_RES)
+            else:
+                ops.gemm(t3, self.w(p + "out_layers.3.weight"), b.cout, b.cout, out, bias=self.w(p + "out_layers.3.bias"), taps=3,
+                         mode=L_.CONV_SAME, Lin=Lr, Lout=Lr, residual=x, tag=TAG_RES)
             arena.release(m)
 
         attn_index = [0]
@@ -325,11 +328,9 @@ class UNetCompiler:
             ff = arena.alloc(x.rows, 4 * Cc)
             ops.gemm(n3, self.w(t + "ff.net.0.proj.weight"), 8 * Cc, Cc, ff, bias=self.w(t + "ff.net.0.proj.bias"),
                      gate=L_.GATE_GEGLU, Lout=Lr, tag=TAG_ATTN)
-            h3 = h1
-            ops.gemm(ff, self.w(t + "ff.net.2.weight"), Cc, 4 * Cc, h3, bias=self.w(t + "ff.net.2.bias"), residual=h2,
-                     Lout=Lr, tag=TAG_ATTN)
-            ops.gemm(h3, self.w(p + "proj_out.weight"), Cc, Cc, out, bias=self.w(p + "proj_out.bias"), residual=x,
-                     Lout=Lr, tag=TAG_ATTN)
+            # proj_out(ff.net.2(ff) + h2) + x as ONE GEMM over [ff | h2] with the packer-composed weight [Wp Wf | Wp]
+            ops.gemm(ff, self.w(p + "ff_out.weight"), Cc, 4 * Cc, out, bias=self.w(p + "ff_out.bias"), residual=x, Lout=Lr,
+                     A2=h2, tag=TAG_ATTN)
             arena.release(m)
 
         def emit_s4(b: Block, x: View, out: View, lvl: int):
@@ -466,14 +467,12 @@ class DecoderCompiler:
                          mode=L_.CONV_SAME, Lin=Lr, Lout=Lr, tag=TAG_RES)
                 t3 = arena.alloc(B * Lr, b.cout)
                 ops.groupnorm(t2, t3, self.w(p + "norm2.weight"), self.w(p + "norm2.bias"), B, Lr, G, True, TAG_RES)
-                res = cur
                 if b.has_skip_conv:
-                    t4 = arena.alloc(B * Lr, b.cout)
-                    ops.gemm(cur, self.w(p + "nin_shortcut.weight"), b.cout, b.cin, t4, bias=self.w(p + "nin_shortcut.bias"),
-                             Lout=Lr, tag=TAG_RES)
-                    res = t4
-                ops.gemm(t3, self.w(p + "conv2.weight"), b.cout, b.cout, o, bias=self.w(p + "conv2.bias"), taps=3,
-                         mode=L_.CONV_SAME, Lin=Lr, Lout=Lr, residual=res, tag=TAG_RES)
+                    ops.gemm(t3, self.w(p + "out_skip.weight"), b.cout, b.cout, o, bias=self.w(p + "out_skip.bias"), taps=3,
+                             mode=L_.CONV_SAME, Lin=Lr, Lout=Lr, A2=cur, tag=TAG_RES)
+                else:
+                    ops.gemm(t3, self.w(p + "conv2.weight"), b.cout, b.cout, o, bias=self.w(p + "conv2.bias"), taps=3,
+                             mode=L_.CONV_SAME, Lin=Lr, Lout=Lr, residual=cur, tag=TAG_RES)
                 arena.release(m)
                 cur = o
             elif b.kind == "up":

@@ -18,7 +18,7 @@ CONV_NONE, CONV_SAME, CONV_DOWN, CONV_UP, CONV_TAPS = range(5)
 ACT_NONE, ACT_SILU, ACT_GELU = range(3)
 GATE_NONE, GATE_GEGLU, GATE_GLU = range(3)
 GEMM_AUTO, GEMM_SIMT, GEMM_TC = range(3)
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 _f = C.c_void_p  # device pointers travel as integers
 
@@ -31,7 +31,8 @@ class Gemm(C.Structure):
                 ("taps", C.c_int32), ("conv_mode", C.c_int32), ("Lin", C.c_int32), ("Lout", C.c_int32),
                 ("act", C.c_int32), ("gate", C.c_int32), ("impl", C.c_int32),
                 ("split_k", C.c_int32), ("n_counters", C.c_int32), ("tap_shift", C.c_int32), ("tap_dilation", C.c_int32),
-                ("workspace", _f), ("workspace_bytes", C.c_int64), ("counters", _f)]
+                ("workspace", _f), ("workspace_bytes", C.c_int64), ("counters", _f),
+                ("A2", _f), ("lda2", C.c_int64), ("K2", C.c_int32), ("reserved_", C.c_int32)]
 
 
 class GroupNorm(C.Structure):
@@ -152,41 +153,17 @@ def load() -> C.CDLL:
     mine = [C.sizeof(t) for t in (Op, Gemm, GroupNorm, LayerNorm, Attention, S4Conv, DdimUpdate, Transpose, Copy2D, Notes, Embed)]
     if list(sizes) != mine:
         raise MugdError(f"struct layout mismatch: C {list(sizes)} vs ctypes {mine}")
-    lib.mugd_set_tc_cluster_reduce.argtypes = [C.c_int]
+    lib.mugd_set_tc_single_pass_tf32.argtypes = [C.c_void_p, C.c_int]
+    lib.mugd_set_attention_impl.argtypes = [C.c_void_p, C.c_int]
     lib.mugd_debug_set_tc_tile_n.argtypes = [C.c_int]
-    lib.mugd_set_tc_a_in_tmem.argtypes = [C.c_int]
-    if os.environ.get("MUGD_TC_ATMEM"):
-        lib.mugd_set_tc_a_in_tmem(int(os.environ["MUGD_TC_ATMEM"]))
-    lib.mugd_set_tc_inkernel_reduce_max.argtypes = [C.c_int]
-    if os.environ.get("MUGD_TC_INKERNEL"):
-        lib.mugd_set_tc_inkernel_reduce_max(int(os.environ["MUGD_TC_INKERNEL"]))
-    lib.mugd_set_tc_single_pass_tf32.argtypes = [C.c_int]
-    if os.environ.get("MUGD_TC_TF32") == "1":
-        lib.mugd_set_tc_single_pass_tf32(1)
-    lib.mugd_set_tc_narrow_tiles.argtypes = [C.c_int, C.c_float]
-    if os.environ.get("MUGD_TC_NARROW"):
-        lib.mugd_set_tc_narrow_tiles(1, float(os.environ["MUGD_TC_NARROW"]))
     lib.mugd_debug_set_tc_cost.argtypes = [C.c_float, C.c_float, C.c_float]
+    # measurement switches for tuning sweeps (tools/); none of them changes results
     if os.environ.get("MUGD_TC_COST"):
         lib.mugd_debug_set_tc_cost(*[float(v) for v in os.environ["MUGD_TC_COST"].split(",")])
-    lib.mugd_set_tc_coop_reduce.argtypes = [C.c_int, C.c_float]
-    if os.environ.get("MUGD_TC_COOP"):
-        lib.mugd_set_tc_coop_reduce(1 if float(os.environ["MUGD_TC_COOP"]) > 0 else 0, float(os.environ["MUGD_TC_COOP"]))
-    lib.mugd_set_tc_pdl_reduce.argtypes = [C.c_int]
-    if os.environ.get("MUGD_TC_PDLR"):
-        lib.mugd_set_tc_pdl_reduce(int(os.environ["MUGD_TC_PDLR"]))
-    lib.mugd_set_attention_impl.argtypes = [C.c_int]
-    if os.environ.get("MUGD_ATTN"):
-        lib.mugd_set_attention_impl(int(os.environ["MUGD_ATTN"]))
-    lib.mugd_set_tc_multicast.argtypes = [C.c_int]
-    if os.environ.get("MUGD_TC_MC"):
-        lib.mugd_set_tc_multicast(int(os.environ["MUGD_TC_MC"]))
     if os.environ.get("MUGD_TC_BN"):
         lib.mugd_debug_set_tc_tile_n(int(os.environ["MUGD_TC_BN"]))
-    if os.environ.get("MUGD_TC_CLUSTER", "0") == "1":   # A/B switch: split-K reduction through cluster DSMEM
-        lib.mugd_set_tc_cluster_reduce(1)
-    if os.environ.get("MUGD_PDL", "0") == "1":          # A/B switch for programmatic dependent launch (default off)
-        lib.mugd_set_pdl(1)
+    if os.environ.get("MUGD_PDL") in ("0", "1"):
+        lib.mugd_set_pdl(int(os.environ["MUGD_PDL"]))
     _lib = lib
     return lib
 
@@ -203,5 +180,7 @@ def check(rc: int, what: str = ""):
 EXPORTED_SYMBOLS = [
     "mugd_abi_version", "mugd_last_error", "mugd_create", "mugd_destroy", "mugd_device_info", "mugd_set_gemm_impl",
     "mugd_op_run", "mugd_plan_create", "mugd_plan_run", "mugd_plan_capture", "mugd_plan_replay",
-    "mugd_plan_launch_count", "mugd_plan_destroy", "mugd_s4_kernel_gen", "mugd_fill_i32", "mugd_abi_sizes", "mugd_gemm_tc_query", "mugd_set_pdl", "mugd_set_tc_cluster_reduce", "mugd_debug_set_tc_tile_n", "mugd_set_tc_a_in_tmem", "mugd_set_tc_inkernel_reduce_max", "mugd_set_tc_single_pass_tf32", "mugd_set_tc_multicast", "mugd_debug_set_tc_plain_store", "mugd_debug_set_attention_dump", "mugd_set_tc_coop_reduce", "mugd_debug_set_tc_cost", "mugd_set_tc_pdl_reduce", "mugd_set_tc_narrow_tiles", "mugd_set_attention_impl", "mugd_debug_set_tc_timing",
+    "mugd_plan_launch_count", "mugd_plan_destroy", "mugd_s4_kernel_gen", "mugd_fill_i32", "mugd_abi_sizes", "mugd_gemm_tc_query",
+    "mugd_set_pdl", "mugd_set_tc_single_pass_tf32", "mugd_set_attention_impl", "mugd_debug_set_tc_tile_n", "mugd_debug_set_tc_cost",
+    "mugd_debug_set_attention_dump", "mugd_debug_set_tc_timing",
 ]

@@ -7,6 +7,10 @@ Layouts (all row-major fp32, every tensor 256-byte aligned inside the blob):
   cross-attn to_k|to_v       ->  one [2C][ctx] matrix (runs once per request: context is step-invariant)
   GEGLU / S4 output_linear   ->  rows interleaved (value_j, gate_j) so the gate is applied in the epilogue
   emb_layers of all ResBlocks->  one [sum Cout][512] matrix (evaluated once per request for all S steps)
+  ResBlock conv2 + skip 1x1  ->  one [Cout][3*Cout + Cin] matrix: the skip_connection runs as extra k-steps of the second
+                                 conv's GEMM on a second activation source (unet.py:187-193,237-239; decoder nin_shortcut too)
+  ff.net.2 then proj_out     ->  one [C][4C + C] matrix  [Wp Wf | Wp]:  proj_out(ff.net.2(f) + h) = (Wp Wf) f + Wp h + (Wp bf + bp)
+                                 (attention.py:57-65,194-199; the product is formed in fp64 at pack time)
 The blob is what rank 0 broadcasts over NCCL for multi-GPU runs (one collective).
 """
 from __future__ import annotations
@@ -112,29 +116,31 @@ def _pack_block(blob: WeightBlob, sd: Dict[str, torch.Tensor], b: Block):
         for n in ("in_layers.0.", "out_layers.0."):
             blob.add_shaped(p + n + "weight", sd[p + n + "weight"])
             blob.add_shaped(p + n + "bias", sd[p + n + "bias"])
-        for n in ("in_layers.2.", "out_layers.3."):
+        for n in ("in_layers.2.",) + (() if b.has_skip_conv else ("out_layers.3.",)):
             blob.add_shaped(p + n + "weight", _conv3(sd[p + n + "weight"]))
             blob.add_shaped(p + n + "bias", sd[p + n + "bias"])
         if b.has_skip_conv:
-            blob.add_shaped(p + "skip_connection.weight", _conv1(sd[p + "skip_connection.weight"]))
-            blob.add_shaped(p + "skip_connection.bias", sd[p + "skip_connection.bias"])
+            blob.add_shaped(p + "out_skip.weight", torch.cat([_conv3(sd[p + "out_layers.3.weight"]), _conv1(sd[p + "skip_connection.weight"])], dim=1))
+            blob.add_shaped(p + "out_skip.bias", sd[p + "out_layers.3.bias"] + sd[p + "skip_connection.bias"])
     elif b.kind == "dec_res":
         for n in ("norm1.", "norm2."):
             blob.add_shaped(p + n + "weight", sd[p + n + "weight"])
             blob.add_shaped(p + n + "bias", sd[p + n + "bias"])
-        for n in ("conv1.", "conv2."):
+        for n in ("conv1.",) + (() if b.has_skip_conv else ("conv2.",)):
             blob.add_shaped(p + n + "weight", _conv3(sd[p + n + "weight"]))
             blob.add_shaped(p + n + "bias", sd[p + n + "bias"])
         if b.has_skip_conv:
-            blob.add_shaped(p + "nin_shortcut.weight", _conv1(sd[p + "nin_shortcut.weight"]))
-            blob.add_shaped(p + "nin_shortcut.bias", sd[p + "nin_shortcut.bias"])
+            blob.add_shaped(p + "out_skip.weight", torch.cat([_conv3(sd[p + "conv2.weight"]), _conv1(sd[p + "nin_shortcut.weight"])], dim=1))
+            blob.add_shaped(p + "out_skip.bias", sd[p + "conv2.bias"] + sd[p + "nin_shortcut.bias"])
     elif b.kind == "attn":
         blob.add_shaped(p + "norm.weight", sd[p + "norm.weight"])
         blob.add_shaped(p + "norm.bias", sd[p + "norm.bias"])
-        for n in ("proj_in.", "proj_out."):
-            blob.add_shaped(p + n + "weight", _conv1(sd[p + n + "weight"]))
-            blob.add_shaped(p + n + "bias", sd[p + n + "bias"])
+        blob.add_shaped(p + "proj_in.weight", _conv1(sd[p + "proj_in.weight"]))
+        blob.add_shaped(p + "proj_in.bias", sd[p + "proj_in.bias"])
         t = p + "transformer_blocks.0."
+        wp, wf = _conv1(sd[p + "proj_out.weight"]).double(), sd[t + "ff.net.2.weight"].double()
+        blob.add_shaped(p + "ff_out.weight", torch.cat([wp @ wf, wp], dim=1).float())
+        blob.add_shaped(p + "ff_out.bias", (wp @ sd[t + "ff.net.2.bias"].double() + sd[p + "proj_out.bias"].double()).float())
         blob.add_shaped(t + "attn1.qkv.weight", torch.cat([sd[t + "attn1.to_q.weight"], sd[t + "attn1.to_k.weight"],
                                                            sd[t + "attn1.to_v.weight"]], dim=0))
         blob.add_shaped(t + "attn2.to_q.weight", sd[t + "attn2.to_q.weight"])
@@ -146,8 +152,6 @@ def _pack_block(blob: WeightBlob, sd: Dict[str, torch.Tensor], b: Block):
             blob.add_shaped(t + a + "C_embedding", sd[t + a + "C_embedding"])
         blob.add_shaped(t + "ff.net.0.proj.weight", _interleave_halves(sd[t + "ff.net.0.proj.weight"]))
         blob.add_shaped(t + "ff.net.0.proj.bias", _interleave_halves(sd[t + "ff.net.0.proj.bias"]))
-        blob.add_shaped(t + "ff.net.2.weight", sd[t + "ff.net.2.weight"])
-        blob.add_shaped(t + "ff.net.2.bias", sd[t + "ff.net.2.bias"])
         for n in ("norm1.", "norm2.", "norm3."):
             blob.add_shaped(t + n + "weight", sd[t + n + "weight"])
             blob.add_shaped(t + n + "bias", sd[t + n + "bias"])

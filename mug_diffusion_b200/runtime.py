@@ -94,10 +94,10 @@ class MugEngine:
 
     def set_gemm_impl(self, impl: str):
         # "tc_tf32" is an opt-in speed mode: single-pass TF32 tensor-core products (~2^-11 per product) instead of the
-        # fp32-accurate 3xTF32 split.  It is process-wide (library global) and never used by the parity tests or bench.py.
+        # fp32-accurate 3xTF32 split.  Per-handle state; never used by the parity tests or bench.py.
         code = {"auto": L_.GEMM_TC, "simt": L_.GEMM_SIMT, "tc": L_.GEMM_TC, "tc_tf32": L_.GEMM_TC}[impl]
         L_.check(self.lib.mugd_set_gemm_impl(self.handle, code), "set_gemm_impl")
-        L_.check(self.lib.mugd_set_tc_single_pass_tf32(1 if impl == "tc_tf32" else 0), "set_tc_single_pass_tf32")
+        L_.check(self.lib.mugd_set_tc_single_pass_tf32(self.handle, 1 if impl == "tc_tf32" else 0), "set_tc_single_pass_tf32")
         self.gemm_impl = impl
         self.sessions.clear()
         self.dec_sessions.clear()
@@ -271,19 +271,26 @@ class Session:
         ops.gemm(h2, w(up + "emb_all.weight"), self.emb_table.shape[1], cfg.time_embed_dim, et, bias=w(up + "emb_all.bias"))
         eng.run_ops(ops)
 
-    def set_context(self, context: torch.Tensor):
-        """context [Beff, ctx_dim, T] (reference layout) -> per-layer cross-attention K|V projections
-        (attention.py:97-98), constant over the DDIM steps."""
+    def set_context(self, context):
+        """context [Beff, ctx_dim, T] (reference layout; or a list of such tensors that follow each other along the batch, e.g.
+        [uc, c] under classifier-free guidance, ddim.py:173) -> per-layer cross-attention K|V projections (attention.py:97-98),
+        constant over the DDIM steps."""
         eng = self.engine
         cfg = eng.cfg.unet
-        Bc, Cd, T = context.shape
-        assert Bc == self.Beff and Cd == cfg.context_dim and T <= CTX_TOKENS_MAX
+        parts = list(context) if isinstance(context, (list, tuple)) else [context]
+        parts = [c.to(eng.device, torch.float32).contiguous() for c in parts]
+        Bc = sum(int(c.shape[0]) for c in parts)
+        _, Cd, T = parts[0].shape
+        assert Bc == self.Beff and Cd == cfg.context_dim and T <= CTX_TOKENS_MAX and all(c.shape[1:] == parts[0].shape[1:] for c in parts)
         if T != self.ctx_tokens:
             self.ctx_tokens = T
             self._build(self.comp)            # Lk is baked into the attention ops
-        context = context.to(eng.device, torch.float32).contiguous()
         ops = OpList(tc_weight_map(eng.blob, eng.wbase))
-        ops.transpose(_ptr(context), _ptr(self.ctx), 0, cfg.context_dim, Bc, Cd, T, True)
+        row = 0
+        for c in parts:
+            ops.transpose(_ptr(c), _ptr(self.ctx) + 4 * row * cfg.context_dim, 0, cfg.context_dim, int(c.shape[0]), Cd, T, True)
+            row += int(c.shape[0]) * T
+        context = parts
         cv = View(_ptr(self.ctx), cfg.context_dim, Bc * T, cfg.context_dim)
         blocks = [b for b in _all_blocks(self.comp) if b.kind == "attn"]
         for b, kv in zip(blocks, self.ctx_kv):
@@ -292,20 +299,22 @@ class Session:
         eng.run_ops(ops)
         self._keep = context
 
-    def set_audio(self, audios: Sequence[torch.Tensor]):
+    def set_audio(self, audios: Sequence[torch.Tensor], dup: bool = False):
         """The last ``levels`` entries of the wave-encoder output list (unet.py:527-543), NCL layout, written
-        (transposed) into every concat slot that holds them."""
+        (transposed) into every concat slot that holds them.  ``dup``: the tensors hold Beff/2 samples and both halves of the
+        batch get them (the reference concatenates them with themselves under classifier-free guidance, ddim.py:171-174)."""
         cfg = self.engine.cfg.unet
-        w4 = list(audios)[-cfg.levels:]
-        keep = []
+        w4 = [a.to(self.engine.device, torch.float32).contiguous() for a in list(audios)[-cfg.levels:]]
+        Bh = self.Beff // 2 if dup else self.Beff
         ops = OpList()
         for lvl, view in self.audio_slots:
-            a = w4[lvl].to(self.engine.device, torch.float32).contiguous()
-            keep.append(a)
-            assert a.shape == (self.Beff, cfg.audio_channels[lvl], self.Lz >> lvl), (a.shape, lvl)
-            ops.transpose(_ptr(a), view.ptr, 0, view.ld, self.Beff, a.shape[1], a.shape[2], True)
+            a = w4[lvl]
+            assert a.shape == (Bh, cfg.audio_channels[lvl], self.Lz >> lvl), (a.shape, lvl)
+            ops.transpose(_ptr(a), view.ptr, 0, view.ld, Bh, a.shape[1], a.shape[2], True)
+            if dup:
+                ops.transpose(_ptr(a), view.r(Bh * a.shape[2], 2 * Bh * a.shape[2]).ptr, 0, view.ld, Bh, a.shape[1], a.shape[2], True)
         self.engine.run_ops(ops)
-        self._keep_audio = keep
+        self._keep_audio = w4
 
     def load_x(self, x: torch.Tensor, dup: bool):
         """x [B,C,L] -> xin rows (both halves when dup)."""
@@ -382,7 +391,10 @@ class DecoderSession:
         ops = OpList()
         ops.transpose(_ptr(z), self.zin.ptr, 0, self.zin.ld, self.B, cfg.z_channels, self.Lz, True)
         eng.run_ops(ops)
-        self.plan.run()
+        if not self.plan.captured:
+            self.plan.run()                   # warm-up (lazy module load, cudaFuncSetAttribute) outside capture
+            self.plan.capture()
+        self.plan.replay(1)
         out = torch.empty(self.B, cfg.x_channels, self.Lout, device=eng.device)
         ops = OpList()
         ops.transpose(self.logits.ptr, _ptr(out), self.logits.ld, 0, self.B, cfg.x_channels, self.Lout, False)

@@ -259,13 +259,9 @@ class DDIMSampler(object):
 
             # ---- once per request -----------------------------------------------------------
             sess.set_timestep_table(time_range.copy())                      # row i = i-th loop iteration
-            if cfg_on:
-                ctx = torch.cat([unconditional_conditioning.to(dev), c.to(dev)])    # ddim.py:173
-                aud = [torch.cat([wi.to(dev)] * 2) for wi in list(w)[-model.cfg.unet.levels:]]
-            else:
-                ctx, aud = c, list(w)[-model.cfg.unet.levels:]
-            sess.set_context(ctx)
-            sess.set_audio(aud)
+            # ddim.py:170-174 concatenates [uc, c] and [w, w]; here the two halves are written straight into their rows
+            sess.set_context([unconditional_conditioning, c] if cfg_on else c)
+            sess.set_audio(list(w)[-model.cfg.unet.levels:], dup=cfg_on)
             coef = np.stack([np.asarray(self.ddim_alphas, dtype=np.float32), np.asarray(self.ddim_alphas_prev, dtype=np.float32),
                              np.asarray(self.ddim_sigmas, dtype=np.float32),
                              np.asarray(self.ddim_sqrt_one_minus_alphas, dtype=np.float32)], axis=1)

@@ -50,7 +50,14 @@ def test_unet_forward_lengthens_s4_state_like_reference(golden_dir):
     eps = m.model.forward(inp["x_T"].cuda(), torch.tensor([981, 1]).cuda(), inp["c"].cuda(), [w.cuda() for w in inp["w"]])
     gold = gc.load_golden(os.path.join(golden_dir, "unet_L96_from48.npz"))["eps"]
     assert rel_err(eps, gold) < 1e-4
-    assert m.engine.blob.meta["model.unet_model.input_blocks.2.1.s4_model.kernel.kernel.L"] == 96
+    key = "model.unet_model.input_blocks.2.1.s4_model.kernel.kernel.L"
+    assert m.engine.s4_L[key] == 96
+    # the lengthened C~ lives in THIS engine's device weights; the shared host blob (and its length record) is untouched, so a second
+    # engine built from the same blob lengthens again and reproduces the result instead of pairing the short C~ with the long L
+    assert m.engine.blob.meta[key] == 48
+    m2 = MugDiffusionB200(None, m.cfg, z_length=96, blob=m.engine.blob)
+    eps2 = m2.model.forward(inp["x_T"].cuda(), torch.tensor([981, 1]).cuda(), inp["c"].cuda(), [w.cuda() for w in inp["w"]])
+    assert rel_err(eps2, gold) < 1e-4 and m2.engine.s4_L[key] == 96
 
 
 def test_unet_forward_vs_oracle_other_batch():

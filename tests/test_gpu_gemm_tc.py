@@ -165,9 +165,9 @@ def test_upsample_as_two_parity_gemms(R, impl, B, L, C):
 
 
 @pytest.mark.parametrize("kind", ["linear", "conv3"])
-def test_tc_weight_multicast_clusters(R, kind):
-    """grids that oversubscribe the 148 SMs run as clusters of 2 (or 4, MUGD_TC_MC=4) tiles sharing the weight tile by TMA
-    multicast: same numbers as the fp64 reference"""
+def test_tc_oversubscribed_grid(R, kind):
+    """grids of several waves (more tiles than the 148 SMs, 256-wide tiles with the decoupled weight ring where N allows):
+    same numbers as the fp64 reference"""
     if kind == "linear":
         M, K, N = 296 * 128, 128, 256
         x, w, b = g("mcx", (M, K)), g("mcw", (N, K)) / math.sqrt(K), 0.1 * g("mcb", (N,))
@@ -184,3 +184,47 @@ def test_tc_weight_multicast_clusters(R, kind):
         out = torch.zeros(B * L, Cout).cuda()
         run_tc(R, view(xc), wp, Cout, Cin, view(out), taps=3, mode=L_.CONV_SAME, Lin=L, Lout=L)
         assert rel_err(ncl(out.cpu(), B), ref) < TOL
+
+
+@pytest.mark.parametrize("impl", [L_.GEMM_TC, L_.GEMM_SIMT], ids=["tc", "simt"])
+@pytest.mark.parametrize("B,L,C1,C2,Cout,split", [(2, 64, 512, 1536, 512, 0), (3, 128, 256, 768, 256, 0), (8, 512, 128, 384, 128, 0),
+                                                   (2, 12, 64, 96, 64, 0), (2, 64, 512, 1536, 512, 5)])
+def test_gemm_conv3_plus_skip_second_source(R, impl, B, L, C1, C2, Cout, split):
+    """conv3(t3) + skip_connection(x) of a TimestepResBlock (unet.py:187-193,237-239) as ONE GEMM: the 1x1 term runs as extra
+    k-steps on a second activation source; split-K ranges that straddle the two sources included"""
+    t3, x = g("d_t3", (B, C1, L)), g("d_x", (B, C2, L))
+    w3, w1 = g("d_w3", (Cout, C1, 3)) / math.sqrt(3 * C1), g("d_w1", (Cout, C2, 1)) / math.sqrt(C2)
+    b = 0.1 * g("d_b", (Cout,))
+    ref = F.conv1d(t3.double(), w3.double(), b.double(), padding=1) + F.conv1d(x.double(), w1.double())
+    wcat = torch.cat([w3.permute(0, 2, 1).reshape(Cout, 3 * C1), w1.reshape(Cout, C2)], dim=1).contiguous()
+    hi, lo = tf32_split(wcat)
+    wc, hc, lc, bc = wcat.cuda(), hi.cuda(), lo.cuda(), b.cuda()
+    tc_, xc = nlc(t3).cuda(), nlc(x).cuda()
+    out = torch.zeros(B * L, Cout).cuda()
+    ops = OpList()
+    ops.gemm(view(tc_), ptr(wc), Cout, C1, view(out), W_hi=ptr(hc), W_lo=ptr(lc), bias=ptr(bc), taps=3, mode=L_.CONV_SAME, Lin=L, Lout=L,
+             A2=view(xc), impl=impl, split_k=split)
+    R.run(ops)
+    e = rel_err(ncl(out.cpu(), B), ref)
+    print(f"conv3+skip impl={impl} B={B} L={L} rel_err={e:.2e}")
+    assert e < TOL
+
+
+@pytest.mark.parametrize("impl", [L_.GEMM_TC, L_.GEMM_SIMT], ids=["tc", "simt"])
+def test_gemm_ff_out_composed(R, impl):
+    """proj_out(ff.net.2(f) + h) + x (attention.py:57-65,194-199) as one GEMM over [f | h] with the composed weight [Wp Wf | Wp]"""
+    M, C = 1024, 256
+    f, h, x = g("c_f", (M, 4 * C)), g("c_h", (M, C)), g("c_x", (M, C))
+    wf, bf = g("c_wf", (C, 4 * C)) / math.sqrt(4 * C), 0.1 * g("c_bf", (C,))
+    wp, bp = g("c_wp", (C, C)) / math.sqrt(C), 0.1 * g("c_bp", (C,))
+    ref = F.linear(F.linear(f.double(), wf.double(), bf.double()) + h.double(), wp.double(), bp.double()) + x.double()
+    wcat = torch.cat([wp.double() @ wf.double(), wp.double()], dim=1).float().contiguous()
+    bcat = (wp.double() @ bf.double() + bp.double()).float()
+    hi, lo = tf32_split(wcat)
+    wc, hc, lc, bc = wcat.cuda(), hi.cuda(), lo.cuda(), bcat.cuda()
+    fc, hcc, xc = f.cuda(), h.cuda(), x.cuda()
+    out = torch.zeros(M, C).cuda()
+    ops = OpList()
+    ops.gemm(view(fc), ptr(wc), C, 4 * C, view(out), W_hi=ptr(hc), W_lo=ptr(lc), bias=ptr(bc), residual=view(xc), A2=view(hcc), impl=impl)
+    R.run(ops)
+    assert rel_err(out, ref) < TOL

@@ -183,7 +183,7 @@ def attn_ref(q, k, v, rel, cg, H, pos_max=64):
 def test_attention(R, B, H, D, Lq, Lk, impl):
     """both attention kernels (tensor-core 3xTF32 and the exact FFMA referee) against the fp64 formula; covers several key
     tiles, ragged last tiles (Lk % 16 != 0), Lq < one tile and the 21-token prompt context"""
-    R.lib.mugd_set_attention_impl(impl)
+    R.lib.mugd_set_attention_impl(R.handle, impl)
     C = H * D
     q, k, v = g("aq", (B, Lq, C)), g("ak", (B, Lk, C)), g("av", (B, Lk, C))
     rel, cg = 0.5 * g("ar", (129, H)), 1 + 0.1 * g("ac", (129, H))
@@ -198,7 +198,7 @@ def test_attention(R, B, H, D, Lq, Lk, impl):
     try:
         R.run(ops)
     finally:
-        R.lib.mugd_set_attention_impl(1)
+        R.lib.mugd_set_attention_impl(R.handle, 1)
     assert rel_err(out.view(B, Lq, C), ref) < 2e-5
 
 

@@ -114,8 +114,10 @@ def test_unet_plan_compiles_and_is_consistent(packed, Beff, Lz):
             g = o.u.gemm
             assert g.K % 16 == 0 and g.N % 4 == 0 and g.M % g.Lout == 0
     # the parity-split Upsample convs (CONV_TAPS) do 2/3 of the literal FLOPs: count them at the reference's cost
-    flops = sum(2.0 * o.u.gemm.M * o.u.gemm.N * o.u.gemm.K * o.u.gemm.taps * (1.5 if o.u.gemm.conv_mode == L_.CONV_TAPS else 1.0)
+    flops = sum(2.0 * o.u.gemm.M * o.u.gemm.N * (o.u.gemm.K * o.u.gemm.taps * (1.5 if o.u.gemm.conv_mode == L_.CONV_TAPS else 1.0) + o.u.gemm.K2)
                 for o in ops if o.kind == L_.OP_GEMM)
+    # the 16 skip_connection convs and the 16 proj_out convs ride as second sources of other GEMMs
+    assert sum(1 for o in ops if o.kind == L_.OP_GEMM and o.u.gemm.K2 > 0) == 32
     if Lz == 512:
         # GEMM-class work per sample-eval (21.80 GFLOP) minus the hoisted emb / ctx-KV projections
         assert abs(flops / Beff / 1e9 - 21.8) < 0.3
@@ -163,7 +165,7 @@ def test_tensor_core_planner_invariants(packed, Beff, Lz):
             assert sp.value == 0 and ws.value == 0
             continue
         n_tc += 1
-        ksteps = g.taps * (g.K // 32)
+        ksteps = g.taps * (g.K // 32) + g.K2 // 32
         assert 1 <= sp.value <= ksteps and 1 <= nt.value <= 4096
         if sp.value > 1:
             n_split += 1
@@ -177,7 +179,7 @@ def test_tensor_core_planner_invariants(packed, Beff, Lz):
         sp2, nt2 = C.c_int32(), C.c_int32()
         lib.mugd_gemm_tc_query(None, C.byref(g), 64, None, C.byref(sp2), None, C.byref(nt2))
         assert sp2.value == 1 or nt2.value * sp2.value <= 2 * 64
-    assert n_tc >= 220
+    assert n_tc >= 190          # 228 - 32 (fused second-source GEMMs) + 1
     if Beff <= 8:
         assert n_split > 100                                     # small batches underfill 148 SMs: most GEMMs are split
     if Beff == 64:
