@@ -216,10 +216,10 @@ def run_reference(args, wl, name):
     line = dict(metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=1000.0 / v, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
                 impl="reference",
-                config=config_of(name, wl, 1,
-                                 note="CPU oracle port of the reference PyTorch path (oracle/mug_oracle.py, bit-identical to the reference on "
-                                      "tests/golden); S4 kernels regenerated every eval like the reference.  One host runs ONE per-GPU batch: at "
-                                      "--gpus N > 1 only rank 0 measures, so the driver's ratio compares N GPUs with one CPU host"),
+                config=config_of(name, wl, args.gpus),        # identical keys and values to the B200 arm's `config`
+                info=dict(note="CPU oracle port of the reference PyTorch path (oracle/mug_oracle.py, bit-identical to the reference on "
+                               "tests/golden); S4 kernels regenerated every eval like the reference.  One host runs ONE per-GPU batch: at "
+                               "--gpus N > 1 only rank 0 measures one per-GPU batch, so the driver's ratio compares N GPUs with one CPU host"),
                 cpu_baseline=cpu_baseline_dict(r, args.steps, args.warmup),
                 e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line))
@@ -546,9 +546,10 @@ def main():
         Beff = m["Beff"]
         line = dict(metric=METRIC, value=m["value"], unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                     ms_per_step=m["ms_per_step"], higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-                    config=config_of(name, wl, world, gemm_impl=args.gemm, parallelism=f"replica-sharded batch x{world}",
-                                     l2="working set exceeds L2: ~0.8 GB of pre-split fp32 weights are streamed every step",
-                                     gflop_per_step=Beff * GFLOP_PER_EVAL.get(L, 0.0), outputs_finite=m["finite"]),
+                    config=config_of(name, wl, world),
+                    info=dict(gemm_impl=args.gemm, parallelism=f"replica-sharded batch x{world}",
+                              l2="working set exceeds L2: ~0.8 GB of pre-split fp32 weights are streamed every step",
+                              gflop_per_step=Beff * GFLOP_PER_EVAL.get(L, 0.0), outputs_finite=m["finite"]),
                     roofline=m["roofline"], cpu_baseline=cpu, e2e=m["e2e"], secondary=secondary,
                     gpu_launches=m["launches_per_step"] * args.steps, launches_per_step=m["launches_per_step"], clocks=m["clocks"])
         print(json.dumps(line))
