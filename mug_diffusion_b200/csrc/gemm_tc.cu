@@ -49,15 +49,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 }
 
-// split-K second pass: one thread per (row, 4-column group); fully parallel over the GPU and L2-resident.
+// split-K second pass: fully parallel over the GPU and L2-resident (see tc_reduce_rows).
 template <int BN>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(TC_THREADS)
 gemm_tc_reduce_kernel(const __grid_constant__ TcParams p) {
     pdl_wait();
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long total = (long long)p.gx * p.gy * TC_BM * (BN / 4);
-    if (idx >= total) return;
-    tc_reduce_item<BN>(p, idx);
+    tc_reduce_block<BN>(p, blockIdx.x);
 }
 
 #ifdef MUGD_TC_TIMELINE
@@ -100,6 +97,27 @@ bool gemm_tc_supported(const mugd_gemm& g) {
     if (g.lda % 4 != 0 || !aligned16(g.A) || !aligned16(g.W_hi) || !aligned16(g.W_lo)) return false;
     if (g.K2 > 0 && (!g.A2 || g.lda2 % 4 != 0 || !aligned16(g.A2))) return false;
     return true;
+}
+
+// statistics sinks and the folded LayerNorm exist on the tensor-core path only
+static int tc_validate_fusions(const mugd_gemm& g) {
+    const bool sinks = g.sink[0].kind != 0 || g.sink[1].kind != 0;
+    if (sinks) {
+        MUGD_REQUIRE(g.act == MUGD_ACT_NONE && g.gate == MUGD_GATE_NONE && !g.ln_stats, "gemm: statistics sinks need act == gate == NONE and no folded LayerNorm");
+        for (int k = 0; k < 2; ++k) {
+            const mugd_stat_sink& s = g.sink[k];
+            MUGD_REQUIRE(s.kind >= 0 && s.kind <= 2, "gemm: sink kind %d", s.kind);
+            if (s.kind) MUGD_REQUIRE(s.buf && (reinterpret_cast<uintptr_t>(s.buf) & 7u) == 0, "gemm: sink buffer");
+            if (s.kind == 1) MUGD_REQUIRE(s.cg > 0 && s.cg % 4 == 0 && s.col0 % 4 == 0 && s.G > 0 && s.col0 + g.N <= s.cg * s.G,
+                                          "gemm: group sink geometry (col0=%d cg=%d G=%d N=%d)", s.col0, s.cg, s.G, g.N);
+        }
+    }
+    if (g.ln_stats) {
+        MUGD_REQUIRE(g.ln_colsum && aligned16(g.ln_colsum) && g.taps == 1 && g.K2 == 0 && g.act == MUGD_ACT_NONE &&
+                         (g.gate == MUGD_GATE_NONE || g.gate == MUGD_GATE_GEGLU) && !g.rowvec,
+                     "gemm: folded LayerNorm needs a single-source Linear with act NONE and gate NONE/GEGLU");
+    }
+    return MUGD_OK;
 }
 
 TcGeometry tc_geometry(const mugd_gemm& g, int sm_count, int forced_split) {
@@ -156,6 +174,10 @@ TcGeometry tc_geometry(const mugd_gemm& g, int sm_count, int forced_split) {
 
 int tc_plan(const DeviceInfo& dev, const mugd_gemm& g, TcPlanned* out) {
     MUGD_REQUIRE(gemm_tc_supported(g), "gemm_tc: unsupported shape/operands");
+    {
+        const int rc = tc_validate_fusions(g);
+        if (rc != MUGD_OK) return rc;
+    }
     EncodeTiledFn enc = get_encode();
     MUGD_REQUIRE(enc != nullptr, "gemm_tc: cuTensorMapEncodeTiled not available from the driver");
     const TcGeometry t = tc_geometry(g, dev.sm_count, g.split_k);
@@ -238,10 +260,8 @@ static int tc_launch(const TcPlanned& pl, cudaStream_t st) {
     const TcParams& p = pl.p;
     MUGD_CHECK_CUDA(launch_k(gemm_tc_kernel<BN>, dim3(p.gx, p.gy, p.splits), dim3(TC_THREADS), TcSmem<BN>::TOTAL, st, pl.maps[0], pl.maps[1],
                              pl.maps[2], pl.maps[3], pl.maps[4], pl.maps[5], p));
-    if (p.splits > 1) {
-        const long long total = (long long)p.gx * p.gy * TC_BM * (BN / 4);
-        MUGD_CHECK_CUDA(launch_k(gemm_tc_reduce_kernel<BN>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, p));
-    }
+    if (p.splits > 1)
+        MUGD_CHECK_CUDA(launch_k(gemm_tc_reduce_kernel<BN>, dim3((unsigned)(p.gx * p.gy * TcReduceGeom<BN>::BPT)), dim3(TC_THREADS), 0, st, p));
     return MUGD_OK;
 }
 

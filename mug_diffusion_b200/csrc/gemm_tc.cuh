@@ -185,15 +185,72 @@ struct TcSmem {
     static constexpr int TMEM_NEED = BN + SA * 64;         // accumulator + per slot 32 columns a_hi + 32 columns a_lo
     static constexpr int TMEM_COLS = TMEM_NEED <= 64 ? 64 : (TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512));
     static_assert(TMEM_NEED <= 512, "tensor memory budget");
-    static_assert(128u * (BN + 4) * 4u <= TILE_BYTES, "the staged accumulator tile must fit the pipeline buffers");
+    static_assert(128u * (BN + 4) * 4u + 1024u <= TILE_BYTES, "the staged accumulator tile + row statistics must fit the pipeline buffers");
 };
+
+// ---- statistics sinks (mugd_stat_sink): moments of the OUTPUT for the norm that follows, accumulated while it is written ----
+// Group moments: a thread keeps (sum, sum of squares) of the float4s it stores -- its column quad, hence its group, is fixed for
+// the whole tile -- and flushes them with two fp64 reductions into global memory whenever the sample changes and at the end.
+struct TcGroupAcc {
+    double s, ss;
+    int b;                                   // sample the running sums belong to (-1: empty)
+    __device__ __forceinline__ void reset() { s = 0.0; ss = 0.0; b = -1; }
+    __device__ __forceinline__ void flush(const mugd_stat_sink& k, int grp) {
+        if (b >= 0) {
+            double* d = k.buf + ((int64_t)b * k.G + grp) * 2;
+            atomicAdd(d, s);
+            atomicAdd(d + 1, ss);
+        }
+        s = 0.0; ss = 0.0;
+    }
+    __device__ __forceinline__ void add(const mugd_stat_sink& k, int grp, int bb, float4 v) {
+        if (bb != b) { flush(k, grp); b = bb; }
+        s += (double)((v.x + v.y) + (v.z + v.w));
+        ss += (double)((v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w));
+    }
+};
+// Row moments (LayerNorm of the consumer): the SEG lanes that hold one output row of this tile reduce with shuffles, the segment
+// leader adds the tile's share of the row to the row's two doubles.  Every lane of the warp must call it (inactive: v = 0, m < 0).
+template <int SEG>
+__device__ __forceinline__ void tc_row_sink(const mugd_stat_sink& k, int m, float4 v) {
+    double s = (double)((v.x + v.y) + (v.z + v.w));
+    double ss = (double)((v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w));
+#pragma unroll
+    for (int o = SEG / 2; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    }
+    if ((threadIdx.x & (SEG - 1)) == 0 && m >= 0) {
+        atomicAdd(k.buf + (int64_t)m * 2, s);
+        atomicAdd(k.buf + (int64_t)m * 2 + 1, ss);
+    }
+}
+// mean / rstd of a row from its two moments (LayerNorm folded into the GEMM, mugd_gemm.ln_stats)
+__device__ __forceinline__ float2 tc_ln_row(const double* st, int m, int K, float eps) {
+    const double s = st[(int64_t)m * 2], ss = st[(int64_t)m * 2 + 1];
+    const double mean = s / (double)K;
+    double var = ss / (double)K - mean * mean;
+    if (var < 0.0) var = 0.0;
+    return make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+}
+
+// epilogue modes of a tile / reduce pass
+constexpr int TC_EPI_PLAIN = 0, TC_EPI_SINK = 1 /* act == gate == NONE + statistics sinks */, TC_EPI_LN = 2 /* LayerNorm folded in */;
 
 // Fused epilogue math on 4 consecutive accumulator columns.  ACT / GATE are compile-time so that the compiler
 // cannot if-convert the branches into "compute SiLU, GELU and both gates for every element, then select"
 // (which it did, costing ~4 us per tile); callers dispatch once per tile on the (uniform) act/gate values.
-template <int ACT, int GATE>
-__device__ __forceinline__ void tc_finish4(const mugd_gemm& g, float4 acc, float4 bia, float4 rvv, float4 res, int m, int nn) {
-    float x[4] = {acc.x + bia.x + rvv.x, acc.y + bia.y + rvv.y, acc.z + bia.z + rvv.z, acc.w + bia.w + rvv.w};
+// LNF: acc is A W'^T of the un-normalised rows; (acc - mean*colsum)*rstd is the product with the LayerNorm'd rows.
+// Returns the stored float4 (GATE_NONE) for the statistics sinks.
+template <int ACT, int GATE, bool LNF>
+__device__ __forceinline__ float4 tc_finish4(const mugd_gemm& g, float4 acc, float4 bia, float4 rvv, float4 res, float4 cs, float2 ln, int m, int nn) {
+    float x[4];
+    if constexpr (LNF) {
+        x[0] = (acc.x - ln.x * cs.x) * ln.y + bia.x + rvv.x; x[1] = (acc.y - ln.x * cs.y) * ln.y + bia.y + rvv.y;
+        x[2] = (acc.z - ln.x * cs.z) * ln.y + bia.z + rvv.z; x[3] = (acc.w - ln.x * cs.w) * ln.y + bia.w + rvv.w;
+    } else {
+        x[0] = acc.x + bia.x + rvv.x; x[1] = acc.y + bia.y + rvv.y; x[2] = acc.z + bia.z + rvv.z; x[3] = acc.w + bia.w + rvv.w;
+    }
     if constexpr (ACT == MUGD_ACT_SILU) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) x[j] = silu_f(x[j]);
@@ -202,7 +259,9 @@ __device__ __forceinline__ void tc_finish4(const mugd_gemm& g, float4 acc, float
         for (int j = 0; j < 4; ++j) x[j] = gelu_f(x[j]);
     }
     if constexpr (GATE == MUGD_GATE_NONE) {
-        st_f4(g.C + (int64_t)m * g.ldc + nn, make_float4(x[0] + res.x, x[1] + res.y, x[2] + res.z, x[3] + res.w));
+        const float4 o = make_float4(x[0] + res.x, x[1] + res.y, x[2] + res.z, x[3] + res.w);
+        st_f4(g.C + (int64_t)m * g.ldc + nn, o);
+        return o;
     } else {
         float o0, o1;
         if constexpr (GATE == MUGD_GATE_GEGLU) { o0 = x[0] * gelu_f(x[1]); o1 = x[2] * gelu_f(x[3]); }
@@ -213,19 +272,32 @@ __device__ __forceinline__ void tc_finish4(const mugd_gemm& g, float4 acc, float
             o0 += rr.x; o1 += rr.y;
         }
         *reinterpret_cast<float2*>(g.C + (int64_t)m * g.ldc + no) = make_float2(o0, o1);
+        return make_float4(o0, o1, 0.f, 0.f);
     }
 }
 
 // phase 2 of the epilogue for one CTA: read the staged accumulator tile from shared memory (row pitch BN+4) and
 // finish it with coalesced global traffic; U float4 per thread in flight, every global load issued before any use.
-template <int BN, int ACT, int GATE>
-__device__ __forceinline__ void tc_store_tile(const mugd_gemm& g, uint32_t stage, int m_base, int n0, int rows_valid, const float* rowvec) {
+// MODE = TC_EPI_LN reads the (mean, rstd) of tile row r from shared memory at rowstat + 8*r (written in phase 1).
+template <int BN, int ACT, int GATE, int MODE>
+__device__ __forceinline__ void tc_store_tile(const mugd_gemm& g, uint32_t stage, int m_base, int n0, int rows_valid, const float* rowvec,
+                                              uint32_t rowstat) {
     constexpr int SP = BN + 4;
     constexpr int C4 = BN / 4;
     constexpr int U = 8;
+    constexpr int SEG = C4 < 32 ? C4 : 32;
+    TcGroupAcc ga[2];
+    int grp[2] = {0, 0};
+    if constexpr (MODE == TC_EPI_SINK) {
+        ga[0].reset(); ga[1].reset();
+        const int nn = n0 + ((int)threadIdx.x % C4) * 4;          // this thread's column quad is the same for every row it visits
+#pragma unroll
+        for (int k = 0; k < 2; ++k) grp[k] = g.sink[k].kind == 1 ? (g.sink[k].col0 + nn) / g.sink[k].cg : 0;
+    }
 #pragma unroll 1
     for (int i0 = 0; i0 < TC_BM * C4; i0 += TC_THREADS * U) {
-        float4 acc[U], bia[U], rvv[U], res[U];
+        float4 acc[U], bia[U], rvv[U], res[U], cs[U];
+        float2 ln[U];
         bool ok[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -235,40 +307,52 @@ __device__ __forceinline__ void tc_store_tile(const mugd_gemm& g, uint32_t stage
                          : "r"(stage + (uint32_t)(row * SP + c4 * 4) * 4u));
             const int m = m_base + row, nn = n0 + c4 * 4;
             ok[u] = row < rows_valid && m < g.M && nn < g.N;
-            bia[u] = rvv[u] = res[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            bia[u] = rvv[u] = res[u] = cs[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            ln[u] = make_float2(0.f, 1.f);
             if (ok[u]) {
                 if (g.bias) bia[u] = ld_f4(g.bias + nn);
                 if (rowvec) rvv[u] = ld_f4(rowvec + (int64_t)(m / g.Lout) * g.rowvec_b_stride + nn);
                 if (GATE == MUGD_GATE_NONE && g.residual) res[u] = ld_f4(g.residual + (int64_t)m * g.ldr + nn);
+                if constexpr (MODE == TC_EPI_LN) {
+                    cs[u] = ld_f4(g.ln_colsum + nn);
+                    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(ln[u].x), "=f"(ln[u].y) : "r"(rowstat + (uint32_t)row * 8u));
+                }
             }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            if (!ok[u]) continue;
             const int idx = i0 + u * TC_THREADS + (int)threadIdx.x;
             const int row = idx / C4, c4 = idx - row * C4;
-            tc_finish4<ACT, GATE>(g, acc[u], bia[u], rvv[u], res[u], m_base + row, n0 + c4 * 4);
+            const int m = m_base + row;
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok[u]) o = tc_finish4<ACT, GATE, MODE == TC_EPI_LN>(g, acc[u], bia[u], rvv[u], res[u], cs[u], ln[u], m, n0 + c4 * 4);
+            if constexpr (MODE == TC_EPI_SINK) {
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    if (g.sink[k].kind == 1) { if (ok[u]) ga[k].add(g.sink[k], grp[k], m / g.Lout, o); }
+                    else if (g.sink[k].kind == 2) tc_row_sink<SEG>(g.sink[k], ok[u] ? m : -1, o);     // (warp-uniform branch)
+                }
+            }
         }
     }
-}
-
-// single float4 variant used by the split-K reduce
-template <int ACT, int GATE>
-__device__ __forceinline__ void tc_epi4(const mugd_gemm& g, float4 acc, int m, int nn, const float* rowvec) {
-    float4 bia = make_float4(0.f, 0.f, 0.f, 0.f), rvv = bia, res = bia;
-    if (g.bias) bia = ld_f4(g.bias + nn);
-    if (rowvec) rvv = ld_f4(rowvec + (int64_t)(m / g.Lout) * g.rowvec_b_stride + nn);
-    if (GATE == MUGD_GATE_NONE && g.residual) res = ld_f4(g.residual + (int64_t)m * g.ldr + nn);
-    tc_finish4<ACT, GATE>(g, acc, bia, rvv, res, m, nn);
+    if constexpr (MODE == TC_EPI_SINK) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+            if (g.sink[k].kind == 1) ga[k].flush(g.sink[k], grp[k]);
+    }
 }
 
 #define TC_DISPATCH_EPI(g, CALL)                                                                      \
     do {                                                                                              \
-        if ((g).gate == MUGD_GATE_GEGLU) { CALL(MUGD_ACT_NONE, MUGD_GATE_GEGLU); }                    \
-        else if ((g).gate == MUGD_GATE_GLU) { CALL(MUGD_ACT_NONE, MUGD_GATE_GLU); }                   \
-        else if ((g).act == MUGD_ACT_SILU) { CALL(MUGD_ACT_SILU, MUGD_GATE_NONE); }                   \
-        else if ((g).act == MUGD_ACT_GELU) { CALL(MUGD_ACT_GELU, MUGD_GATE_NONE); }                   \
-        else { CALL(MUGD_ACT_NONE, MUGD_GATE_NONE); }                                                 \
+        if ((g).ln_stats) {                                                                           \
+            if ((g).gate == MUGD_GATE_GEGLU) { CALL(MUGD_ACT_NONE, MUGD_GATE_GEGLU, TC_EPI_LN); }     \
+            else { CALL(MUGD_ACT_NONE, MUGD_GATE_NONE, TC_EPI_LN); }                                  \
+        } else if ((g).sink[0].kind | (g).sink[1].kind) { CALL(MUGD_ACT_NONE, MUGD_GATE_NONE, TC_EPI_SINK); } \
+        else if ((g).gate == MUGD_GATE_GEGLU) { CALL(MUGD_ACT_NONE, MUGD_GATE_GEGLU, TC_EPI_PLAIN); } \
+        else if ((g).gate == MUGD_GATE_GLU) { CALL(MUGD_ACT_NONE, MUGD_GATE_GLU, TC_EPI_PLAIN); }     \
+        else if ((g).act == MUGD_ACT_SILU) { CALL(MUGD_ACT_SILU, MUGD_GATE_NONE, TC_EPI_PLAIN); }     \
+        else if ((g).act == MUGD_ACT_GELU) { CALL(MUGD_ACT_GELU, MUGD_GATE_NONE, TC_EPI_PLAIN); }     \
+        else { CALL(MUGD_ACT_NONE, MUGD_GATE_NONE, TC_EPI_PLAIN); }                                   \
     } while (0)
 
 // rows of output tile `by`
@@ -482,6 +566,12 @@ __device__ __forceinline__ void gemm_tc_tile(const CUtensorMap* tmA, const CUten
             }
             TC_STAMP(threadIdx.x == 128 && i < 24, 8 + i * 6 + 2);
         }
+        // LayerNorm folded into this GEMM: the moments of this thread's row (written by the previous kernels) -> mean / rstd
+        float2 lnrow = make_float2(0.f, 1.f);
+        if (g.ln_stats) {
+            const int rr = (warp & 3) * 32 + lane;
+            if (rr < rows_valid && m_base + rr < g.M) lnrow = tc_ln_row(g.ln_stats, m_base + rr, g.K, g.ln_eps);
+        }
         // ===================================== epilogue, phase 1 ================================
         mbar_wait(B.accum(), 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -501,6 +591,8 @@ __device__ __forceinline__ void gemm_tc_tile(const CUtensorMap* tmA, const CUten
                 asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(base + (uint32_t)(r * SP + c0 + j * 4) * 4u), "f"(v[j * 4]),
                              "f"(v[j * 4 + 1]), "f"(v[j * 4 + 2]), "f"(v[j * 4 + 3]) : "memory");
         }
+        if (g.ln_stats)      // (mean, rstd) of tile row r for phase 2, in the last KB of the (now idle) pipeline buffers
+            asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(base + S::TILE_BYTES - 1024u + (uint32_t)r * 8u), "f"(lnrow.x), "f"(lnrow.y) : "memory");
         TC_STAMP(threadIdx.x == 128, 3);
     }
     // ---- phase 2 (all 8 warps): consecutive threads take consecutive float4 of a row -> coalesced global traffic.
@@ -530,7 +622,7 @@ __device__ __forceinline__ void gemm_tc_tile(const CUtensorMap* tmA, const CUten
                 for (int u = 0; u < U; ++u) st_f4(wsp + (i0 + u * TC_THREADS + (int)threadIdx.x) * 4, acc[u]);   // [row][BN] dense
             }
         } else {
-#define TC_CALL_STORE(A_, G_) tc_store_tile<BN, A_, G_>(g, base, m_base, n0, rows_valid, rowvec)
+#define TC_CALL_STORE(A_, G_, M_) tc_store_tile<BN, A_, G_, M_>(g, base, m_base, n0, rows_valid, rowvec, base + S::TILE_BYTES - 1024u)
             TC_DISPATCH_EPI(g, TC_CALL_STORE);
 #undef TC_CALL_STORE
         }
@@ -539,33 +631,98 @@ __device__ __forceinline__ void gemm_tc_tile(const CUtensorMap* tmA, const CUten
 #undef TC_STAMP
 }
 
-// split-K second pass, one float4 of the output per call: sum the partial tiles in fixed split order (deterministic) and run
-// the fused epilogue.  idx enumerates (tile, row, 4-column group) over the whole tile grid.
+// split-K second pass.  One call = one thread's share of reduce block `blk`: 4 output rows x one 4-column group.  A block of 256
+// threads covers RPB = 4 * (256 / (BN/4)) rows of one tile; the partial tiles are summed in fixed split order (deterministic), four
+// independent load chains per thread, then the fused epilogue (+ statistics sinks / folded LayerNorm) runs.
 template <int BN>
-__device__ __forceinline__ void tc_reduce_item(const TcParams& p, long long idx) {
+struct TcReduceGeom {
+    static constexpr int C4 = BN / 4;
+    static constexpr int RPP = TC_THREADS / C4;       // rows per pass
+    static constexpr int RPB = 4 * RPP;               // rows per block
+    static constexpr int BPT = TC_BM / RPB;           // blocks per tile
+    static_assert(TC_BM % RPB == 0, "reduce geometry");
+};
+
+template <int BN, int ACT, int GATE, int MODE>
+__device__ __forceinline__ void tc_reduce_rows(const TcParams& p, int tile_lin, int rb, const float* rowvec) {
+    using G = TcReduceGeom<BN>;
+    constexpr int C4 = G::C4;
+    constexpr int SEG = C4 < 32 ? C4 : 32;
     const mugd_gemm& g = p.g;
-    constexpr int C4 = BN / 4;
-    const int c4 = (int)(idx % C4);
-    const int r = (int)((idx / C4) % TC_BM);
-    const int tile_lin = (int)(idx / ((long long)C4 * TC_BM));
     const int bx = tile_lin % p.gx, by = tile_lin / p.gx;
     int b_base, l_base, rows_valid;
     tc_tile_rows(p, by, b_base, l_base, rows_valid);
-    const int m = b_base * p.Lrows + l_base + r;
+    const int m_base = b_base * p.Lrows + l_base;
+    const int c4 = (int)threadIdx.x % C4;
+    const int r0 = rb * G::RPB + (int)threadIdx.x / C4;
     const int n = bx * BN + c4 * 4;
-    if (r >= rows_valid || m >= g.M || n >= g.N) return;
-    const float* src = p.ws + ((long long)tile_lin * p.splits) * (TC_BM * BN) + (long long)r * BN + c4 * 4;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-    for (int z = 0; z < p.splits; ++z) {                                   // fixed order -> deterministic
-        const float4 t4 = __ldcg(reinterpret_cast<const float4*>(src + (long long)z * (TC_BM * BN)));
-        acc.x += t4.x; acc.y += t4.y; acc.z += t4.z; acc.w += t4.w;
+    const float* src = p.ws + ((long long)tile_lin * p.splits) * (TC_BM * BN) + c4 * 4;
+    float4 acc[4];
+    bool ok[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int r = r0 + j * G::RPP;
+        ok[j] = r < rows_valid && m_base + r < g.M && n < g.N;
+        acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
+#pragma unroll 2
+    for (int z = 0; z < p.splits; ++z) {                                   // fixed order -> deterministic
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (ok[j]) {
+                const float4 t4 = __ldcg(reinterpret_cast<const float4*>(src + (long long)z * (TC_BM * BN) + (long long)(r0 + j * G::RPP) * BN));
+                acc[j].x += t4.x; acc[j].y += t4.y; acc[j].z += t4.z; acc[j].w += t4.w;
+            }
+        }
+    }
+    TcGroupAcc ga[2];
+    int grp[2] = {0, 0};
+    if constexpr (MODE == TC_EPI_SINK) {
+        ga[0].reset(); ga[1].reset();
+#pragma unroll
+        for (int k = 0; k < 2; ++k) grp[k] = g.sink[k].kind == 1 ? (g.sink[k].col0 + n) / g.sink[k].cg : 0;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int m = m_base + r0 + j * G::RPP;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok[j]) {
+            float4 bia = make_float4(0.f, 0.f, 0.f, 0.f), rvv = bia, res = bia, cs = bia;
+            float2 ln = make_float2(0.f, 1.f);
+            if (g.bias) bia = ld_f4(g.bias + n);
+            if (rowvec) rvv = ld_f4(rowvec + (int64_t)(m / g.Lout) * g.rowvec_b_stride + n);
+            if (GATE == MUGD_GATE_NONE && g.residual) res = ld_f4(g.residual + (int64_t)m * g.ldr + n);
+            if constexpr (MODE == TC_EPI_LN) {
+                cs = ld_f4(g.ln_colsum + n);
+                ln = tc_ln_row(g.ln_stats, m, g.K, g.ln_eps);
+            }
+            o = tc_finish4<ACT, GATE, MODE == TC_EPI_LN>(g, acc[j], bia, rvv, res, cs, ln, m, n);
+        }
+        if constexpr (MODE == TC_EPI_SINK) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                if (g.sink[k].kind == 1) { if (ok[j]) ga[k].add(g.sink[k], grp[k], m / g.Lout, o); }
+                else if (g.sink[k].kind == 2) tc_row_sink<SEG>(g.sink[k], ok[j] ? m : -1, o);
+            }
+        }
+    }
+    if constexpr (MODE == TC_EPI_SINK) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+            if (g.sink[k].kind == 1) ga[k].flush(g.sink[k], grp[k]);
+    }
+}
+
+template <int BN>
+__device__ __forceinline__ void tc_reduce_block(const TcParams& p, int blk) {
+    using G = TcReduceGeom<BN>;
+    const mugd_gemm& g = p.g;
     const int step = g.step ? *g.step : 0;
     const float* rowvec = g.rowvec ? g.rowvec + (int64_t)step * g.rowvec_step_stride : nullptr;
-#define TC_CALL_EPI(A_, G_) tc_epi4<A_, G_>(g, acc, m, n, rowvec)
-    TC_DISPATCH_EPI(g, TC_CALL_EPI);
-#undef TC_CALL_EPI
+    const int tile_lin = blk / G::BPT, rb = blk % G::BPT;
+#define TC_CALL_RED(A_, G_, M_) tc_reduce_rows<BN, A_, G_, M_>(p, tile_lin, rb, rowvec)
+    TC_DISPATCH_EPI(g, TC_CALL_RED);
+#undef TC_CALL_RED
 }
 #endif  // __CUDACC__
 
