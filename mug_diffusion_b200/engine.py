@@ -91,7 +91,7 @@ class OpList:
              gate: int = L_.GATE_NONE, residual: Optional[View] = None, rowvec: int = 0,
              rowvec_b_stride: int = 0, rowvec_step_stride: int = 0, step: int = 0, impl: int = L_.GEMM_AUTO,
              W_hi: int = 0, W_lo: int = 0, split_k: int = 0, tap_shift: int = 0, dilation: int = 1, tag: int = 0,
-             A2: Optional[View] = None):
+             A2: Optional[View] = None, ln: Optional[Tuple[int, int, float]] = None) -> int:
         g = L_.Gemm()
         M = out.rows
         g.A, g.lda = A.ptr, A.ld
@@ -114,19 +114,46 @@ class OpList:
         g.Lout = Lout or M
         g.Lin = Lin or g.Lout
         g.act, g.gate, g.impl = act, gate, impl
+        if ln is not None:                     # LayerNorm folded in: (row moments of A, column sums of the gamma-scaled weight, eps)
+            g.ln_stats, g.ln_colsum, g.ln_eps = ln[0], ln[1], float(ln[2])
         nout = N // 2 if gate else N
         assert out.cols == nout, (out.cols, nout)
         assert A.cols == K, (A.cols, K)
         self.add(L_.OP_GEMM, g, tag)
+        return len(self.ops) - 1
 
-    def groupnorm(self, x: View, y: View, gamma: int, beta: int, B: int, Lrows: int, G: int, silu: bool, tag: int = 0):
+    def sink_capable(self, i: int) -> bool:
+        """can op i carry one more statistics sink?  (tensor-core GEMM with a plain epilogue and a free slot)"""
+        op = self.ops[i]
+        if op.kind != L_.OP_GEMM:
+            return False
+        g = op.u.gemm
+        tc = bool(g.W_hi) and g.K % 32 == 0 and g.K2 % 32 == 0 and g.N >= 64 and g.impl != L_.GEMM_SIMT and \
+            g.conv_mode != L_.CONV_UP and not (g.conv_mode == L_.CONV_DOWN and g.K2)
+        return tc and g.act == L_.ACT_NONE and g.gate == L_.GATE_NONE and not g.ln_stats and any(g.sink[k].kind == 0 for k in range(2))
+
+    def add_sink(self, i: int, kind: int, buf: int, col0: int = 0, cg: int = 0, G: int = 0):
+        g = self.ops[i].u.gemm
+        k = 0 if g.sink[0].kind == 0 else 1
+        assert g.sink[k].kind == 0
+        g.sink[k].buf, g.sink[k].kind, g.sink[k].col0, g.sink[k].cg, g.sink[k].G = buf, kind, col0, cg, G
+
+    def groupnorm(self, x: View, y: Optional[View], gamma: int, beta: int, B: int, Lrows: int, G: int, silu: bool, tag: int = 0,
+                  stats: int = 0, stats_col0: int = 0, stats_cg: int = 0, stats_G: int = 0) -> int:
+        """stats: [B][G][2] fp64 moments filled by the producers of x (single-pass apply); y None = accumulate x's moments only"""
         d = L_.GroupNorm()
-        d.x, d.ldx, d.y, d.ldy = x.ptr, x.ld, y.ptr, y.ld
-        d.gamma, d.beta = gamma, beta
+        d.x, d.ldx = x.ptr, x.ld
+        if y is not None:
+            d.y, d.ldy = y.ptr, y.ld
+            assert y.cols == x.cols
+        d.gamma, d.beta = gamma or None, beta or None
         d.B, d.L, d.C, d.G = B, Lrows, x.cols, G
         d.eps, d.silu = GN_EPS, int(silu)
-        assert x.rows == B * Lrows and y.cols == x.cols
+        if stats:
+            d.stats, d.stats_col0, d.stats_cg, d.stats_G = stats, stats_col0, stats_cg or x.cols // G, stats_G or G
+        assert x.rows == B * Lrows
         self.add(L_.OP_GROUPNORM, d, tag)
+        return len(self.ops) - 1
 
     def layernorm(self, x: View, y: View, gamma: int, beta: int, tag: int = 0):
         d = L_.LayerNorm()
@@ -134,6 +161,7 @@ class OpList:
         d.gamma, d.beta = gamma, beta
         d.rows, d.C, d.eps = x.rows, x.cols, LN_EPS
         self.add(L_.OP_LAYERNORM, d, tag)
+        return len(self.ops) - 1
 
     def attention(self, q: View, k: View, v: View, o: View, relpos: int, cgain: int, B: int, H: int, Lq: int,
                   Lk: int, pos_max: int, tag: int = 0):
@@ -168,14 +196,16 @@ def emit_upsample_conv(ops: "OpList", blob: WeightBlob, wfn, prefix: str, x: Vie
     """Upsample (nearest x2) + conv3 (models.py:66-70).  With the parity-split weights of the packer this is two 2-tap
     GEMMs over the Lin input rows writing the even / odd output rows (row stride 2*ld) -- 2/3 of the FLOPs of the
     literal form and eligible for the tensor-core kernel; otherwise the generic MUGD_CONV_UP addressing is used."""
+    idx = []
     if (prefix + "conv.up_even.weight") in blob.entries:
         for parity, name, shift in ((0, "conv.up_even.weight", -1), (1, "conv.up_odd.weight", 0)):
             dst = View(out.ptr + 4 * parity * out.ld, 2 * out.ld, x.rows, out.cols)
-            ops.gemm(x, wfn(prefix + name), cout, cin, dst, bias=wfn(prefix + "conv.bias"), taps=2, mode=L_.CONV_TAPS,
-                     Lin=Lin, Lout=Lin, tap_shift=shift, tag=tag)
+            idx.append(ops.gemm(x, wfn(prefix + name), cout, cin, dst, bias=wfn(prefix + "conv.bias"), taps=2, mode=L_.CONV_TAPS,
+                                Lin=Lin, Lout=Lin, tap_shift=shift, tag=tag))
     else:
-        ops.gemm(x, wfn(prefix + "conv.weight"), cout, cin, out, bias=wfn(prefix + "conv.bias"), taps=3, mode=L_.CONV_UP,
-                 Lin=Lin, Lout=2 * Lin, tag=tag)
+        idx.append(ops.gemm(x, wfn(prefix + "conv.weight"), cout, cin, out, bias=wfn(prefix + "conv.bias"), taps=3, mode=L_.CONV_UP,
+                            Lin=Lin, Lout=2 * Lin, tag=tag))
+    return idx
 
 
 def tc_weight_map(blob: WeightBlob, wbase: int) -> Dict[int, Tuple[int, int]]:
@@ -192,6 +222,51 @@ def tc_weight_map(blob: WeightBlob, wbase: int) -> Dict[int, Tuple[int, int]]:
     return m
 
 
+class Writers:
+    """Who wrote which columns of which buffer last -- so that a normalisation can ask the producers of its input for the moments
+    (mugd_stat_sink) instead of reading the input twice.  Entries: (logical output view, op indices | "audio" | None)."""
+
+    def __init__(self):
+        self.items: List[Tuple[View, object]] = []
+
+    def add(self, view: View, who):
+        self.items.append((view, who))
+
+    @staticmethod
+    def _span(v: View) -> Tuple[int, int]:
+        return v.ptr, v.ptr + 4 * ((v.rows - 1) * v.ld + v.cols)
+
+    def cover(self, x: View):
+        """latest writers of all columns of x as [(who, col_lo, col_hi)], or None when they cannot be told apart cleanly"""
+        need = x.cols
+        covered = [False] * (x.cols // 4)
+        out = []
+        x0, x1 = self._span(x)
+        for view, who in reversed(self.items):
+            v0, v1 = self._span(view)
+            if v1 <= x0 or v0 >= x1:
+                continue
+            off = view.ptr - x.ptr
+            if view.ld != x.ld or view.rows != x.rows or off < 0 or off % 16 or off // 4 + view.cols > x.cols:
+                # overlapping bytes with another geometry: could be a column window of a wider row that does not touch x's columns
+                if view.ld == x.ld and view.rows == x.rows and (off // 4 >= x.cols or off // 4 + view.cols <= 0):
+                    continue
+                return None
+            lo, hi = off // 4, off // 4 + view.cols
+            seen = [covered[q] for q in range(lo // 4, hi // 4)]
+            if all(seen):
+                continue                    # overwritten later
+            if any(seen) or who is None:
+                return None
+            for q in range(lo // 4, hi // 4):
+                covered[q] = True
+            out.append((who, lo, hi))
+            need -= hi - lo
+            if need == 0:
+                return out
+        return None
+
+
 # tags (profiling labels carried in mugd_op.tag)
 TAG_RES, TAG_ATTN, TAG_S4, TAG_UPDOWN, TAG_IO = 1, 2, 3, 4, 5
 
@@ -206,19 +281,47 @@ class UNetCompiler:
     def w(self, name: str) -> int:
         return self.wbase + 4 * self.blob.offset(name)
 
-    def compile(self, arena: Arena, Beff: int, Lz: int, ext: Dict[str, int], per_sample_t: bool) -> dict:
+    def compile(self, arena: Arena, Beff: int, Lz: int, ext: Dict[str, int], per_sample_t: bool, fuse_norms: bool = True) -> dict:
+        """fuse_norms: GroupNorm moments come from the producers of its input (statistics sinks in the GEMM epilogues, one
+        light apply kernel left) and LayerNorm is folded into the Linear that follows it; False = the stand-alone two-pass
+        GroupNorm / LayerNorm kernels (the referee path, and what the exact-fp32 FFMA GEMM uses)."""
         cfg = self.cfg
         ops = OpList(tc_weight_map(self.blob, self.wbase))
         nlev = cfg.levels
         assert Lz % (1 << (nlev - 1)) == 0 and (Lz >> (nlev - 1)) % 4 == 0, "z_length must be a multiple of 32"
         rows = [Beff * (Lz >> l) for l in range(nlev)]
         lens = [Lz >> l for l in range(nlev)]
-        lvl_of_ds = {1 << l: l for l in range(nlev)}
         mc = cfg.model_channels
+        G = cfg.gn_groups
+        fuse_ln = fuse_norms and (self.prefix + "input_blocks.0.0.weight") in self.blob.entries and any(k.endswith("qkv_ln.weight") for k in self.blob.entries)
+
+        # ---- statistics block: [live | base] fp64 moments, `live` re-armed from `base` by the first op of every evaluation ----
+        all_blocks = [b for e in self.lay.input + [self.lay.middle] + self.lay.output if not isinstance(e, tuple) for b in e]
+        n_gn = sum({"res": 2, "attn": 1, "s4": 1}.get(b.kind, 0) for b in all_blocks) + 1
+        lvl_of_ds = {1 << l: l for l in range(nlev)}
+        ln_rows = sum(3 * rows[lvl_of_ds[b.ds]] for b in all_blocks if b.kind == "attn")
+        stat_doubles = (n_gn * Beff * G * 2 + ln_rows * 2 + 64) if fuse_norms else 0
+        stat_floats = (2 * stat_doubles + 63) // 64 * 64
+        live = arena.alloc(1, stat_floats) if fuse_norms else None
+        base = arena.alloc(1, stat_floats) if fuse_norms else None
+        stat_top = [0]                        # doubles handed out
+
+        def stat_alloc(n_doubles: int) -> Tuple[int, int]:
+            o = stat_top[0]
+            stat_top[0] += (n_doubles + 1) // 2 * 2
+            assert stat_top[0] <= stat_doubles, "statistics block overflow"
+            return live.ptr + 8 * o, base.ptr + 8 * o
+
+        if fuse_norms:
+            ops.copy2d(base, live, TAG_IO)
+
+        W = Writers()
+        audio_stats: List[Tuple[View, int, int, int, int]] = []       # (audio columns, base moments, col0, cg, G) per request
 
         # ---- persistent buffers --------------------------------------------------------------
         xin = arena.alloc(rows[0], cfg.in_channels)
         eps = arena.alloc(rows[0], cfg.out_channels)
+        W.add(xin, None)
         ctx_tokens = ext["ctx_tokens"]
         # down-path concat buffers [h | audio_l]
         down_cat = []
@@ -260,93 +363,142 @@ class UNetCompiler:
             ch_h, ca, ich = up_parts[bi]
             audio_slots.append((level, up_cat[bi].c(ch_h, ch_h + ca)))
             bi += cfg.num_res_blocks + 1
+        for _, v in audio_slots:
+            W.add(v, "audio")
 
         emb_total = self.blob.meta["emb_total"]
         emb_off = self.blob.meta["emb_offsets"]
         E = ext["emb_table"]
         step = ext["step"]
 
+        # ---- op emitters that keep the writer registry up to date ---------------------------------
+        def gemm(A, Wt, N, K, out, **kw) -> int:
+            i = ops.gemm(A, Wt, N, K, out, **kw)
+            W.add(out, [i])
+            return i
+
+        def copy(src: View, dst: View, tag: int):
+            """copy of a tensor that lives in two concat buffers; the copy inherits the producers of the source"""
+            ops.copy2d(src, dst, tag)
+            cov = W.cover(src)
+            who = cov[0][0] if cov is not None and len(cov) == 1 and cov[0][1] == 0 and cov[0][2] == src.cols else None
+            W.add(dst, who)
+
+        def groupnorm(x: View, y: View, gamma: int, beta: int, Lr: int, silu: bool, tag: int):
+            """GroupNorm(32, eps 1e-6) [+ SiLU]: single-pass apply when every column of x has a producer that can deliver its moments"""
+            cov = W.cover(x) if fuse_norms else None
+            if cov is not None:
+                for who, lo, hi in cov:
+                    if who != "audio" and not all(ops.sink_capable(i) for i in who):
+                        cov = None
+                        break
+            if cov is None:
+                ops.groupnorm(x, y, gamma, beta, Beff, Lr, G, silu, tag)
+            else:
+                cg = x.cols // G
+                lv, bs = stat_alloc(Beff * G * 2)
+                for who, lo, hi in cov:
+                    if who == "audio":
+                        audio_stats.append((x.c(lo, hi), bs, lo, cg, G))
+                    else:
+                        for i in who:
+                            ops.add_sink(i, 1, lv, lo, cg, G)
+                ops.groupnorm(x, y, gamma, beta, Beff, Lr, G, silu, tag, stats=lv, stats_col0=0, stats_cg=cg, stats_G=G)
+            W.add(y, None)
+
         # ---- block emitters ------------------------------------------------------------------
         def emit_res(b: Block, x: View, out: View, lvl: int):
-            Bq, Lr = Beff, lens[lvl]
+            Lr = lens[lvl]
             m = arena.mark()
             p = b.prefix
             t1 = arena.alloc(x.rows, b.cin)
-            ops.groupnorm(x, t1, self.w(p + "in_layers.0.weight"), self.w(p + "in_layers.0.bias"), Bq, Lr, cfg.gn_groups, True, TAG_RES)
+            groupnorm(x, t1, self.w(p + "in_layers.0.weight"), self.w(p + "in_layers.0.bias"), Lr, True, TAG_RES)
             t2 = arena.alloc(x.rows, b.cout)
-            ops.gemm(t1, self.w(p + "in_layers.2.weight"), b.cout, b.cin, t2, bias=self.w(p + "in_layers.2.bias"), taps=3,
-                     mode=L_.CONV_SAME, Lin=Lr, Lout=Lr, rowvec=E + 4 * emb_off[p],
-                     rowvec_b_stride=emb_total if per_sample_t else 0,
-                     rowvec_step_stride=0 if per_sample_t else emb_total, step=0 if per_sample_t else step, tag=TAG_RES)
+            gemm(t1, self.w(p + "in_layers.2.weight"), b.cout, b.cin, t2, bias=self.w(p + "in_layers.2.bias"), taps=3,
+                 mode=L_.CONV_SAME, Lin=Lr, Lout=Lr, rowvec=E + 4 * emb_off[p],
+                 rowvec_b_stride=emb_total if per_sample_t else 0,
+                 rowvec_step_stride=0 if per_sample_t else emb_total, step=0 if per_sample_t else step, tag=TAG_RES)
             t3 = arena.alloc(x.rows, b.cout)
-            ops.groupnorm(t2, t3, self.w(p + "out_layers.0.weight"), self.w(p + "out_layers.0.bias"), Bq, Lr, cfg.gn_groups, True, TAG_RES)
+            groupnorm(t2, t3, self.w(p + "out_layers.0.weight"), self.w(p + "out_layers.0.bias"), Lr, True, TAG_RES)
             if b.has_skip_conv:
                 # conv3(t3) + skip_connection(x) as ONE GEMM: the 1x1 skip runs as extra k-steps on a second source
-                ops.gemm(t3, self.w(p + "out_skip.weight"), b.cout, b.cout, out, bias=self.w(p + "out_skip.bias"), taps=3,
-                         mode=L_.CONV_SAME, Lin=Lr, Lout=Lr, A2=x, tag=TAG_RES)
+                gemm(t3, self.w(p + "out_skip.weight"), b.cout, b.cout, out, bias=self.w(p + "out_skip.bias"), taps=3,
+                     mode=L_.CONV_SAME, Lin=Lr, Lout=Lr, A2=x, tag=TAG_RES)
             else:
-                ops.gemm(t3, self.w(p + "out_layers.3.weight"), b.cout, b.cout, out, bias=self.w(p + "out_layers.3.bias"), taps=3,
-                         mode=L_.CONV_SAME, Lin=Lr, Lout=Lr, residual=x, tag=TAG_RES)
+                gemm(t3, self.w(p + "out_layers.3.weight"), b.cout, b.cout, out, bias=self.w(p + "out_layers.3.bias"), taps=3,
+                     mode=L_.CONV_SAME, Lin=Lr, Lout=Lr, residual=x, tag=TAG_RES)
             arena.release(m)
 
         attn_index = [0]
 
         def emit_attn(b: Block, x: View, out: View, lvl: int):
-            Bq, Lr, Cc, H = Beff, lens[lvl], b.cin, b.heads
+            Lr, Cc, H = lens[lvl], b.cin, b.heads
             m = arena.mark()
             p = b.prefix
             t = p + "transformer_blocks.0."
             kv = ext["ctx_kv"][attn_index[0]]          # View [Beff*ctx_tokens, 2C] filled at prepare()
             attn_index[0] += 1
             g = arena.alloc(x.rows, Cc)
-            ops.groupnorm(x, g, self.w(p + "norm.weight"), self.w(p + "norm.bias"), Bq, Lr, cfg.gn_groups, False, TAG_ATTN)
+            groupnorm(x, g, self.w(p + "norm.weight"), self.w(p + "norm.bias"), Lr, False, TAG_ATTN)
             h0 = arena.alloc(x.rows, Cc)
-            ops.gemm(g, self.w(p + "proj_in.weight"), Cc, Cc, h0, bias=self.w(p + "proj_in.bias"), Lout=Lr, tag=TAG_ATTN)
-            n1 = arena.alloc(x.rows, Cc)
-            ops.layernorm(h0, n1, self.w(t + "norm1.weight"), self.w(t + "norm1.bias"), TAG_ATTN)
+            i_h0 = gemm(g, self.w(p + "proj_in.weight"), Cc, Cc, h0, bias=self.w(p + "proj_in.bias"), Lout=Lr, tag=TAG_ATTN)
+
+            def normed_linear(src: View, i_src: int, norm: str, lin: str, N: int, dst: View, gate: int = L_.GATE_NONE, has_bias: bool = False):
+                """Linear(LayerNorm(src)) (attention.py:147-151).  Folded: the producer of src (op i_src) delivers the row moments,
+                the Linear runs on the raw rows with gamma-scaled weights and corrects in its epilogue; else LayerNorm kernel + Linear."""
+                if fuse_ln and ops.sink_capable(i_src):
+                    lv, _ = stat_alloc(src.rows * 2)
+                    ops.add_sink(i_src, 2, lv)
+                    gemm(src, self.w(t + lin + "_ln.weight"), N, Cc, dst, bias=self.w(t + lin + "_ln.bias"), gate=gate, Lout=Lr,
+                         ln=(lv, self.w(t + lin + "_ln.colsum"), LN_EPS), tag=TAG_ATTN)
+                else:
+                    n = arena.alloc(src.rows, Cc)
+                    ops.layernorm(src, n, self.w(t + norm + ".weight"), self.w(t + norm + ".bias"), TAG_ATTN)
+                    W.add(n, None)
+                    gemm(n, self.w(t + lin + ".weight"), N, Cc, dst, bias=self.w(t + lin + ".bias") if has_bias else 0, gate=gate,
+                         Lout=Lr, tag=TAG_ATTN)
+
             qkv = arena.alloc(x.rows, 3 * Cc)
-            ops.gemm(n1, self.w(t + "attn1.qkv.weight"), 3 * Cc, Cc, qkv, Lout=Lr, tag=TAG_ATTN)
+            normed_linear(h0, i_h0, "norm1", "attn1.qkv", 3 * Cc, qkv)
             ao = arena.alloc(x.rows, Cc)
             ops.attention(qkv.c(0, Cc), qkv.c(Cc, 2 * Cc), qkv.c(2 * Cc, 3 * Cc), ao,
                           self.w(t + "attn1.relative_position_embedding"), self.w(t + "attn1.C_embedding"),
-                          Bq, H, Lr, Lr, cfg.pos_max, TAG_ATTN)
+                          Beff, H, Lr, Lr, cfg.pos_max, TAG_ATTN)
+            W.add(ao, None)
             h1 = arena.alloc(x.rows, Cc)
-            ops.gemm(ao, self.w(t + "attn1.to_out.0.weight"), Cc, Cc, h1, bias=self.w(t + "attn1.to_out.0.bias"),
-                     residual=h0, Lout=Lr, tag=TAG_ATTN)
-            n2 = n1
-            ops.layernorm(h1, n2, self.w(t + "norm2.weight"), self.w(t + "norm2.bias"), TAG_ATTN)
-            q2 = qkv.c(0, Cc)
-            ops.gemm(n2, self.w(t + "attn2.to_q.weight"), Cc, Cc, q2, Lout=Lr, tag=TAG_ATTN)
+            i_h1 = gemm(ao, self.w(t + "attn1.to_out.0.weight"), Cc, Cc, h1, bias=self.w(t + "attn1.to_out.0.bias"),
+                        residual=h0, Lout=Lr, tag=TAG_ATTN)
+            q2 = arena.alloc(x.rows, Cc)
+            normed_linear(h1, i_h1, "norm2", "attn2.to_q", Cc, q2)
             ops.attention(q2, kv.c(0, Cc), kv.c(Cc, 2 * Cc), ao,
                           self.w(t + "attn2.relative_position_embedding"), self.w(t + "attn2.C_embedding"),
-                          Bq, H, Lr, ctx_tokens, cfg.pos_max, TAG_ATTN)
+                          Beff, H, Lr, ctx_tokens, cfg.pos_max, TAG_ATTN)
+            W.add(ao, None)
             h2 = h0                                    # h0 is dead after the first residual add
-            ops.gemm(ao, self.w(t + "attn2.to_out.0.weight"), Cc, Cc, h2, bias=self.w(t + "attn2.to_out.0.bias"),
-                     residual=h1, Lout=Lr, tag=TAG_ATTN)
-            n3 = n1
-            ops.layernorm(h2, n3, self.w(t + "norm3.weight"), self.w(t + "norm3.bias"), TAG_ATTN)
+            i_h2 = gemm(ao, self.w(t + "attn2.to_out.0.weight"), Cc, Cc, h2, bias=self.w(t + "attn2.to_out.0.bias"),
+                        residual=h1, Lout=Lr, tag=TAG_ATTN)
             ff = arena.alloc(x.rows, 4 * Cc)
-            ops.gemm(n3, self.w(t + "ff.net.0.proj.weight"), 8 * Cc, Cc, ff, bias=self.w(t + "ff.net.0.proj.bias"),
-                     gate=L_.GATE_GEGLU, Lout=Lr, tag=TAG_ATTN)
+            normed_linear(h2, i_h2, "norm3", "ff.net.0.proj", 8 * Cc, ff, gate=L_.GATE_GEGLU, has_bias=True)
             # proj_out(ff.net.2(ff) + h2) + x as ONE GEMM over [ff | h2] with the packer-composed weight [Wp Wf | Wp]
-            ops.gemm(ff, self.w(p + "ff_out.weight"), Cc, 4 * Cc, out, bias=self.w(p + "ff_out.bias"), residual=x, Lout=Lr,
-                     A2=h2, tag=TAG_ATTN)
+            gemm(ff, self.w(p + "ff_out.weight"), Cc, 4 * Cc, out, bias=self.w(p + "ff_out.bias"), residual=x, Lout=Lr,
+                 A2=h2, tag=TAG_ATTN)
             arena.release(m)
 
         def emit_s4(b: Block, x: View, out: View, lvl: int):
-            Bq, Lr, Hc = Beff, lens[lvl], b.cin
+            Lr, Hc = lens[lvl], b.cin
             m = arena.mark()
             p = b.prefix
-            s = p + "s4_model."
+            s_ = p + "s4_model."
             g = arena.alloc(x.rows, Hc)
-            ops.groupnorm(x, g, self.w(p + "norm.weight"), self.w(p + "norm.bias"), Bq, Lr, cfg.gn_groups, False, TAG_S4)
+            groupnorm(x, g, self.w(p + "norm.weight"), self.w(p + "norm.bias"), Lr, False, TAG_S4)
             y = arena.alloc(x.rows, Hc)
-            ops.s4conv(g, ext["s4_kt"][p].ptr, self.w(s + "D"), y, Bq, Lr, TAG_S4)
+            ops.s4conv(g, ext["s4_kt"][p].ptr, self.w(s_ + "D"), y, Beff, Lr, TAG_S4)
+            W.add(y, None)
             z = g
-            ops.gemm(y, self.w(s + "output_linear.0.weight"), 2 * Hc, Hc, z, bias=self.w(s + "output_linear.0.bias"),
-                     gate=L_.GATE_GLU, Lout=Lr, tag=TAG_S4)
-            ops.gemm(z, self.w(p + "out_layer.weight"), Hc, Hc, out, bias=self.w(p + "out_layer.bias"), taps=3,
-                     mode=L_.CONV_SAME, Lin=Lr, Lout=Lr, residual=x, tag=TAG_S4)
+            gemm(y, self.w(s_ + "output_linear.0.weight"), 2 * Hc, Hc, z, bias=self.w(s_ + "output_linear.0.bias"),
+                 gate=L_.GATE_GLU, Lout=Lr, tag=TAG_S4)
+            gemm(z, self.w(p + "out_layer.weight"), Hc, Hc, out, bias=self.w(p + "out_layer.bias"), taps=3,
+                 mode=L_.CONV_SAME, Lin=Lr, Lout=Lr, residual=x, tag=TAG_S4)
             arena.release(m)
 
         def run_blocks(blocks: List[Block], x: View, final_out: Optional[View], lvl: int) -> Tuple[View, int]:
@@ -357,7 +509,10 @@ class UNetCompiler:
                 if b.kind == "up":
                     tgt_rows = rows[lvl - 1]
                     out = final_out if (last and final_out is not None) else arena.alloc(tgt_rows, b.cout)
-                    emit_upsample_conv(ops, self.blob, self.w, b.prefix, cur, out, lens[lvl], b.cin, b.cout, TAG_UPDOWN)
+                    idx = emit_upsample_conv(ops, self.blob, self.w, b.prefix, cur, out, lens[lvl], b.cin, b.cout, TAG_UPDOWN)
+                    # the two parity GEMMs write the even / odd rows of `out`: together they are its producer.  Their rows are
+                    # indexed on the un-upsampled axis, which keeps row / rows-per-sample = sample for the group moments.
+                    W.add(out, idx if len(idx) == 2 else None)
                     lvl -= 1
                     cur = out
                     continue
@@ -384,16 +539,16 @@ class UNetCompiler:
             b0 = entry[0]
             if b0.kind == "conv_in":
                 dst = down_cat[0].c(0, mc)
-                ops.gemm(xin, self.w(b0.prefix + "weight"), b0.cout, b0.cin, dst, bias=self.w(b0.prefix + "bias"), taps=3,
-                         mode=L_.CONV_SAME, Lin=lens[0], Lout=lens[0], tag=TAG_IO)
-                ops.copy2d(dst, skip_home[k], TAG_IO)
+                gemm(xin, self.w(b0.prefix + "weight"), b0.cout, b0.cin, dst, bias=self.w(b0.prefix + "bias"), taps=3,
+                     mode=L_.CONV_SAME, Lin=lens[0], Lout=lens[0], tag=TAG_IO)
+                copy(dst, skip_home[k], TAG_IO)
                 k += 1
                 h = dst
             elif b0.kind == "down":
                 dst = down_cat[lvl + 1].c(0, b0.cout)
-                ops.gemm(h, self.w(b0.prefix + "conv.weight"), b0.cout, b0.cin, dst, bias=self.w(b0.prefix + "conv.bias"),
-                         taps=3, mode=L_.CONV_DOWN, Lin=lens[lvl], Lout=lens[lvl + 1], tag=TAG_UPDOWN)
-                ops.copy2d(dst, skip_home[k], TAG_UPDOWN)
+                gemm(h, self.w(b0.prefix + "conv.weight"), b0.cout, b0.cin, dst, bias=self.w(b0.prefix + "conv.bias"),
+                     taps=3, mode=L_.CONV_DOWN, Lin=lens[lvl], Lout=lens[lvl + 1], tag=TAG_UPDOWN)
+                copy(dst, skip_home[k], TAG_UPDOWN)
                 k += 1
                 lvl += 1
                 h = dst
@@ -425,11 +580,11 @@ class UNetCompiler:
         ob = self.lay.out
         m = arena.mark()
         t = arena.alloc(rows[0], mc)
-        ops.groupnorm(final, t, self.w(ob.prefix + "0.weight"), self.w(ob.prefix + "0.bias"), Beff, lens[0], cfg.gn_groups, True, TAG_IO)
-        ops.gemm(t, self.w(ob.prefix + "2.weight"), ob.cout, ob.cin, eps, bias=self.w(ob.prefix + "2.bias"), taps=3,
-                 mode=L_.CONV_SAME, Lin=lens[0], Lout=lens[0], tag=TAG_IO)
+        groupnorm(final, t, self.w(ob.prefix + "0.weight"), self.w(ob.prefix + "0.bias"), lens[0], True, TAG_IO)
+        gemm(t, self.w(ob.prefix + "2.weight"), ob.cout, ob.cin, eps, bias=self.w(ob.prefix + "2.bias"), taps=3,
+             mode=L_.CONV_SAME, Lin=lens[0], Lout=lens[0], tag=TAG_IO)
         arena.release(m)
-        return dict(ops=ops, xin=xin, eps=eps, audio_slots=audio_slots)
+        return dict(ops=ops, xin=xin, eps=eps, audio_slots=audio_slots, stats_base=base, audio_stats=audio_stats)
 
 
 class DecoderCompiler:

@@ -155,6 +155,18 @@ def _pack_block(blob: WeightBlob, sd: Dict[str, torch.Tensor], b: Block):
         for n in ("norm1.", "norm2.", "norm3."):
             blob.add_shaped(t + n + "weight", sd[t + n + "weight"])
             blob.add_shaped(t + n + "bias", sd[t + n + "bias"])
+        # LayerNorm folded into the Linear behind it (attention.py:147-151):  W LN(h) + b = rstd (W' h - mean colsum) + b'  with
+        # W' = W diag(gamma), colsum = W' 1, b' = W beta + b  -- formed in fp64
+        for norm, lin, wkey, bkey in (("norm1.", "attn1.qkv", t + "attn1.qkv.weight", None),
+                                      ("norm2.", "attn2.to_q", t + "attn2.to_q.weight", None),
+                                      ("norm3.", "ff.net.0.proj", t + "ff.net.0.proj.weight", t + "ff.net.0.proj.bias")):
+            w = blob_tensor(blob, wkey).double()
+            gam, bet = sd[t + norm + "weight"].double(), sd[t + norm + "bias"].double()
+            wg = (w * gam[None, :]).float()
+            blob.add_shaped(t + lin + "_ln.weight", wg)
+            blob.add_shaped(t + lin + "_ln.colsum", wg.double().sum(dim=1).float())
+            bias = w @ bet + (blob_tensor(blob, bkey).double() if bkey else 0.0)
+            blob.add_shaped(t + lin + "_ln.bias", bias.float())
     elif b.kind == "s4":
         blob.add_shaped(p + "norm.weight", sd[p + "norm.weight"])
         blob.add_shaped(p + "norm.bias", sd[p + "norm.bias"])
@@ -241,6 +253,11 @@ def pack_model(sd: Dict[str, torch.Tensor], ucfg: UNetConfig, dcfg: DecoderConfi
                 blob.add_shaped(name + "#lo", lo)
     blob.finalize()
     return blob
+
+
+def blob_tensor(blob: WeightBlob, name: str) -> torch.Tensor:
+    """an entry that was added earlier (in the packed layout, before finalize)"""
+    return _chunk_of(blob, name).view(blob.entries[name].shape)
 
 
 def _chunk_of(blob: WeightBlob, name: str) -> torch.Tensor:
