@@ -108,8 +108,13 @@ static int tc_validate_fusions(const mugd_gemm& g) {
             const mugd_stat_sink& s = g.sink[k];
             MUGD_REQUIRE(s.kind >= 0 && s.kind <= 2, "gemm: sink kind %d", s.kind);
             if (s.kind) MUGD_REQUIRE(s.buf && (reinterpret_cast<uintptr_t>(s.buf) & 7u) == 0, "gemm: sink buffer");
-            if (s.kind == 1) MUGD_REQUIRE(s.cg > 0 && s.cg % 4 == 0 && s.col0 % 4 == 0 && s.G > 0 && s.col0 + g.N <= s.cg * s.G,
-                                          "gemm: group sink geometry (col0=%d cg=%d G=%d N=%d)", s.col0, s.cg, s.G, g.N);
+            if (s.kind == 1) {
+                MUGD_REQUIRE(s.cg > 0 && s.cg % 4 == 0 && s.col0 % 4 == 0 && s.G > 0 && s.col0 + g.N <= s.cg * s.G,
+                             "gemm: group sink geometry (col0=%d cg=%d G=%d N=%d)", s.col0, s.cg, s.G, g.N);
+                const int lrows = g.conv_mode == MUGD_CONV_NONE ? g.M : g.Lout;       // rows per sample as the tiles see them
+                MUGD_REQUIRE(g.conv_mode != MUGD_CONV_NONE && (lrows >= TC_BM || TC_BM / lrows <= 2),
+                             "gemm: group sinks need a conv-mode row structure with at most two samples per 128-row tile (Lout=%d)", g.Lout);
+            }
         }
     }
     if (g.ln_stats) {

@@ -189,40 +189,83 @@ struct TcSmem {
 };
 
 // ---- statistics sinks (mugd_stat_sink): moments of the OUTPUT for the norm that follows, accumulated while it is written ----
-// Group moments: a thread keeps (sum, sum of squares) of the float4s it stores -- its column quad, hence its group, is fixed for
-// the whole tile -- and flushes them with two fp64 reductions into global memory whenever the sample changes and at the end.
+// Group moments (kind 1).  A thread's column quad -- hence its group -- is fixed for the whole tile; it keeps fp64 (sum, sum of
+// squares) of the float4s it stores, separately for the (at most two) samples a 128-row tile can hold.  tc_group_flush() then
+// reduces inside the CTA (threads that share a column quad, then quads that share a group) and issues ONE fp64 reduction per
+// (sample, group) of the tile: per-thread atomics on the few [B][G] addresses serialise in L2 (measured: +0.7 ms per step).
 struct TcGroupAcc {
-    double s, ss;
-    int b;                                   // sample the running sums belong to (-1: empty)
-    __device__ __forceinline__ void reset() { s = 0.0; ss = 0.0; b = -1; }
-    __device__ __forceinline__ void flush(const mugd_stat_sink& k, int grp) {
-        if (b >= 0) {
-            double* d = k.buf + ((int64_t)b * k.G + grp) * 2;
-            atomicAdd(d, s);
-            atomicAdd(d + 1, ss);
-        }
-        s = 0.0; ss = 0.0;
-    }
-    __device__ __forceinline__ void add(const mugd_stat_sink& k, int grp, int bb, float4 v) {
-        if (bb != b) { flush(k, grp); b = bb; }
-        s += (double)((v.x + v.y) + (v.z + v.w));
-        ss += (double)((v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w));
+    double s0, ss0, s1, ss1;               // sample-in-tile 0 / 1
+    __device__ __forceinline__ void reset() { s0 = ss0 = s1 = ss1 = 0.0; }
+    __device__ __forceinline__ void add(int si, float4 v) {
+        const double s = (double)((v.x + v.y) + (v.z + v.w));
+        const double ss = (double)((v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w));
+        if (si == 0) { s0 += s; ss0 += ss; } else { s1 += s; ss1 += ss; }
     }
 };
-// Row moments (LayerNorm of the consumer): the SEG lanes that hold one output row of this tile reduce with shuffles, the segment
-// leader adds the tile's share of the row to the row's two doubles.  Every lane of the warp must call it (inactive: v = 0, m < 0).
+// scratch: double2 P[2 sinks][2 samples][TC_THREADS] at `scratch` (shared memory, 16 KB), free at this point.  C4 = column quads of
+// the tile (threads tid, tid + C4, ... share a quad); n0 = first column of the tile; b0 = first sample of the tile.
+template <int C4>
+__device__ __forceinline__ void tc_group_flush(const mugd_gemm& g, const TcGroupAcc* ga, uint32_t scratch, int n0, int b0, int nsamp) {
+    const int tid = (int)threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        if (g.sink[k].kind != 1) continue;
+        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(scratch + (uint32_t)(((k * 2 + 0) * TC_THREADS + tid) * 16)), "d"(ga[k].s0), "d"(ga[k].ss0) : "memory");
+        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(scratch + (uint32_t)(((k * 2 + 1) * TC_THREADS + tid) * 16)), "d"(ga[k].s1), "d"(ga[k].ss1) : "memory");
+    }
+    __syncthreads();
+    // stage 1: thread (k, si, c4) sums the TC_THREADS / C4 threads that share column quad c4 (fixed order -> deterministic per tile)
+    const int c4 = tid % C4, which = tid / C4;                    // which = k * 2 + si, needs 4 * C4 <= TC_THREADS
+    double s = 0.0, ss = 0.0;
+    if (which < 4 && g.sink[which >> 1].kind == 1) {
+#pragma unroll 4
+        for (int j = 0; j < TC_THREADS / C4; ++j) {
+            double a, b;
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(scratch + (uint32_t)((which * TC_THREADS + c4 + j * C4) * 16)));
+            s += a; ss += b;
+        }
+    }
+    __syncthreads();
+    if (which < 4)
+        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(scratch + (uint32_t)((which * TC_THREADS + c4) * 16)), "d"(s), "d"(ss) : "memory");
+    __syncthreads();
+    // stage 2: the first quad of every group in this tile sums the quads of its group and issues the reduction
+    if (which < 4 && g.sink[which >> 1].kind == 1) {
+        const mugd_stat_sink& k = g.sink[which >> 1];
+        const int si = which & 1;
+        const int nn = n0 + c4 * 4;
+        if (si < nsamp && nn < g.N) {
+            const int grp = (k.col0 + nn) / k.cg;
+            const bool leader = c4 == 0 || (k.col0 + nn - 4) / k.cg != grp;
+            if (leader) {
+                double ts = 0.0, tss = 0.0;
+                for (int q = c4; q < C4 && n0 + q * 4 < g.N && (k.col0 + n0 + q * 4) / k.cg == grp; ++q) {
+                    double a, b;
+                    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(scratch + (uint32_t)((which * TC_THREADS + q) * 16)));
+                    ts += a; tss += b;
+                }
+                double* d = k.buf + ((int64_t)(b0 + si) * k.G + grp) * 2;
+                atomicAdd(d, ts);
+                atomicAdd(d + 1, tss);
+            }
+        }
+    }
+}
+// Row moments (kind 2, LayerNorm of the consumer): the SEG lanes that hold one output row of this tile reduce with shuffles (fp32: at
+// most 128 values), the segment leader adds the tile's share of the row to the row's two doubles -- one address per row, so no
+// contention.  Every lane of the warp must call it (inactive: v = 0, m < 0).
 template <int SEG>
 __device__ __forceinline__ void tc_row_sink(const mugd_stat_sink& k, int m, float4 v) {
-    double s = (double)((v.x + v.y) + (v.z + v.w));
-    double ss = (double)((v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w));
+    float s = (v.x + v.y) + (v.z + v.w);
+    float ss = (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
 #pragma unroll
     for (int o = SEG / 2; o > 0; o >>= 1) {
         s += __shfl_xor_sync(0xffffffffu, s, o);
         ss += __shfl_xor_sync(0xffffffffu, ss, o);
     }
     if ((threadIdx.x & (SEG - 1)) == 0 && m >= 0) {
-        atomicAdd(k.buf + (int64_t)m * 2, s);
-        atomicAdd(k.buf + (int64_t)m * 2 + 1, ss);
+        atomicAdd(k.buf + (int64_t)m * 2, (double)s);
+        atomicAdd(k.buf + (int64_t)m * 2 + 1, (double)ss);
     }
 }
 // mean / rstd of a row from its two moments (LayerNorm folded into the GEMM, mugd_gemm.ln_stats)
@@ -281,19 +324,13 @@ __device__ __forceinline__ float4 tc_finish4(const mugd_gemm& g, float4 acc, flo
 // MODE = TC_EPI_LN reads the (mean, rstd) of tile row r from shared memory at rowstat + 8*r (written in phase 1).
 template <int BN, int ACT, int GATE, int MODE>
 __device__ __forceinline__ void tc_store_tile(const mugd_gemm& g, uint32_t stage, int m_base, int n0, int rows_valid, const float* rowvec,
-                                              uint32_t rowstat) {
+                                              uint32_t rowstat, int Lrows) {
     constexpr int SP = BN + 4;
     constexpr int C4 = BN / 4;
     constexpr int U = 8;
     constexpr int SEG = C4 < 32 ? C4 : 32;
     TcGroupAcc ga[2];
-    int grp[2] = {0, 0};
-    if constexpr (MODE == TC_EPI_SINK) {
-        ga[0].reset(); ga[1].reset();
-        const int nn = n0 + ((int)threadIdx.x % C4) * 4;          // this thread's column quad is the same for every row it visits
-#pragma unroll
-        for (int k = 0; k < 2; ++k) grp[k] = g.sink[k].kind == 1 ? (g.sink[k].col0 + nn) / g.sink[k].cg : 0;
-    }
+    if constexpr (MODE == TC_EPI_SINK) { ga[0].reset(); ga[1].reset(); }
 #pragma unroll 1
     for (int i0 = 0; i0 < TC_BM * C4; i0 += TC_THREADS * U) {
         float4 acc[U], bia[U], rvv[U], res[U], cs[U];
@@ -327,18 +364,20 @@ __device__ __forceinline__ void tc_store_tile(const mugd_gemm& g, uint32_t stage
             float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
             if (ok[u]) o = tc_finish4<ACT, GATE, MODE == TC_EPI_LN>(g, acc[u], bia[u], rvv[u], res[u], cs[u], ln[u], m, n0 + c4 * 4);
             if constexpr (MODE == TC_EPI_SINK) {
+                const int si = row >= Lrows ? 1 : 0;               // a 128-row tile holds at most two samples when group sinks are on
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {
-                    if (g.sink[k].kind == 1) { if (ok[u]) ga[k].add(g.sink[k], grp[k], m / g.Lout, o); }
+                    if (g.sink[k].kind == 1) { if (ok[u]) ga[k].add(si, o); }
                     else if (g.sink[k].kind == 2) tc_row_sink<SEG>(g.sink[k], ok[u] ? m : -1, o);     // (warp-uniform branch)
                 }
             }
         }
     }
     if constexpr (MODE == TC_EPI_SINK) {
-#pragma unroll
-        for (int k = 0; k < 2; ++k)
-            if (g.sink[k].kind == 1) ga[k].flush(g.sink[k], grp[k]);
+        if (g.sink[0].kind == 1 || g.sink[1].kind == 1) {
+            __syncthreads();                                          // every thread is done reading the staged tile
+            tc_group_flush<C4>(g, ga, stage, n0, m_base / g.Lout, (rows_valid + Lrows - 1) / Lrows);
+        }
     }
 }
 
@@ -622,7 +661,7 @@ __device__ __forceinline__ void gemm_tc_tile(const CUtensorMap* tmA, const CUten
                 for (int u = 0; u < U; ++u) st_f4(wsp + (i0 + u * TC_THREADS + (int)threadIdx.x) * 4, acc[u]);   // [row][BN] dense
             }
         } else {
-#define TC_CALL_STORE(A_, G_, M_) tc_store_tile<BN, A_, G_, M_>(g, base, m_base, n0, rows_valid, rowvec, base + S::TILE_BYTES - 1024u)
+#define TC_CALL_STORE(A_, G_, M_) tc_store_tile<BN, A_, G_, M_>(g, base, m_base, n0, rows_valid, rowvec, base + S::TILE_BYTES - 1024u, p.Lrows)
             TC_DISPATCH_EPI(g, TC_CALL_STORE);
 #undef TC_CALL_STORE
         }
@@ -676,12 +715,7 @@ __device__ __forceinline__ void tc_reduce_rows(const TcParams& p, int tile_lin, 
         }
     }
     TcGroupAcc ga[2];
-    int grp[2] = {0, 0};
-    if constexpr (MODE == TC_EPI_SINK) {
-        ga[0].reset(); ga[1].reset();
-#pragma unroll
-        for (int k = 0; k < 2; ++k) grp[k] = g.sink[k].kind == 1 ? (g.sink[k].col0 + n) / g.sink[k].cg : 0;
-    }
+    if constexpr (MODE == TC_EPI_SINK) { ga[0].reset(); ga[1].reset(); }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int m = m_base + r0 + j * G::RPP;
@@ -699,17 +733,19 @@ __device__ __forceinline__ void tc_reduce_rows(const TcParams& p, int tile_lin, 
             o = tc_finish4<ACT, GATE, MODE == TC_EPI_LN>(g, acc[j], bia, rvv, res, cs, ln, m, n);
         }
         if constexpr (MODE == TC_EPI_SINK) {
+            const int si = (r0 + j * G::RPP) >= p.Lrows ? 1 : 0;
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
-                if (g.sink[k].kind == 1) { if (ok[j]) ga[k].add(g.sink[k], grp[k], m / g.Lout, o); }
+                if (g.sink[k].kind == 1) { if (ok[j]) ga[k].add(si, o); }
                 else if (g.sink[k].kind == 2) tc_row_sink<SEG>(g.sink[k], ok[j] ? m : -1, o);
             }
         }
     }
     if constexpr (MODE == TC_EPI_SINK) {
-#pragma unroll
-        for (int k = 0; k < 2; ++k)
-            if (g.sink[k].kind == 1) ga[k].flush(g.sink[k], grp[k]);
+        if (g.sink[0].kind == 1 || g.sink[1].kind == 1) {
+            __shared__ __align__(16) double red_scratch[2 * 2 * TC_THREADS * 2];          // 16 KB
+            tc_group_flush<C4>(g, ga, smem_u32(red_scratch), bx * BN, m_base / g.Lout, (rows_valid + p.Lrows - 1) / p.Lrows);
+        }
     }
 }
 

@@ -71,46 +71,64 @@ groupnorm_silu_kernel(const float* __restrict__ x, int64_t ldx, float* __restric
 }
 
 // ---- GroupNorm with moments supplied by the producers of x (mugd_stat_sink kind 1) --------------------------------------
-// Single pass: one CTA per (row chunk, sample); the first G threads turn the sample's [G][2] fp64 moments into (mean, rstd),
-// then every thread applies them to coalesced float4s.  No reduction, no second read of x.
-constexpr int GNA_ROWS = 32;      // rows per CTA
+// Single pass: one CTA per (row chunk, sample) with ~1024 float4 of work; every thread first ISSUES its (up to 4) loads of x,
+// gamma, beta, then the first G threads turn the sample's [G][2] fp64 moments into (mean, rstd) while those loads fly, then the
+// values are normalised and stored.  No reduction, no second read of x, one memory round trip of latency.
+constexpr int GNA_F4 = 1024;      // float4 per CTA
+constexpr int GNA_U = GNA_F4 / GN_THREADS;
 
 __global__ void __launch_bounds__(GN_THREADS)
-groupnorm_apply_kernel(const mugd_groupnorm p) {
+groupnorm_apply_kernel(const mugd_groupnorm p, int rows_per_cta) {
     __shared__ float s_mean[128], s_rstd[128];
     pdl_wait();
     const int b = blockIdx.y;
     const int cgn = p.stats_cg;                               // channels per group of the normalised tensor
-    const double n = (double)p.L * cgn;
-    for (int gi = threadIdx.x; gi < p.stats_G; gi += GN_THREADS) {
-        const double* st = p.stats + ((int64_t)b * p.stats_G + gi) * 2;
-        const double mean = st[0] / n;
-        double var = st[1] / n - mean * mean;
-        if (var < 0.0) var = 0.0;
-        s_mean[gi] = (float)mean;
-        s_rstd[gi] = (float)(1.0 / sqrt(var + (double)p.eps));
-    }
-    __syncthreads();
     const int q = p.C >> 2;
-    const int r0 = blockIdx.x * GNA_ROWS;
-    const int r1 = min(p.L, r0 + GNA_ROWS);
+    const int r0 = blockIdx.x * rows_per_cta;
+    const int r1 = min(p.L, r0 + rows_per_cta);
     const float* xb = p.x + (int64_t)b * p.L * p.ldx;
     float* yb = p.y + (int64_t)b * p.L * p.ldy;
     const int total = (r1 - r0) * q;
-    for (int i = threadIdx.x; i < total; i += GN_THREADS) {
-        const int row = r0 + i / q, c = (i % q) * 4;
-        const int gi = (p.stats_col0 + c) / cgn;
-        const float mean = s_mean[gi], rstd = s_rstd[gi];
-        const float4 v = ld_f4(xb + (int64_t)row * p.ldx + c);
-        const float4 ga = ld_f4(p.gamma + c);
-        const float4 be = ld_f4(p.beta + c);
-        float4 o;
-        o.x = (v.x - mean) * rstd * ga.x + be.x;
-        o.y = (v.y - mean) * rstd * ga.y + be.y;
-        o.z = (v.z - mean) * rstd * ga.z + be.z;
-        o.w = (v.w - mean) * rstd * ga.w + be.w;
-        if (p.silu) { o.x = silu_f(o.x); o.y = silu_f(o.y); o.z = silu_f(o.z); o.w = silu_f(o.w); }
-        st_f4(yb + (int64_t)row * p.ldy + c, o);
+    for (int i0 = 0; i0 < total; i0 += GN_THREADS * GNA_U) {
+        float4 v[GNA_U], ga[GNA_U], be[GNA_U];
+        int row[GNA_U], c[GNA_U];
+#pragma unroll
+        for (int u = 0; u < GNA_U; ++u) {
+            const int i = i0 + u * GN_THREADS + (int)threadIdx.x;
+            row[u] = -1;
+            if (i < total) {
+                row[u] = r0 + i / q;
+                c[u] = (i % q) * 4;
+                v[u] = ld_f4(xb + (int64_t)row[u] * p.ldx + c[u]);
+                ga[u] = ld_f4(p.gamma + c[u]);
+                be[u] = ld_f4(p.beta + c[u]);
+            }
+        }
+        if (i0 == 0) {
+            const double n = (double)p.L * cgn;
+            for (int gi = threadIdx.x; gi < p.stats_G; gi += GN_THREADS) {
+                const double* st = p.stats + ((int64_t)b * p.stats_G + gi) * 2;
+                const double mean = st[0] / n;
+                double var = st[1] / n - mean * mean;
+                if (var < 0.0) var = 0.0;
+                s_mean[gi] = (float)mean;
+                s_rstd[gi] = (float)(1.0 / sqrt(var + (double)p.eps));
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int u = 0; u < GNA_U; ++u) {
+            if (row[u] < 0) continue;
+            const int gi = (p.stats_col0 + c[u]) / cgn;
+            const float mean = s_mean[gi], rstd = s_rstd[gi];
+            float4 o;
+            o.x = (v[u].x - mean) * rstd * ga[u].x + be[u].x;
+            o.y = (v[u].y - mean) * rstd * ga[u].y + be[u].y;
+            o.z = (v[u].z - mean) * rstd * ga[u].z + be[u].z;
+            o.w = (v[u].w - mean) * rstd * ga[u].w + be[u].w;
+            if (p.silu) { o.x = silu_f(o.x); o.y = silu_f(o.y); o.z = silu_f(o.z); o.w = silu_f(o.w); }
+            st_f4(yb + (int64_t)row[u] * p.ldy + c[u], o);
+        }
     }
 }
 
@@ -160,7 +178,9 @@ int launch_groupnorm(const DeviceInfo&, const mugd_groupnorm& g, cudaStream_t st
             MUGD_CHECK_CUDA(launch_k(groupnorm_stats_kernel, dim3(g_last - g_first + 1, g.B), dim3(GN_THREADS), 0, st, g, g_first));
         } else {
             MUGD_REQUIRE(g.ldy % 4 == 0 && aligned16(g.y) && aligned16(g.gamma) && aligned16(g.beta) && g.ldy >= g.C, "groupnorm: y / gamma / beta alignment");
-            MUGD_CHECK_CUDA(launch_k(groupnorm_apply_kernel, dim3((g.L + GNA_ROWS - 1) / GNA_ROWS, g.B), dim3(GN_THREADS), 0, st, g));
+            int rpc = GNA_F4 / (g.C / 4);
+            if (rpc < 1) rpc = 1;
+            MUGD_CHECK_CUDA(launch_k(groupnorm_apply_kernel, dim3((g.L + rpc - 1) / rpc, g.B), dim3(GN_THREADS), 0, st, g, rpc));
         }
         if (launches) *launches += 1;
         return MUGD_OK;

@@ -137,6 +137,15 @@ class OpList:
         k = 0 if g.sink[0].kind == 0 else 1
         assert g.sink[k].kind == 0
         g.sink[k].buf, g.sink[k].kind, g.sink[k].col0, g.sink[k].cg, g.sink[k].G = buf, kind, col0, cg, G
+        if kind == 1 and g.conv_mode == L_.CONV_NONE:
+            # group moments are kept per sample: run the 1x1 as a one-tap conv so that output tiles follow the sample structure
+            # (3-D tensor map (k, l, b)) instead of cutting the flat row range every 128 rows
+            g.conv_mode, g.taps, g.tap_shift, g.tap_dilation, g.Lin = L_.CONV_TAPS, 1, 0, 1, g.Lout
+
+    def group_sink_ok(self, i: int) -> bool:
+        """a 128-row tile of op i holds at most two samples (what the epilogue's group-moment accumulators are built for)"""
+        g = self.ops[i].u.gemm
+        return g.Lout >= 128 or 128 // g.Lout <= 2
 
     def groupnorm(self, x: View, y: Optional[View], gamma: int, beta: int, B: int, Lrows: int, G: int, silu: bool, tag: int = 0,
                   stats: int = 0, stats_col0: int = 0, stats_cg: int = 0, stats_G: int = 0) -> int:
@@ -389,7 +398,7 @@ class UNetCompiler:
             cov = W.cover(x) if fuse_norms else None
             if cov is not None:
                 for who, lo, hi in cov:
-                    if who != "audio" and not all(ops.sink_capable(i) for i in who):
+                    if who != "audio" and not all(ops.sink_capable(i) and ops.group_sink_ok(i) for i in who):
                         cov = None
                         break
             if cov is None:

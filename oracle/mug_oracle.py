@@ -333,7 +333,8 @@ def make_schedule(S: int, eta: float = 0.0, timesteps: int = 1000, linear_start:
     mug/diffusion/utils.py:16-40 (betas f64), diffusion.py:131-151 (alphas_cumprod -> f32),
     ddim.py:24-53 + utils.py:50-80 (uniform timesteps, alphas, alphas_prev, sigmas)."""
     betas = (torch.linspace(linear_start ** 0.5, linear_end ** 0.5, timesteps, dtype=torch.float64) ** 2).numpy()
-    alphas_cumprod = torch.tensor(np.cumprod(1.0 - betas, axis=0), dtype=torch.float32)
+    acp64 = np.cumprod(1.0 - betas, axis=0)
+    alphas_cumprod = torch.tensor(acp64, dtype=torch.float32)
     c = timesteps // S
     ddim_timesteps = np.asarray(list(range(0, timesteps, c))) + 1
     ac = alphas_cumprod  # float32 torch tensor indexed with numpy ints, as ddim.py does
@@ -341,16 +342,23 @@ def make_schedule(S: int, eta: float = 0.0, timesteps: int = 1000, linear_start:
     alphas_prev = np.asarray([ac[0]] + ac[ddim_timesteps[:-1]].tolist())
     sigmas = eta * np.sqrt((1 - alphas_prev) / (1 - alphas) * (1 - alphas / alphas_prev))
     return dict(timesteps=ddim_timesteps, alphas=alphas, alphas_prev=alphas_prev, sigmas=sigmas,
-                sqrt_one_minus_alphas=np.sqrt(1.0 - alphas), alphas_cumprod=alphas_cumprod)
+                sqrt_one_minus_alphas=np.sqrt(1.0 - alphas), alphas_cumprod=alphas_cumprod,
+                # q_sample tables: square roots taken in f64, then cast (diffusion.py:148-150)
+                sqrt_alphas_cumprod=torch.tensor(np.sqrt(acp64), dtype=torch.float32),
+                sqrt_one_minus_alphas_cumprod=torch.tensor(np.sqrt(1.0 - acp64), dtype=torch.float32))
 
 
 def ddim_sample(p: Params, S: int, c: torch.Tensor, w: Sequence[torch.Tensor], x_T: torch.Tensor,
                 scale: float = 1.0, uc: Optional[torch.Tensor] = None, eta: float = 0.0,
                 cfg: dict = DEFAULT_UNET, noise_gen: Optional[torch.Generator] = None,
-                return_eps: bool = False, noise_seq: Optional[Sequence[torch.Tensor]] = None, temperature: float = 1.0):
-    """DDIMSampler.ddim_sampling + p_sample_ddim  -- mug/diffusion/ddim.py:110-196 (mask=None path).
+                return_eps: bool = False, noise_seq: Optional[Sequence[torch.Tensor]] = None, temperature: float = 1.0,
+                mask: Optional[torch.Tensor] = None, x0: Optional[torch.Tensor] = None,
+                q_noise_seq: Optional[Sequence[torch.Tensor]] = None):
+    """DDIMSampler.ddim_sampling + p_sample_ddim  -- mug/diffusion/ddim.py:110-196.
     ``noise_seq[i]`` replaces the i-th ``noise_like`` draw (:192), already passed through ``dropout`` (:193-194) if any, so a
-    test can hand the exact per-step noise of another RNG stream to this restatement."""
+    test can hand the exact per-step noise of another RNG stream to this restatement.
+    ``mask`` / ``x0``: the inpainting blend of :140-143 with ``DDPM.q_sample`` (diffusion.py:327-333); ``q_noise_seq[i]`` replaces the
+    ``randn_like(x0)`` it draws in iteration i."""
     sch = make_schedule(S, eta)
     ts = sch["timesteps"]
     x = x_T
@@ -360,6 +368,11 @@ def ddim_sample(p: Params, S: int, c: torch.Tensor, w: Sequence[torch.Tensor], x
     for i, step in enumerate(np.flip(ts)):
         index = total - i - 1
         t = torch.full((B,), int(step), dtype=torch.long)
+        if mask is not None:
+            assert x0 is not None
+            qn = q_noise_seq[i] if q_noise_seq is not None else torch.randn(x0.shape, generator=noise_gen)
+            x_orig = sch["sqrt_alphas_cumprod"][t].view(-1, 1, 1) * x0 + sch["sqrt_one_minus_alphas_cumprod"][t].view(-1, 1, 1) * qn
+            x = x_orig * mask + (1. - mask) * x
         if uc is None or scale == 1.0:
             e_t = unet_forward(p, x, t, c, w, cfg)
         else:

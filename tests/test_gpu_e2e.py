@@ -256,3 +256,73 @@ def test_mask_branch_with_zero_mask_is_identity():
     z0, _ = sampler.sample(**kw)
     z1, _ = sampler.sample(mask=torch.zeros(B, 16, L).cuda(), x0=torch.ones(B, 16, L).cuda(), **kw)
     assert torch.equal(z0, z1)
+
+
+def test_mask_branch_matches_oracle_with_shared_noise():
+    """non-trivial inpainting mask (ddim.py:140-143): the first half of the chart is pinned to q_sample(x0, t) every step.  The
+    sampler's only RNG call per step at eta = 0 is q_sample's randn_like(x0) on the CUDA generator, so re-seeding and repeating
+    the draws hands the oracle the very same noise."""
+    L, B, S = 96, 2, 6
+    m = model_for(L)
+    inp = synth.synthetic_inputs(B, L)
+    sampler = DDIMSampler(m)
+    x0 = synth._gauss(synth._rng(31, "x0"), (B, 16, L))
+    mask = torch.zeros(B, 16, L)
+    mask[:, :, :L // 2] = 1.0
+    mask[1, 4:, L // 4:L // 2] = 0.5                                   # soft edge on one sample
+    torch.cuda.manual_seed(77)
+    z, _ = sampler.sample(S=S, c=inp["c"].cuda(), w=[w.cuda() for w in inp["w"]], batch_size=B, verbose=False, x_T=inp["x_T"].cuda(),
+                          eta=0.0, shape=(16, L), mask=mask.cuda(), x0=x0.cuda(), unconditional_guidance_scale=3.0,
+                          unconditional_conditioning=inp["uc"].cuda())
+    torch.cuda.manual_seed(77)
+    n_steps = len(range(0, 1000, 1000 // S))                           # S = 6 gives 7 DDIM steps (utils.py:52-63)
+    qseq = [torch.randn((B, 16, L), device="cuda").cpu() for _ in range(n_steps)]
+    with torch.no_grad():
+        ref = orc.ddim_sample(synth.synthetic_state_dict(L), S, inp["c"], inp["w"], inp["x_T"], scale=3.0, uc=inp["uc"], mask=mask, x0=x0,
+                              q_noise_seq=qseq)
+        plain = orc.ddim_sample(synth.synthetic_state_dict(L), S, inp["c"], inp["w"], inp["x_T"], scale=3.0, uc=inp["uc"])
+    assert rel_err(z, ref) < 2e-4
+    assert rel_err(plain, ref) > 1e-2                                  # the mask really changed the trajectory
+
+
+def test_config2_shape_ten_guided_steps_vs_live_oracle():
+    """BASELINE config 2's own shape -- 4 charts, z_length 512, CFG 5 -- for 10 DDIM steps against the LIVE CPU oracle (not another
+    GPU run), then decode and compare logits and note decisions"""
+    L, B, S = 512, 4, 10
+    sd = synth.synthetic_state_dict(L)
+    m = model_for(L)
+    m.z_length = L
+    inp = synth.synthetic_inputs(B, L, seed=404)
+    sampler = DDIMSampler(m)
+    z, _ = sampler.sample(S=S, c=inp["c"].cuda(), w=[w.cuda() for w in inp["w"]], batch_size=B, verbose=False, x_T=inp["x_T"].cuda(),
+                          eta=0.0, shape=(16, L), unconditional_guidance_scale=5.0, unconditional_conditioning=inp["uc"].cuda())
+    logits = m.model.decode(z)
+    with torch.no_grad():
+        z_ref = orc.ddim_sample(sd, S, inp["c"], inp["w"], inp["x_T"], scale=5.0, uc=inp["uc"])
+        l_ref = orc.decoder_forward(sd, z_ref)
+    ez, el = rel_err(z, z_ref), rel_err(logits, l_ref)
+    print(f"config2 shape: z {ez:.2e} logits {el:.2e}")
+    assert ez < 1e-3 and el < 1e-3
+    rows = [0, 1, 2, 3, 8, 9, 10, 11]                                  # note-on / hold channels (convertor.py:211-264)
+    flips = ((logits.cpu()[:, rows] > 0) != (l_ref[:, rows] > 0))
+    assert (l_ref[:, rows][flips].abs() <= 1e-3 * l_ref.abs().max()).all(), "a note decision flipped away from logit ~ 0"
+
+
+def test_long_chart_guided_trajectory_and_decode_vs_live_oracle():
+    """BASELINE config 5's length (6-min audio, z_length 992 -> levels 992/496/248/124): 5 guided steps of 2 charts + decode against the
+    live CPU oracle"""
+    L, B, S = 992, 2, 5
+    sd = synth.synthetic_state_dict(L)
+    m = model_for(L)
+    m.z_length = L
+    inp = synth.synthetic_inputs(B, L, seed=992)
+    sampler = DDIMSampler(m)
+    z, _ = sampler.sample(S=S, c=inp["c"].cuda(), w=[w.cuda() for w in inp["w"]], batch_size=B, verbose=False, x_T=inp["x_T"].cuda(),
+                          eta=0.0, shape=(16, L), unconditional_guidance_scale=5.0, unconditional_conditioning=inp["uc"].cuda())
+    logits = m.model.decode(z)
+    with torch.no_grad():
+        z_ref = orc.ddim_sample(sd, S, inp["c"], inp["w"], inp["x_T"], scale=5.0, uc=inp["uc"])
+        l_ref = orc.decoder_forward(sd, z_ref)
+    ez, el = rel_err(z, z_ref), rel_err(logits, l_ref)
+    print(f"L=992: z {ez:.2e} logits {el:.2e}")
+    assert ez < 1e-3 and el < 1e-3

@@ -111,7 +111,8 @@ def test_unet_plan_compiles_and_is_consistent(packed, Beff, Lz, fuse):
         assert kinds.count(L_.OP_LAYERNORM) == 0 and sum(1 for g in gemms if g.ln_stats) == 48
         assert sum(1 for g in gemms for k in range(2) if g.sink[k].kind == 2) == 48
         # every GroupNorm whose input comes from tensor-core GEMMs (all but the two fed by conv_in, K = 16) applies in one pass
-        assert sum(1 for g in gns if g.stats) == 75 and len(res["audio_stats"]) == 7
+        # (levels shorter than 43 rows pack 3+ samples into a 128-row tile: there the stand-alone kernel stays)
+        assert sum(1 for g in gns if g.stats) == (75 if Lz >= 512 else 32) and len(res["audio_stats"]) == (7 if Lz >= 512 else 3)
         assert kinds[0] == L_.OP_COPY2D and kinds.count(L_.OP_COPY2D) == 5   # first op re-arms the statistics block
         for g in gemms:
             for k in range(2):

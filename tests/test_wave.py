@@ -91,3 +91,20 @@ def test_gpu_request_path_mel_to_hit_objects():
     assert rel(z, z_ref) < 1e-3
     ref_lines = orc.array_to_objects(lg_ref[0].numpy(), 4, 46.439909297052154)
     assert len(set(lines[0]) & set(ref_lines)) >= 0.97 * len(ref_lines)
+
+
+@pytest.mark.gpu
+def test_gpu_wave_encoder_three_minute_audio_vs_live_oracle():
+    """the 3-minute shape the sampler's headline config runs on (T = 64 * 512 = 32768 mel frames -> w[-4:] at 512/256/128/64),
+    against the live CPU oracle (itself pinned to the reference at T = 6144)"""
+    from mug_diffusion_b200.sampler import MugDiffusionB200
+    T = 64 * 512
+    sd = {**synth.synthetic_state_dict(512), **wave.synthetic_wave_state_dict()}
+    mel = wave.synthetic_mel(1, T, seed=5)
+    m = MugDiffusionB200.from_state_dict(sd, z_length=512)
+    hs = m.model.wave_model(mel.cuda())
+    with torch.no_grad():
+        ref = worc.wave_forward(sd, mel)
+    assert [tuple(h.shape) for h in hs[6:]] == [(1, 256, 512), (1, 512, 256), (1, 512, 128), (1, 512, 64)]
+    for i in range(6, 10):
+        assert rel(hs[i], ref[i]) < 1e-4
