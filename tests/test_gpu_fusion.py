@@ -61,7 +61,7 @@ def test_group_moment_sinks(R, B, L, Cin, Cout, Ctot, col0, split):
         exp[:, gi, 0] += o[:, c].sum(-1)
         exp[:, gi, 1] += (o[:, c] ** 2).sum(-1)
     got = stats.cpu()
-    assert float((got - exp).abs().max() / exp.abs().max()) < 1e-9
+    assert float((got - exp).abs().max() / exp.abs().max()) < 1e-7       # (a float4's four values are added in fp32 first)
 
 
 @pytest.mark.parametrize("B,L,K,N,split", [(4, 124, 512, 384, 0), (8, 64, 512, 512, 3), (2, 496, 256, 256, 0)])
@@ -85,7 +85,7 @@ def test_group_moment_sinks_on_a_1x1(R, B, L, K, N, split):
     assert rel_err(out, ref) < 1e-5
     o = out.cpu().double().view(B, L, G, cg)
     exp = torch.stack([o.sum((1, 3)), (o ** 2).sum((1, 3))], dim=-1)
-    assert float((stats.cpu() - exp).abs().max() / exp.abs().max()) < 1e-9
+    assert float((stats.cpu() - exp).abs().max() / exp.abs().max()) < 1e-7
 
 
 @pytest.mark.parametrize("M,K,N,split", [(1024, 256, 256, 0), (512, 512, 512, 4), (300, 384, 384, 0), (2048, 128, 64, 0), (640, 256, 512, 2)])

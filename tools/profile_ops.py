@@ -23,10 +23,11 @@ def signature(op):
     k = op.kind
     if k == L_.OP_GEMM:
         g = op.u.gemm
-        return ("gemm", g.M, g.N, g.K, g.taps, g.conv_mode, g.gate, g.act, int(bool(g.residual)), int(bool(g.rowvec)))
+        return ("gemm", g.M, g.N, g.K, g.taps, g.conv_mode, g.gate, g.act, int(bool(g.residual)), int(bool(g.rowvec)), f"K2={g.K2}",
+                f"sinks={g.sink[0].kind}{g.sink[1].kind}", f"ln={int(bool(g.ln_stats))}")
     if k == L_.OP_GROUPNORM:
         g = op.u.gn
-        return ("groupnorm", g.B, g.L, g.C, g.G, g.silu)
+        return ("groupnorm", g.B, g.L, g.C, g.G, g.silu, f"stats={int(bool(g.stats))}")
     if k == L_.OP_LAYERNORM:
         g = op.u.ln
         return ("layernorm", g.rows, g.C)
@@ -46,10 +47,11 @@ def main():
     ap.add_argument("--nocfg", action="store_true")
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--gemm", default="auto")
+    ap.add_argument("--fuse", type=int, default=1, help="0: stand-alone GroupNorm / LayerNorm kernels")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     cfg = ModelConfig()
-    model = MugDiffusionB200(synth.synthetic_state_dict(a.L), cfg, z_length=a.L, device=dev, gemm_impl=a.gemm)
+    model = MugDiffusionB200(synth.synthetic_state_dict(a.L), cfg, z_length=a.L, device=dev, gemm_impl=a.gemm, fuse_norms=bool(a.fuse))
     eng = model.engine
     Beff = a.B if a.nocfg else 2 * a.B
     sess = eng.session(Beff, a.L, per_sample_t=False)
@@ -81,7 +83,7 @@ def main():
             g = arr[idx[0]].u.gemm
             try:
                 eng.lib.mugd_gemm_tc_query(eng.handle, C.byref(g), 148, C.byref(ok), C.byref(sp), None, C.byref(nt))
-                extra = f"tc={ok.value} tiles={nt.value} split={sp.value} TF/s={2.0*g.M*g.N*g.K*g.taps/us/1e6:.0f}"
+                extra = f"tc={ok.value} tiles={nt.value} split={sp.value} TF/s={2.0*g.M*g.N*(g.K*g.taps+g.K2)/us/1e6:.0f}"
             except Exception as e:       # noqa: BLE001
                 extra = str(e)
         rows.append((us * len(idx), len(idx), us, launches, sig, extra))
