@@ -250,7 +250,7 @@ def build_model(L, world, rank, dev, gemm):
         blob = broadcast_blob(sd, cfg, dev)
         return MugDiffusionB200(None, cfg, z_length=L, device=dev, gemm_impl=gemm, blob=blob), sd
     sd = synth.synthetic_state_dict(L)
-    return MugDiffusionB200(sd, cfg, z_length=L, device=dev, gemm_impl=gemm), sd
+    return MugDiffusionB200(sd, cfg, z_length=L, device=dev, gemm_impl=gemm, fold_ln={"0": False, "1": True}.get(os.environ.get("MUGD_FOLD_LN", ""))), sd
 
 
 def measure(model, name, wl, steps, warmup, world, rank, dev, with_roofline=True, sustain=True):

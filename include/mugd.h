@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MUGD_ABI_VERSION 9
+#define MUGD_ABI_VERSION 10
 
 typedef struct mugd_handle mugd_handle;   /* one device + scratch state            */
 typedef struct mugd_plan mugd_plan;       /* validated launch plan (+ CUDA graph)  */
@@ -72,19 +72,6 @@ enum mugd_gate { MUGD_GATE_NONE = 0, MUGD_GATE_GEGLU = 1 /* a*gelu(g), attention
 enum mugd_gemm_impl { MUGD_GEMM_AUTO = 0, MUGD_GEMM_SIMT = 1 /* exact fp32 FMA */,
                       MUGD_GEMM_TC = 2 /* tcgen05 3xTF32 split, fp32 accumulate in TMEM */ };
 
-/* Statistics sink of a producer: while a GEMM writes its output it also accumulates the moments a LATER normalisation needs, so
- * that GroupNorm / LayerNorm no longer read their input twice (or at all).  fp64 atomics into a buffer that the plan resets at the
- * start of every evaluation (MUGD_OP_COPY2D from a `base` image: zeros, plus the moments of step-invariant columns such as the
- * audio features of AudioConcatBlock, unet.py:114-118).
- *   kind 1 (GroupNorm, models.py:10-13): buf[(b*G + (col0 + n) / cg) * 2 + {0,1}] += {x, x^2}  for output column n of sample b
- *   kind 2 (LayerNorm, attention.py:136-138): buf[m * 2 + {0,1}] += {x, x^2}  for every column of output row m            */
-typedef struct mugd_stat_sink {
-    double* buf;
-    int32_t kind;                          /* 0 = none                                                      */
-    int32_t col0;                          /* kind 1: channel of output column 0 inside the normalised tensor (concat offset) */
-    int32_t cg, G;                         /* kind 1: channels per group, groups                            */
-} mugd_stat_sink;
-
 typedef struct mugd_gemm {
     const float* A;  int64_t lda;          /* [B*Lin, K] activations                                       */
     const float* W;                        /* [N][taps*K], K-major per tap (conv weight [Cout][k][Cin])    */
@@ -112,12 +99,15 @@ typedef struct mugd_gemm {
      * block (attention.py:57-65,194-199) with the packer-composed weight.  NULL / 0 = single source. */
     const float* A2; int64_t lda2;         /* [B*Lout, K2]                                                 */
     int32_t K2; int32_t reserved_;
-    /* statistics of the OUTPUT for later norms (tensor-core path, act == gate == NONE only) */
-    mugd_stat_sink sink[2];
+    /* Row moments of the OUTPUT for a LayerNorm that follows (tensor-core path, act == gate == NONE only): while the tile is stored,
+     * row_moments[m*2 + {0,1}] += {sum, sum of squares} of the columns of output row m (fp64 atomics; the plan zeroes the buffer at
+     * the start of every evaluation).  Round 2 also built GroupNorm-moment sinks + a single-pass apply kernel; they lost at every batch
+     * size (profiles/r02_norm_fusion_ab.md) and were removed. */
+    double* row_moments;
     /* LayerNorm folded into this GEMM (attention.py:147-151: norm_i followed by a Linear): with W' = W diag(gamma) packed as the
      * weight, colsum[n] = sum_k W'[n][k] and bias' = W beta + b,   C = rstd_m * (A W'^T - mean_m * colsum) + bias'   where mean_m,
-     * rstd_m come from the row moments ln_stats[m*2 + {0,1}] = {sum, sum of squares} over the K channels of A's row m (a kind-2
-     * sink of A's producer).  The normalised tensor is never materialised.  NULL = plain GEMM. */
+     * rstd_m come from the row moments ln_stats[m*2 + {0,1}] = {sum, sum of squares} over the K channels of A's row m (the row_moments
+     * of A's producer).  The normalised tensor is never materialised.  NULL = plain GEMM. */
     const double* ln_stats; const float* ln_colsum; float ln_eps; int32_t reserved2_;
 } mugd_gemm;
 
@@ -125,10 +115,6 @@ typedef struct mugd_groupnorm {
     const float* x; int64_t ldx; float* y; int64_t ldy;
     const float* gamma; const float* beta;
     int32_t B, L, C, G; float eps; int32_t silu;
-    /* stats != NULL: the moments were accumulated by the producers of x (mugd_stat_sink kind 1, [B][G][2] doubles): single-pass
-     * apply.  y == NULL with stats != NULL: only ACCUMULATE the moments of x into stats (used once per request for step-invariant
-     * columns); gamma/beta are ignored.  stats_col0 / stats_cg / stats_G place x's columns inside the normalised tensor. */
-    double* stats; int32_t stats_col0, stats_cg, stats_G, reserved_;
 } mugd_groupnorm;
 
 typedef struct mugd_layernorm {

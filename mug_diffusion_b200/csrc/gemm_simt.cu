@@ -251,8 +251,8 @@ int launch_gemm(const DeviceInfo& dev, const mugd_gemm& g, int default_impl, cud
         if (gemm_tc_supported(g)) return launch_gemm_tc(dev, g, st, launches);
         MUGD_REQUIRE(g.impl != MUGD_GEMM_TC, "gemm: tensor-core path requested but shape unsupported (M=%d N=%d K=%d)", g.M, g.N, g.K);
     }
-    MUGD_REQUIRE(!g.sink[0].kind && !g.sink[1].kind && !g.ln_stats,
-                 "gemm: statistics sinks / folded LayerNorm exist on the tensor-core path only (M=%d N=%d K=%d fell to the FFMA kernel)", g.M, g.N, g.K);
+    MUGD_REQUIRE(!g.row_moments && !g.ln_stats,
+                 "gemm: the row-moment sink / folded LayerNorm exist on the tensor-core path only (M=%d N=%d K=%d fell to the FFMA kernel)", g.M, g.N, g.K);
     GemmParams p;
     p.g = g;
     p.nk = (g.taps * g.K + g.K2) / SG_BK;

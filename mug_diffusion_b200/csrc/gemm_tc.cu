@@ -7,7 +7,7 @@
 
 namespace mugd {
 
-template <int BN>
+template <int BN, int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmWhi,
@@ -40,7 +40,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // the producer warp waits for the previous kernel (griddepcontrol.wait) before its first activation load; every other
     // global access of this kernel (epilogue) is ordered behind data that went through that load
     if (warp != 0) pdl_wait();
-    gemm_tc_tile<BN, true>(&tmA, &tmA1, &tmA2, &tmB, &tmWhi, &tmWlo, p, blockIdx.x, blockIdx.y, blockIdx.z, base, tmem_base);
+    gemm_tc_tile<BN, true, EPI>(&tmA, &tmA1, &tmA2, &tmB, &tmWhi, &tmWlo, p, blockIdx.x, blockIdx.y, blockIdx.z, base, tmem_base);
     // ---- teardown (all tcgen05.ld completed before the phase-2 barrier inside the tile function) ----
     __syncthreads();
     if (warp == 2) {
@@ -50,11 +50,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // split-K second pass: fully parallel over the GPU and L2-resident (see tc_reduce_rows).
-template <int BN>
+template <int BN, int EPI>
 __global__ void __launch_bounds__(TC_THREADS)
 gemm_tc_reduce_kernel(const __grid_constant__ TcParams p) {
     pdl_wait();
-    tc_reduce_block<BN>(p, blockIdx.x);
+    tc_reduce_block<BN, EPI>(p, blockIdx.x);
 }
 
 #ifdef MUGD_TC_TIMELINE
@@ -99,27 +99,14 @@ bool gemm_tc_supported(const mugd_gemm& g) {
     return true;
 }
 
-// statistics sinks and the folded LayerNorm exist on the tensor-core path only
+// the row-moment sink and the folded LayerNorm exist on the tensor-core path only
 static int tc_validate_fusions(const mugd_gemm& g) {
-    const bool sinks = g.sink[0].kind != 0 || g.sink[1].kind != 0;
-    if (sinks) {
-        MUGD_REQUIRE(g.act == MUGD_ACT_NONE && g.gate == MUGD_GATE_NONE && !g.ln_stats, "gemm: statistics sinks need act == gate == NONE and no folded LayerNorm");
-        for (int k = 0; k < 2; ++k) {
-            const mugd_stat_sink& s = g.sink[k];
-            MUGD_REQUIRE(s.kind >= 0 && s.kind <= 2, "gemm: sink kind %d", s.kind);
-            if (s.kind) MUGD_REQUIRE(s.buf && (reinterpret_cast<uintptr_t>(s.buf) & 7u) == 0, "gemm: sink buffer");
-            if (s.kind == 1) {
-                MUGD_REQUIRE(s.cg > 0 && s.cg % 4 == 0 && s.col0 % 4 == 0 && s.G > 0 && s.col0 + g.N <= s.cg * s.G,
-                             "gemm: group sink geometry (col0=%d cg=%d G=%d N=%d)", s.col0, s.cg, s.G, g.N);
-                const int lrows = g.conv_mode == MUGD_CONV_NONE ? g.M : g.Lout;       // rows per sample as the tiles see them
-                MUGD_REQUIRE(g.conv_mode != MUGD_CONV_NONE && (lrows >= TC_BM || TC_BM / lrows <= 2),
-                             "gemm: group sinks need a conv-mode row structure with at most two samples per 128-row tile (Lout=%d)", g.Lout);
-            }
-        }
-    }
+    if (g.row_moments)
+        MUGD_REQUIRE(g.act == MUGD_ACT_NONE && g.gate == MUGD_GATE_NONE && !g.ln_stats && (reinterpret_cast<uintptr_t>(g.row_moments) & 15u) == 0,
+                     "gemm: row_moments needs act == gate == NONE, no folded LayerNorm and a 16-byte aligned buffer");
     if (g.ln_stats) {
-        MUGD_REQUIRE(g.ln_colsum && aligned16(g.ln_colsum) && g.taps == 1 && g.K2 == 0 && g.act == MUGD_ACT_NONE &&
-                         (g.gate == MUGD_GATE_NONE || g.gate == MUGD_GATE_GEGLU) && !g.rowvec,
+        MUGD_REQUIRE(g.ln_colsum && aligned16(g.ln_colsum) && (reinterpret_cast<uintptr_t>(g.ln_stats) & 15u) == 0 && g.taps == 1 && g.K2 == 0 &&
+                         g.act == MUGD_ACT_NONE && (g.gate == MUGD_GATE_NONE || g.gate == MUGD_GATE_GEGLU) && !g.rowvec,
                      "gemm: folded LayerNorm needs a single-source Linear with act NONE and gate NONE/GEGLU");
     }
     return MUGD_OK;
@@ -247,6 +234,7 @@ int tc_plan(const DeviceInfo& dev, const mugd_gemm& g, TcPlanned* out) {
     p.tiles_per_sample = t.tiles_per_sample;
     p.single_pass = dev.tc_single_pass ? 1 : 0;
     p.BN = t.BN;
+    p.ln_invK = 1.0 / (double)g.K;
     p.gx = t.gx;
     p.gy = t.gy;
 #ifdef MUGD_TC_TIMELINE
@@ -255,28 +243,52 @@ int tc_plan(const DeviceInfo& dev, const mugd_gemm& g, TcPlanned* out) {
     return MUGD_OK;
 }
 
-template <int BN>
+template <int BN, int EPI>
 static int tc_launch(const TcPlanned& pl, cudaStream_t st) {
+    const TcParams& p = pl.p;
+    if (p.splits > 1) {
+        // the main kernel only writes partial tiles: it runs the smallest instantiation, the epilogue variant lives in the reduce
+        static bool configured = false;
+        if (!configured) {
+            MUGD_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, TC_E_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcSmem<BN>::TOTAL));
+            configured = true;
+        }
+        MUGD_CHECK_CUDA(launch_k(gemm_tc_kernel<BN, TC_E_NONE>, dim3(p.gx, p.gy, p.splits), dim3(TC_THREADS), TcSmem<BN>::TOTAL, st, pl.maps[0],
+                                 pl.maps[1], pl.maps[2], pl.maps[3], pl.maps[4], pl.maps[5], p));
+        MUGD_CHECK_CUDA(launch_k(gemm_tc_reduce_kernel<BN, EPI>, dim3((unsigned)(p.gx * p.gy * TcReduceGeom<BN>::BPT)), dim3(TC_THREADS), 0, st, p));
+        return MUGD_OK;
+    }
     static bool configured = false;
     if (!configured) {
-        MUGD_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcSmem<BN>::TOTAL));
+        MUGD_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcSmem<BN>::TOTAL));
         configured = true;
     }
-    const TcParams& p = pl.p;
-    MUGD_CHECK_CUDA(launch_k(gemm_tc_kernel<BN>, dim3(p.gx, p.gy, p.splits), dim3(TC_THREADS), TcSmem<BN>::TOTAL, st, pl.maps[0], pl.maps[1],
+    MUGD_CHECK_CUDA(launch_k(gemm_tc_kernel<BN, EPI>, dim3(p.gx, p.gy, 1), dim3(TC_THREADS), TcSmem<BN>::TOTAL, st, pl.maps[0], pl.maps[1],
                              pl.maps[2], pl.maps[3], pl.maps[4], pl.maps[5], p));
-    if (p.splits > 1)
-        MUGD_CHECK_CUDA(launch_k(gemm_tc_reduce_kernel<BN>, dim3((unsigned)(p.gx * p.gy * TcReduceGeom<BN>::BPT)), dim3(TC_THREADS), 0, st, p));
     return MUGD_OK;
+}
+
+template <int BN>
+static int tc_launch_bn(const TcPlanned& pl, cudaStream_t st) {
+    switch (tc_epi_of(pl.p.g)) {
+        case TC_E_GEGLU: return tc_launch<BN, TC_E_GEGLU>(pl, st);
+        case TC_E_GLU: return tc_launch<BN, TC_E_GLU>(pl, st);
+        case TC_E_SILU: return tc_launch<BN, TC_E_SILU>(pl, st);
+        case TC_E_GELU: return tc_launch<BN, TC_E_GELU>(pl, st);
+        case TC_E_SINK: return tc_launch<BN, TC_E_SINK>(pl, st);
+        case TC_E_LN: return tc_launch<BN, TC_E_LN>(pl, st);
+        case TC_E_LN_GEGLU: return tc_launch<BN, TC_E_LN_GEGLU>(pl, st);
+        default: return tc_launch<BN, TC_E_NONE>(pl, st);
+    }
 }
 
 int launch_gemm_tc(const DeviceInfo& dev, const mugd_gemm& g, cudaStream_t st, int* launches) {
     TcPlanned pl;
     int rc = tc_plan(dev, g, &pl);
     if (rc != MUGD_OK) return rc;
-    if (pl.p.BN == 256) rc = tc_launch<256>(pl, st);
-    else if (pl.p.BN == 128) rc = tc_launch<128>(pl, st);
-    else rc = tc_launch<64>(pl, st);
+    if (pl.p.BN == 256) rc = tc_launch_bn<256>(pl, st);
+    else if (pl.p.BN == 128) rc = tc_launch_bn<128>(pl, st);
+    else rc = tc_launch_bn<64>(pl, st);
     if (rc != MUGD_OK) return rc;
     if (launches) *launches += pl.p.splits > 1 ? 2 : 1;
     return MUGD_OK;

@@ -46,6 +46,7 @@ struct TcParams {
     int32_t tiles_per_sample; // when Lrows >= 128
     int32_t single_pass;      // 1: plain TF32 (a_hi*w_hi only, ~2^-11 relative) -- opt-in speed mode, NOT used for parity/bench
     int32_t BN, gx, gy;       // tile width and tile grid (gx column tiles x gy row tiles x splits)
+    double ln_invK;           // 1 / K (folded LayerNorm: moments -> mean / variance)
 #ifdef MUGD_TC_TIMELINE
     long long* dbg;           // CTA (0,0,0) writes globaltimer stamps (tools/gemm_timeline.py)
 #endif
@@ -188,74 +189,12 @@ struct TcSmem {
     static_assert(128u * (BN + 4) * 4u + 1024u <= TILE_BYTES, "the staged accumulator tile + row statistics must fit the pipeline buffers");
 };
 
-// ---- statistics sinks (mugd_stat_sink): moments of the OUTPUT for the norm that follows, accumulated while it is written ----
-// Group moments (kind 1).  A thread's column quad -- hence its group -- is fixed for the whole tile; it keeps fp64 (sum, sum of
-// squares) of the float4s it stores, separately for the (at most two) samples a 128-row tile can hold.  tc_group_flush() then
-// reduces inside the CTA (threads that share a column quad, then quads that share a group) and issues ONE fp64 reduction per
-// (sample, group) of the tile: per-thread atomics on the few [B][G] addresses serialise in L2 (measured: +0.7 ms per step).
-struct TcGroupAcc {
-    double s0, ss0, s1, ss1;               // sample-in-tile 0 / 1
-    __device__ __forceinline__ void reset() { s0 = ss0 = s1 = ss1 = 0.0; }
-    __device__ __forceinline__ void add(int si, float4 v) {
-        const double s = (double)((v.x + v.y) + (v.z + v.w));
-        const double ss = (double)((v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w));
-        if (si == 0) { s0 += s; ss0 += ss; } else { s1 += s; ss1 += ss; }
-    }
-};
-// scratch: double2 P[2 sinks][2 samples][TC_THREADS] at `scratch` (shared memory, 16 KB), free at this point.  C4 = column quads of
-// the tile (threads tid, tid + C4, ... share a quad); n0 = first column of the tile; b0 = first sample of the tile.
-template <int C4>
-__device__ __forceinline__ void tc_group_flush(const mugd_gemm& g, const TcGroupAcc* ga, uint32_t scratch, int n0, int b0, int nsamp) {
-    const int tid = (int)threadIdx.x;
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-        if (g.sink[k].kind != 1) continue;
-        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(scratch + (uint32_t)(((k * 2 + 0) * TC_THREADS + tid) * 16)), "d"(ga[k].s0), "d"(ga[k].ss0) : "memory");
-        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(scratch + (uint32_t)(((k * 2 + 1) * TC_THREADS + tid) * 16)), "d"(ga[k].s1), "d"(ga[k].ss1) : "memory");
-    }
-    __syncthreads();
-    // stage 1: thread (k, si, c4) sums the TC_THREADS / C4 threads that share column quad c4 (fixed order -> deterministic per tile)
-    const int c4 = tid % C4, which = tid / C4;                    // which = k * 2 + si, needs 4 * C4 <= TC_THREADS
-    double s = 0.0, ss = 0.0;
-    if (which < 4 && g.sink[which >> 1].kind == 1) {
-#pragma unroll 4
-        for (int j = 0; j < TC_THREADS / C4; ++j) {
-            double a, b;
-            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(scratch + (uint32_t)((which * TC_THREADS + c4 + j * C4) * 16)));
-            s += a; ss += b;
-        }
-    }
-    __syncthreads();
-    if (which < 4)
-        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(scratch + (uint32_t)((which * TC_THREADS + c4) * 16)), "d"(s), "d"(ss) : "memory");
-    __syncthreads();
-    // stage 2: the first quad of every group in this tile sums the quads of its group and issues the reduction
-    if (which < 4 && g.sink[which >> 1].kind == 1) {
-        const mugd_stat_sink& k = g.sink[which >> 1];
-        const int si = which & 1;
-        const int nn = n0 + c4 * 4;
-        if (si < nsamp && nn < g.N) {
-            const int grp = (k.col0 + nn) / k.cg;
-            const bool leader = c4 == 0 || (k.col0 + nn - 4) / k.cg != grp;
-            if (leader) {
-                double ts = 0.0, tss = 0.0;
-                for (int q = c4; q < C4 && n0 + q * 4 < g.N && (k.col0 + n0 + q * 4) / k.cg == grp; ++q) {
-                    double a, b;
-                    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(scratch + (uint32_t)((which * TC_THREADS + q) * 16)));
-                    ts += a; tss += b;
-                }
-                double* d = k.buf + ((int64_t)(b0 + si) * k.G + grp) * 2;
-                atomicAdd(d, ts);
-                atomicAdd(d + 1, tss);
-            }
-        }
-    }
-}
-// Row moments (kind 2, LayerNorm of the consumer): the SEG lanes that hold one output row of this tile reduce with shuffles (fp32: at
+// ---- row moments of the OUTPUT for the LayerNorm that follows, accumulated while the tile is written (mugd_gemm.row_moments) ----
+// The SEG lanes that hold one output row of this tile reduce with shuffles (fp32: at
 // most 128 values), the segment leader adds the tile's share of the row to the row's two doubles -- one address per row, so no
 // contention.  Every lane of the warp must call it (inactive: v = 0, m < 0).
 template <int SEG>
-__device__ __forceinline__ void tc_row_sink(const mugd_stat_sink& k, int m, float4 v) {
+__device__ __forceinline__ void tc_row_sink(double* buf, int m, float4 v) {
     float s = (v.x + v.y) + (v.z + v.w);
     float ss = (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
 #pragma unroll
@@ -264,27 +203,34 @@ __device__ __forceinline__ void tc_row_sink(const mugd_stat_sink& k, int m, floa
         ss += __shfl_xor_sync(0xffffffffu, ss, o);
     }
     if ((threadIdx.x & (SEG - 1)) == 0 && m >= 0) {
-        atomicAdd(k.buf + (int64_t)m * 2, (double)s);
-        atomicAdd(k.buf + (int64_t)m * 2 + 1, (double)ss);
+        atomicAdd(buf + (int64_t)m * 2, (double)s);
+        atomicAdd(buf + (int64_t)m * 2 + 1, (double)ss);
     }
 }
-// mean / rstd of a row from its two moments (LayerNorm folded into the GEMM, mugd_gemm.ln_stats)
-__device__ __forceinline__ float2 tc_ln_row(const double* st, int m, int K, float eps) {
-    const double s = st[(int64_t)m * 2], ss = st[(int64_t)m * 2 + 1];
-    const double mean = s / (double)K;
-    double var = ss / (double)K - mean * mean;
-    if (var < 0.0) var = 0.0;
-    return make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+// mean / rstd of a row from its two moments (LayerNorm folded into the GEMM, mugd_gemm.ln_stats).  The variance is formed in fp64
+// (E[x^2] - mean^2 cancels), the reciprocal square root in fp32 with one Newton step (~1 ulp): a handful of instructions instead of the
+// ~100-deep fp64 divide / sqrt chains, which sat on the critical path between the main loop and the epilogue.
+__device__ __forceinline__ float2 tc_ln_from_moments(double s, double ss, double invK, float eps) {
+    const double mean = s * invK;
+    double var = ss * invK - mean * mean;
+    const float v = fmaxf((float)var, 0.f) + eps;
+    float r = rsqrtf(v);
+    r = r * (1.5f - 0.5f * v * r * r);
+    return make_float2((float)mean, r);
+}
+__device__ __forceinline__ float2 tc_ln_row(const double* st, int m, double invK, float eps) {
+    const double2 mo = *reinterpret_cast<const double2*>(st + (int64_t)m * 2);
+    return tc_ln_from_moments(mo.x, mo.y, invK, eps);
 }
 
 // epilogue modes of a tile / reduce pass
-constexpr int TC_EPI_PLAIN = 0, TC_EPI_SINK = 1 /* act == gate == NONE + statistics sinks */, TC_EPI_LN = 2 /* LayerNorm folded in */;
+constexpr int TC_EPI_PLAIN = 0, TC_EPI_SINK = 1 /* act == gate == NONE + row moments of the output */, TC_EPI_LN = 2 /* LayerNorm folded in */;
 
 // Fused epilogue math on 4 consecutive accumulator columns.  ACT / GATE are compile-time so that the compiler
 // cannot if-convert the branches into "compute SiLU, GELU and both gates for every element, then select"
 // (which it did, costing ~4 us per tile); callers dispatch once per tile on the (uniform) act/gate values.
 // LNF: acc is A W'^T of the un-normalised rows; (acc - mean*colsum)*rstd is the product with the LayerNorm'd rows.
-// Returns the stored float4 (GATE_NONE) for the statistics sinks.
+// Returns the stored float4 (GATE_NONE) for the row-moment sink.
 template <int ACT, int GATE, bool LNF>
 __device__ __forceinline__ float4 tc_finish4(const mugd_gemm& g, float4 acc, float4 bia, float4 rvv, float4 res, float4 cs, float2 ln, int m, int nn) {
     float x[4];
@@ -324,13 +270,11 @@ __device__ __forceinline__ float4 tc_finish4(const mugd_gemm& g, float4 acc, flo
 // MODE = TC_EPI_LN reads the (mean, rstd) of tile row r from shared memory at rowstat + 8*r (written in phase 1).
 template <int BN, int ACT, int GATE, int MODE>
 __device__ __forceinline__ void tc_store_tile(const mugd_gemm& g, uint32_t stage, int m_base, int n0, int rows_valid, const float* rowvec,
-                                              uint32_t rowstat, int Lrows) {
+                                              uint32_t rowstat) {
     constexpr int SP = BN + 4;
     constexpr int C4 = BN / 4;
     constexpr int U = 8;
     constexpr int SEG = C4 < 32 ? C4 : 32;
-    TcGroupAcc ga[2];
-    if constexpr (MODE == TC_EPI_SINK) { ga[0].reset(); ga[1].reset(); }
 #pragma unroll 1
     for (int i0 = 0; i0 < TC_BM * C4; i0 += TC_THREADS * U) {
         float4 acc[U], bia[U], rvv[U], res[U], cs[U];
@@ -363,36 +307,34 @@ __device__ __forceinline__ void tc_store_tile(const mugd_gemm& g, uint32_t stage
             const int m = m_base + row;
             float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
             if (ok[u]) o = tc_finish4<ACT, GATE, MODE == TC_EPI_LN>(g, acc[u], bia[u], rvv[u], res[u], cs[u], ln[u], m, n0 + c4 * 4);
-            if constexpr (MODE == TC_EPI_SINK) {
-                const int si = row >= Lrows ? 1 : 0;               // a 128-row tile holds at most two samples when group sinks are on
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    if (g.sink[k].kind == 1) { if (ok[u]) ga[k].add(si, o); }
-                    else if (g.sink[k].kind == 2) tc_row_sink<SEG>(g.sink[k], ok[u] ? m : -1, o);     // (warp-uniform branch)
-                }
-            }
-        }
-    }
-    if constexpr (MODE == TC_EPI_SINK) {
-        if (g.sink[0].kind == 1 || g.sink[1].kind == 1) {
-            __syncthreads();                                          // every thread is done reading the staged tile
-            tc_group_flush<C4>(g, ga, stage, n0, m_base / g.Lout, (rows_valid + Lrows - 1) / Lrows);
+            if constexpr (MODE == TC_EPI_SINK) tc_row_sink<SEG>(g.row_moments, ok[u] ? m : -1, o);
         }
     }
 }
 
-#define TC_DISPATCH_EPI(g, CALL)                                                                      \
-    do {                                                                                              \
-        if ((g).ln_stats) {                                                                           \
-            if ((g).gate == MUGD_GATE_GEGLU) { CALL(MUGD_ACT_NONE, MUGD_GATE_GEGLU, TC_EPI_LN); }     \
-            else { CALL(MUGD_ACT_NONE, MUGD_GATE_NONE, TC_EPI_LN); }                                  \
-        } else if ((g).sink[0].kind | (g).sink[1].kind) { CALL(MUGD_ACT_NONE, MUGD_GATE_NONE, TC_EPI_SINK); } \
-        else if ((g).gate == MUGD_GATE_GEGLU) { CALL(MUGD_ACT_NONE, MUGD_GATE_GEGLU, TC_EPI_PLAIN); } \
-        else if ((g).gate == MUGD_GATE_GLU) { CALL(MUGD_ACT_NONE, MUGD_GATE_GLU, TC_EPI_PLAIN); }     \
-        else if ((g).act == MUGD_ACT_SILU) { CALL(MUGD_ACT_SILU, MUGD_GATE_NONE, TC_EPI_PLAIN); }     \
-        else if ((g).act == MUGD_ACT_GELU) { CALL(MUGD_ACT_GELU, MUGD_GATE_NONE, TC_EPI_PLAIN); }     \
-        else { CALL(MUGD_ACT_NONE, MUGD_GATE_NONE, TC_EPI_PLAIN); }                                   \
-    } while (0)
+// Epilogue variant of a kernel instantiation.  Every variant is its own kernel (template parameter), so a launch only carries the
+// store loop it executes: with all eight variants inlined in one kernel the hot kernel grew by 60 % and every GEMM of the step
+// got ~0.5 us slower (instruction fetch), fused or not.
+enum TcEpi { TC_E_NONE = 0, TC_E_GEGLU, TC_E_GLU, TC_E_SILU, TC_E_GELU, TC_E_SINK, TC_E_LN, TC_E_LN_GEGLU, TC_E_COUNT };
+template <int EPI> struct TcEpiTraits;
+template <> struct TcEpiTraits<TC_E_NONE>     { static constexpr int ACT = MUGD_ACT_NONE, GATE = MUGD_GATE_NONE,  MODE = TC_EPI_PLAIN; };
+template <> struct TcEpiTraits<TC_E_GEGLU>    { static constexpr int ACT = MUGD_ACT_NONE, GATE = MUGD_GATE_GEGLU, MODE = TC_EPI_PLAIN; };
+template <> struct TcEpiTraits<TC_E_GLU>      { static constexpr int ACT = MUGD_ACT_NONE, GATE = MUGD_GATE_GLU,   MODE = TC_EPI_PLAIN; };
+template <> struct TcEpiTraits<TC_E_SILU>     { static constexpr int ACT = MUGD_ACT_SILU, GATE = MUGD_GATE_NONE,  MODE = TC_EPI_PLAIN; };
+template <> struct TcEpiTraits<TC_E_GELU>     { static constexpr int ACT = MUGD_ACT_GELU, GATE = MUGD_GATE_NONE,  MODE = TC_EPI_PLAIN; };
+template <> struct TcEpiTraits<TC_E_SINK>     { static constexpr int ACT = MUGD_ACT_NONE, GATE = MUGD_GATE_NONE,  MODE = TC_EPI_SINK; };
+template <> struct TcEpiTraits<TC_E_LN>       { static constexpr int ACT = MUGD_ACT_NONE, GATE = MUGD_GATE_NONE,  MODE = TC_EPI_LN; };
+template <> struct TcEpiTraits<TC_E_LN_GEGLU> { static constexpr int ACT = MUGD_ACT_NONE, GATE = MUGD_GATE_GEGLU, MODE = TC_EPI_LN; };
+
+inline int tc_epi_of(const mugd_gemm& g) {
+    if (g.ln_stats) return g.gate == MUGD_GATE_GEGLU ? TC_E_LN_GEGLU : TC_E_LN;
+    if (g.row_moments) return TC_E_SINK;
+    if (g.gate == MUGD_GATE_GEGLU) return TC_E_GEGLU;
+    if (g.gate == MUGD_GATE_GLU) return TC_E_GLU;
+    if (g.act == MUGD_ACT_SILU) return TC_E_SILU;
+    if (g.act == MUGD_ACT_GELU) return TC_E_GELU;
+    return TC_E_NONE;
+}
 
 // rows of output tile `by`
 __device__ __forceinline__ void tc_tile_rows(const TcParams& p, int by, int& b_base, int& l_base, int& rows_valid) {
@@ -446,7 +388,7 @@ struct TcBars {
 // armed by the caller (TcBars::init) and visible to all threads.  All 256 threads call it; on return every TMA has landed, every
 // MMA has retired and been observed, and the tile (or its partial) is on its way to global memory.
 // PDL: stand-alone launches pass true -- the producer side executes griddepcontrol.wait before touching activations.
-template <int BN, bool PDL>
+template <int BN, bool PDL, int EPI>
 __device__ __forceinline__ void gemm_tc_tile(const CUtensorMap* tmA, const CUtensorMap* tmA1, const CUtensorMap* tmA2, const CUtensorMap* tmB,
                                              const CUtensorMap* tmWhi, const CUtensorMap* tmWlo, const TcParams& p, int bx, int by, int bz,
                                              uint32_t base, uint32_t tmem_base) {
@@ -570,6 +512,16 @@ __device__ __forceinline__ void gemm_tc_tile(const CUtensorMap* tmA, const CUten
         }
     } else if (warp >= 4) {
         // ===================================== converter ========================================
+        // LayerNorm folded into this GEMM: fetch the moments of this thread's row now (written by earlier kernels), use them after the loop
+        double ln_s = 0.0, ln_ss = 0.0;
+        if constexpr (TcEpiTraits<EPI>::MODE == TC_EPI_LN) {
+            if constexpr (PDL) pdl_wait();
+            const int rr = (warp & 3) * 32 + lane;
+            if (rr < rows_valid && m_base + rr < g.M) {
+                const double2 mo = *reinterpret_cast<const double2*>(g.ln_stats + (int64_t)(m_base + rr) * 2);
+                ln_s = mo.x; ln_ss = mo.y;
+            }
+        }
         for (int i = 0; i < nit; ++i) {
             const int s = i % SA;                                     // TMEM operand slot
             const int sm = i % SAS;                                   // raw tile in shared memory
@@ -607,10 +559,7 @@ __device__ __forceinline__ void gemm_tc_tile(const CUtensorMap* tmA, const CUten
         }
         // LayerNorm folded into this GEMM: the moments of this thread's row (written by the previous kernels) -> mean / rstd
         float2 lnrow = make_float2(0.f, 1.f);
-        if (g.ln_stats) {
-            const int rr = (warp & 3) * 32 + lane;
-            if (rr < rows_valid && m_base + rr < g.M) lnrow = tc_ln_row(g.ln_stats, m_base + rr, g.K, g.ln_eps);
-        }
+        if constexpr (TcEpiTraits<EPI>::MODE == TC_EPI_LN) lnrow = tc_ln_from_moments(ln_s, ln_ss, p.ln_invK, g.ln_eps);
         // ===================================== epilogue, phase 1 ================================
         mbar_wait(B.accum(), 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -630,7 +579,7 @@ __device__ __forceinline__ void gemm_tc_tile(const CUtensorMap* tmA, const CUten
                 asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(base + (uint32_t)(r * SP + c0 + j * 4) * 4u), "f"(v[j * 4]),
                              "f"(v[j * 4 + 1]), "f"(v[j * 4 + 2]), "f"(v[j * 4 + 3]) : "memory");
         }
-        if (g.ln_stats)      // (mean, rstd) of tile row r for phase 2, in the last KB of the (now idle) pipeline buffers
+        if constexpr (TcEpiTraits<EPI>::MODE == TC_EPI_LN)      // (mean, rstd) of tile row r for phase 2, in the last KB of the (now idle) pipeline buffers
             asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(base + S::TILE_BYTES - 1024u + (uint32_t)r * 8u), "f"(lnrow.x), "f"(lnrow.y) : "memory");
         TC_STAMP(threadIdx.x == 128, 3);
     }
@@ -661,23 +610,24 @@ __device__ __forceinline__ void gemm_tc_tile(const CUtensorMap* tmA, const CUten
                 for (int u = 0; u < U; ++u) st_f4(wsp + (i0 + u * TC_THREADS + (int)threadIdx.x) * 4, acc[u]);   // [row][BN] dense
             }
         } else {
-#define TC_CALL_STORE(A_, G_, M_) tc_store_tile<BN, A_, G_, M_>(g, base, m_base, n0, rows_valid, rowvec, base + S::TILE_BYTES - 1024u, p.Lrows)
-            TC_DISPATCH_EPI(g, TC_CALL_STORE);
-#undef TC_CALL_STORE
+            using E = TcEpiTraits<EPI>;
+            tc_store_tile<BN, E::ACT, E::GATE, E::MODE>(g, base, m_base, n0, rows_valid, rowvec, base + S::TILE_BYTES - 1024u);
         }
     }
     TC_STAMP(threadIdx.x == 0, 4);
 #undef TC_STAMP
 }
 
-// split-K second pass.  One call = one thread's share of reduce block `blk`: 4 output rows x one 4-column group.  A block of 256
-// threads covers RPB = 4 * (256 / (BN/4)) rows of one tile; the partial tiles are summed in fixed split order (deterministic), four
-// independent load chains per thread, then the fused epilogue (+ statistics sinks / folded LayerNorm) runs.
+// split-K second pass.  One call = one thread's share of reduce block `blk`: TC_RED_R output rows x one 4-column group.  A block of
+// 256 threads covers RPB = TC_RED_R * (256 / (BN/4)) rows of one tile; the partial tiles are summed in fixed split order
+// (deterministic), then the fused epilogue (+ row-moment sink / folded LayerNorm) runs.  One row per thread: the reduce of a small
+// GEMM is latency-bound, more and smaller blocks finish sooner (4 rows per thread cost +0.45 ms per step at Beff = 8).
+constexpr int TC_RED_R = 1;
 template <int BN>
 struct TcReduceGeom {
     static constexpr int C4 = BN / 4;
     static constexpr int RPP = TC_THREADS / C4;       // rows per pass
-    static constexpr int RPB = 4 * RPP;               // rows per block
+    static constexpr int RPB = TC_RED_R * RPP;        // rows per block
     static constexpr int BPT = TC_BM / RPB;           // blocks per tile
     static_assert(TC_BM % RPB == 0, "reduce geometry");
 };
@@ -696,28 +646,27 @@ __device__ __forceinline__ void tc_reduce_rows(const TcParams& p, int tile_lin, 
     const int r0 = rb * G::RPB + (int)threadIdx.x / C4;
     const int n = bx * BN + c4 * 4;
     const float* src = p.ws + ((long long)tile_lin * p.splits) * (TC_BM * BN) + c4 * 4;
-    float4 acc[4];
-    bool ok[4];
+    constexpr int R = TC_RED_R;
+    float4 acc[R];
+    bool ok[R];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < R; ++j) {
         const int r = r0 + j * G::RPP;
         ok[j] = r < rows_valid && m_base + r < g.M && n < g.N;
         acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-#pragma unroll 2
+#pragma unroll 4
     for (int z = 0; z < p.splits; ++z) {                                   // fixed order -> deterministic
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < R; ++j) {
             if (ok[j]) {
                 const float4 t4 = __ldcg(reinterpret_cast<const float4*>(src + (long long)z * (TC_BM * BN) + (long long)(r0 + j * G::RPP) * BN));
                 acc[j].x += t4.x; acc[j].y += t4.y; acc[j].z += t4.z; acc[j].w += t4.w;
             }
         }
     }
-    TcGroupAcc ga[2];
-    if constexpr (MODE == TC_EPI_SINK) { ga[0].reset(); ga[1].reset(); }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < R; ++j) {
         const int m = m_base + r0 + j * G::RPP;
         float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
         if (ok[j]) {
@@ -728,37 +677,22 @@ __device__ __forceinline__ void tc_reduce_rows(const TcParams& p, int tile_lin, 
             if (GATE == MUGD_GATE_NONE && g.residual) res = ld_f4(g.residual + (int64_t)m * g.ldr + n);
             if constexpr (MODE == TC_EPI_LN) {
                 cs = ld_f4(g.ln_colsum + n);
-                ln = tc_ln_row(g.ln_stats, m, g.K, g.ln_eps);
+                ln = tc_ln_row(g.ln_stats, m, p.ln_invK, g.ln_eps);
             }
             o = tc_finish4<ACT, GATE, MODE == TC_EPI_LN>(g, acc[j], bia, rvv, res, cs, ln, m, n);
         }
-        if constexpr (MODE == TC_EPI_SINK) {
-            const int si = (r0 + j * G::RPP) >= p.Lrows ? 1 : 0;
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                if (g.sink[k].kind == 1) { if (ok[j]) ga[k].add(si, o); }
-                else if (g.sink[k].kind == 2) tc_row_sink<SEG>(g.sink[k], ok[j] ? m : -1, o);
-            }
-        }
-    }
-    if constexpr (MODE == TC_EPI_SINK) {
-        if (g.sink[0].kind == 1 || g.sink[1].kind == 1) {
-            __shared__ __align__(16) double red_scratch[2 * 2 * TC_THREADS * 2];          // 16 KB
-            tc_group_flush<C4>(g, ga, smem_u32(red_scratch), bx * BN, m_base / g.Lout, (rows_valid + p.Lrows - 1) / p.Lrows);
-        }
+        if constexpr (MODE == TC_EPI_SINK) tc_row_sink<SEG>(g.row_moments, ok[j] ? m : -1, o);
     }
 }
 
-template <int BN>
+template <int BN, int EPI>
 __device__ __forceinline__ void tc_reduce_block(const TcParams& p, int blk) {
     using G = TcReduceGeom<BN>;
+    using E = TcEpiTraits<EPI>;
     const mugd_gemm& g = p.g;
     const int step = g.step ? *g.step : 0;
     const float* rowvec = g.rowvec ? g.rowvec + (int64_t)step * g.rowvec_step_stride : nullptr;
-    const int tile_lin = blk / G::BPT, rb = blk % G::BPT;
-#define TC_CALL_RED(A_, G_, M_) tc_reduce_rows<BN, A_, G_, M_>(p, tile_lin, rb, rowvec)
-    TC_DISPATCH_EPI(g, TC_CALL_RED);
-#undef TC_CALL_RED
+    tc_reduce_rows<BN, E::ACT, E::GATE, E::MODE>(p, blk / G::BPT, blk % G::BPT, rowvec);
 }
 #endif  // __CUDACC__
 

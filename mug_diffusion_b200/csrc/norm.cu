@@ -70,125 +70,12 @@ groupnorm_silu_kernel(const float* __restrict__ x, int64_t ldx, float* __restric
     }
 }
 
-// ---- GroupNorm with moments supplied by the producers of x (mugd_stat_sink kind 1) --------------------------------------
-// Single pass: one CTA per (row chunk, sample) with ~1024 float4 of work; every thread first ISSUES its (up to 4) loads of x,
-// gamma, beta, then the first G threads turn the sample's [G][2] fp64 moments into (mean, rstd) while those loads fly, then the
-// values are normalised and stored.  No reduction, no second read of x, one memory round trip of latency.
-constexpr int GNA_F4 = 1024;      // float4 per CTA
-constexpr int GNA_U = GNA_F4 / GN_THREADS;
-
-__global__ void __launch_bounds__(GN_THREADS)
-groupnorm_apply_kernel(const mugd_groupnorm p, int rows_per_cta) {
-    __shared__ float s_mean[128], s_rstd[128];
-    pdl_wait();
-    const int b = blockIdx.y;
-    const int cgn = p.stats_cg;                               // channels per group of the normalised tensor
-    const int q = p.C >> 2;
-    const int r0 = blockIdx.x * rows_per_cta;
-    const int r1 = min(p.L, r0 + rows_per_cta);
-    const float* xb = p.x + (int64_t)b * p.L * p.ldx;
-    float* yb = p.y + (int64_t)b * p.L * p.ldy;
-    const int total = (r1 - r0) * q;
-    for (int i0 = 0; i0 < total; i0 += GN_THREADS * GNA_U) {
-        float4 v[GNA_U], ga[GNA_U], be[GNA_U];
-        int row[GNA_U], c[GNA_U];
-#pragma unroll
-        for (int u = 0; u < GNA_U; ++u) {
-            const int i = i0 + u * GN_THREADS + (int)threadIdx.x;
-            row[u] = -1;
-            if (i < total) {
-                row[u] = r0 + i / q;
-                c[u] = (i % q) * 4;
-                v[u] = ld_f4(xb + (int64_t)row[u] * p.ldx + c[u]);
-                ga[u] = ld_f4(p.gamma + c[u]);
-                be[u] = ld_f4(p.beta + c[u]);
-            }
-        }
-        if (i0 == 0) {
-            const double n = (double)p.L * cgn;
-            for (int gi = threadIdx.x; gi < p.stats_G; gi += GN_THREADS) {
-                const double* st = p.stats + ((int64_t)b * p.stats_G + gi) * 2;
-                const double mean = st[0] / n;
-                double var = st[1] / n - mean * mean;
-                if (var < 0.0) var = 0.0;
-                s_mean[gi] = (float)mean;
-                s_rstd[gi] = (float)(1.0 / sqrt(var + (double)p.eps));
-            }
-            __syncthreads();
-        }
-#pragma unroll
-        for (int u = 0; u < GNA_U; ++u) {
-            if (row[u] < 0) continue;
-            const int gi = (p.stats_col0 + c[u]) / cgn;
-            const float mean = s_mean[gi], rstd = s_rstd[gi];
-            float4 o;
-            o.x = (v[u].x - mean) * rstd * ga[u].x + be[u].x;
-            o.y = (v[u].y - mean) * rstd * ga[u].y + be[u].y;
-            o.z = (v[u].z - mean) * rstd * ga[u].z + be[u].z;
-            o.w = (v[u].w - mean) * rstd * ga[u].w + be[u].w;
-            if (p.silu) { o.x = silu_f(o.x); o.y = silu_f(o.y); o.z = silu_f(o.z); o.w = silu_f(o.w); }
-            st_f4(yb + (int64_t)row[u] * p.ldy + c[u], o);
-        }
-    }
-}
-
-// Accumulate the moments of the columns of x into a statistics buffer (y == NULL): used once per request for step-invariant
-// columns (the audio features of AudioConcatBlock) and by tests.  One CTA per (group touched by x, sample); groups may be cut by
-// the edges of x (x is a column window of the normalised tensor).
-__global__ void __launch_bounds__(GN_THREADS)
-groupnorm_stats_kernel(const mugd_groupnorm p, int g_first) {
-    pdl_wait();
-    const int gi = g_first + blockIdx.x, b = blockIdx.y;
-    const int c_lo = max(0, gi * p.stats_cg - p.stats_col0), c_hi = min(p.C, (gi + 1) * p.stats_cg - p.stats_col0);
-    const int q = (c_hi - c_lo) >> 2;
-    const int total = p.L * q;
-    const float* xb = p.x + (int64_t)b * p.L * p.ldx + c_lo;
-    double s = 0.0, ss = 0.0;
-    for (int i = threadIdx.x; i < total; i += GN_THREADS) {
-        const int row = i / q, qq = i - row * q;
-        const float4 v = ld_f4(xb + (int64_t)row * p.ldx + qq * 4);
-        s += (double)v.x + (double)v.y + (double)v.z + (double)v.w;
-        ss += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
-    }
-    __shared__ double red[2][GN_THREADS / 32];
-    s = warp_sum(s);
-    ss = warp_sum(ss);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lane == 0) { red[0][warp] = s; red[1][warp] = ss; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double ts = 0.0, tss = 0.0;
-#pragma unroll
-        for (int w = 0; w < GN_THREADS / 32; ++w) { ts += red[0][w]; tss += red[1][w]; }
-        double* d = p.stats + ((int64_t)b * p.stats_G + gi) * 2;
-        atomicAdd(d, ts);
-        atomicAdd(d + 1, tss);
-    }
-}
-
 int launch_groupnorm(const DeviceInfo&, const mugd_groupnorm& g, cudaStream_t st, int* launches) {
-    MUGD_REQUIRE(g.B > 0 && g.L > 0 && g.C > 0, "groupnorm: empty shape B=%d L=%d C=%d G=%d", g.B, g.L, g.C, g.G);
-    MUGD_REQUIRE(g.ldx % 4 == 0 && aligned16(g.x) && g.ldx >= g.C, "groupnorm: x must be 16-byte aligned with ldx %% 4 == 0, ldx >= C");
-    if (g.stats) {
-        MUGD_REQUIRE((reinterpret_cast<uintptr_t>(g.stats) & 7u) == 0 && g.stats_cg > 0 && g.stats_cg % 4 == 0 && g.stats_col0 % 4 == 0 &&
-                         g.stats_col0 >= 0 && g.C % 4 == 0 && g.stats_G > 0 && g.stats_G <= 128 && g.stats_col0 + g.C <= g.stats_cg * g.stats_G,
-                     "groupnorm: statistics geometry (col0=%d cg=%d G=%d C=%d)", g.stats_col0, g.stats_cg, g.stats_G, g.C);
-        if (!g.y) {
-            const int g_first = g.stats_col0 / g.stats_cg, g_last = (g.stats_col0 + g.C - 1) / g.stats_cg;
-            MUGD_CHECK_CUDA(launch_k(groupnorm_stats_kernel, dim3(g_last - g_first + 1, g.B), dim3(GN_THREADS), 0, st, g, g_first));
-        } else {
-            MUGD_REQUIRE(g.ldy % 4 == 0 && aligned16(g.y) && aligned16(g.gamma) && aligned16(g.beta) && g.ldy >= g.C, "groupnorm: y / gamma / beta alignment");
-            int rpc = GNA_F4 / (g.C / 4);
-            if (rpc < 1) rpc = 1;
-            MUGD_CHECK_CUDA(launch_k(groupnorm_apply_kernel, dim3((g.L + rpc - 1) / rpc, g.B), dim3(GN_THREADS), 0, st, g, rpc));
-        }
-        if (launches) *launches += 1;
-        return MUGD_OK;
-    }
-    MUGD_REQUIRE(g.G > 0 && g.C % g.G == 0 && (g.C / g.G) % 4 == 0, "groupnorm: C/G must be a multiple of 4 (C=%d G=%d)", g.C, g.G);
-    MUGD_REQUIRE(g.ldy % 4 == 0 && aligned16(g.y) && aligned16(g.gamma) && aligned16(g.beta),
+    MUGD_REQUIRE(g.B > 0 && g.L > 0 && g.C > 0 && g.G > 0, "groupnorm: empty shape B=%d L=%d C=%d G=%d", g.B, g.L, g.C, g.G);
+    MUGD_REQUIRE(g.C % g.G == 0 && (g.C / g.G) % 4 == 0, "groupnorm: C/G must be a multiple of 4 (C=%d G=%d)", g.C, g.G);
+    MUGD_REQUIRE(g.ldx % 4 == 0 && g.ldy % 4 == 0 && aligned16(g.x) && aligned16(g.y) && aligned16(g.gamma) && aligned16(g.beta),
                  "groupnorm: operands must be 16-byte aligned with ld %% 4 == 0");
-    MUGD_REQUIRE(g.ldy >= g.C, "groupnorm: leading dimension smaller than C");
+    MUGD_REQUIRE(g.ldx >= g.C && g.ldy >= g.C, "groupnorm: leading dimension smaller than C");
     dim3 grid(g.G, g.B);
     MUGD_CHECK_CUDA(launch_k(groupnorm_silu_kernel, grid, dim3(GN_THREADS), 0, st, g.x, g.ldx, g.y, g.ldy, g.gamma, g.beta, g.L, g.C, g.G,
                              g.eps, g.silu));

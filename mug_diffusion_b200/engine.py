@@ -122,45 +122,22 @@ class OpList:
         self.add(L_.OP_GEMM, g, tag)
         return len(self.ops) - 1
 
-    def sink_capable(self, i: int) -> bool:
-        """can op i carry one more statistics sink?  (tensor-core GEMM with a plain epilogue and a free slot)"""
+    def can_deliver_row_moments(self, i: int) -> bool:
+        """can GEMM op i also accumulate the row moments of its output?  (tensor-core path with a plain epilogue)"""
         op = self.ops[i]
         if op.kind != L_.OP_GEMM:
             return False
         g = op.u.gemm
-        tc = bool(g.W_hi) and g.K % 32 == 0 and g.K2 % 32 == 0 and g.N >= 64 and g.impl != L_.GEMM_SIMT and \
-            g.conv_mode != L_.CONV_UP and not (g.conv_mode == L_.CONV_DOWN and g.K2)
-        return tc and g.act == L_.ACT_NONE and g.gate == L_.GATE_NONE and not g.ln_stats and any(g.sink[k].kind == 0 for k in range(2))
+        tc = bool(g.W_hi) and g.K % 32 == 0 and g.K2 % 32 == 0 and g.N >= 64 and g.impl != L_.GEMM_SIMT and g.conv_mode != L_.CONV_UP
+        return tc and g.act == L_.ACT_NONE and g.gate == L_.GATE_NONE and not g.ln_stats and not g.row_moments
 
-    def add_sink(self, i: int, kind: int, buf: int, col0: int = 0, cg: int = 0, G: int = 0):
-        g = self.ops[i].u.gemm
-        k = 0 if g.sink[0].kind == 0 else 1
-        assert g.sink[k].kind == 0
-        g.sink[k].buf, g.sink[k].kind, g.sink[k].col0, g.sink[k].cg, g.sink[k].G = buf, kind, col0, cg, G
-        if kind == 1 and g.conv_mode == L_.CONV_NONE:
-            # group moments are kept per sample: run the 1x1 as a one-tap conv so that output tiles follow the sample structure
-            # (3-D tensor map (k, l, b)) instead of cutting the flat row range every 128 rows
-            g.conv_mode, g.taps, g.tap_shift, g.tap_dilation, g.Lin = L_.CONV_TAPS, 1, 0, 1, g.Lout
-
-    def group_sink_ok(self, i: int) -> bool:
-        """a 128-row tile of op i holds at most two samples (what the epilogue's group-moment accumulators are built for)"""
-        g = self.ops[i].u.gemm
-        return g.Lout >= 128 or 128 // g.Lout <= 2
-
-    def groupnorm(self, x: View, y: Optional[View], gamma: int, beta: int, B: int, Lrows: int, G: int, silu: bool, tag: int = 0,
-                  stats: int = 0, stats_col0: int = 0, stats_cg: int = 0, stats_G: int = 0) -> int:
-        """stats: [B][G][2] fp64 moments filled by the producers of x (single-pass apply); y None = accumulate x's moments only"""
+    def groupnorm(self, x: View, y: View, gamma: int, beta: int, B: int, Lrows: int, G: int, silu: bool, tag: int = 0) -> int:
         d = L_.GroupNorm()
-        d.x, d.ldx = x.ptr, x.ld
-        if y is not None:
-            d.y, d.ldy = y.ptr, y.ld
-            assert y.cols == x.cols
-        d.gamma, d.beta = gamma or None, beta or None
+        d.x, d.ldx, d.y, d.ldy = x.ptr, x.ld, y.ptr, y.ld
+        d.gamma, d.beta = gamma, beta
         d.B, d.L, d.C, d.G = B, Lrows, x.cols, G
         d.eps, d.silu = GN_EPS, int(silu)
-        if stats:
-            d.stats, d.stats_col0, d.stats_cg, d.stats_G = stats, stats_col0, stats_cg or x.cols // G, stats_G or G
-        assert x.rows == B * Lrows
+        assert x.rows == B * Lrows and y.cols == x.cols
         self.add(L_.OP_GROUPNORM, d, tag)
         return len(self.ops) - 1
 
@@ -231,51 +208,6 @@ def tc_weight_map(blob: WeightBlob, wbase: int) -> Dict[int, Tuple[int, int]]:
     return m
 
 
-class Writers:
-    """Who wrote which columns of which buffer last -- so that a normalisation can ask the producers of its input for the moments
-    (mugd_stat_sink) instead of reading the input twice.  Entries: (logical output view, op indices | "audio" | None)."""
-
-    def __init__(self):
-        self.items: List[Tuple[View, object]] = []
-
-    def add(self, view: View, who):
-        self.items.append((view, who))
-
-    @staticmethod
-    def _span(v: View) -> Tuple[int, int]:
-        return v.ptr, v.ptr + 4 * ((v.rows - 1) * v.ld + v.cols)
-
-    def cover(self, x: View):
-        """latest writers of all columns of x as [(who, col_lo, col_hi)], or None when they cannot be told apart cleanly"""
-        need = x.cols
-        covered = [False] * (x.cols // 4)
-        out = []
-        x0, x1 = self._span(x)
-        for view, who in reversed(self.items):
-            v0, v1 = self._span(view)
-            if v1 <= x0 or v0 >= x1:
-                continue
-            off = view.ptr - x.ptr
-            if view.ld != x.ld or view.rows != x.rows or off < 0 or off % 16 or off // 4 + view.cols > x.cols:
-                # overlapping bytes with another geometry: could be a column window of a wider row that does not touch x's columns
-                if view.ld == x.ld and view.rows == x.rows and (off // 4 >= x.cols or off // 4 + view.cols <= 0):
-                    continue
-                return None
-            lo, hi = off // 4, off // 4 + view.cols
-            seen = [covered[q] for q in range(lo // 4, hi // 4)]
-            if all(seen):
-                continue                    # overwritten later
-            if any(seen) or who is None:
-                return None
-            for q in range(lo // 4, hi // 4):
-                covered[q] = True
-            out.append((who, lo, hi))
-            need -= hi - lo
-            if need == 0:
-                return out
-        return None
-
-
 # tags (profiling labels carried in mugd_op.tag)
 TAG_RES, TAG_ATTN, TAG_S4, TAG_UPDOWN, TAG_IO = 1, 2, 3, 4, 5
 
@@ -290,10 +222,11 @@ class UNetCompiler:
     def w(self, name: str) -> int:
         return self.wbase + 4 * self.blob.offset(name)
 
-    def compile(self, arena: Arena, Beff: int, Lz: int, ext: Dict[str, int], per_sample_t: bool, fuse_norms: bool = True) -> dict:
-        """fuse_norms: GroupNorm moments come from the producers of its input (statistics sinks in the GEMM epilogues, one
-        light apply kernel left) and LayerNorm is folded into the Linear that follows it; False = the stand-alone two-pass
-        GroupNorm / LayerNorm kernels (the referee path, and what the exact-fp32 FFMA GEMM uses)."""
+    def compile(self, arena: Arena, Beff: int, Lz: int, ext: Dict[str, int], per_sample_t: bool, fold_ln: Optional[bool] = None) -> dict:
+        """fold_ln: every LayerNorm of the transformer blocks is folded into the Linear behind it (the producer of its input delivers
+        the row moments, the Linear corrects in its epilogue; no LayerNorm kernel, the normalised tensor is never written).  Worth
+        1.2 % at Beff = 8 and -0.8 % at Beff = 64 (profiles/r02_norm_fusion_ab.md), so None = fold below 8192 token rows.
+        False = stand-alone LayerNorm kernels (the referee path, and what the exact-fp32 FFMA GEMM uses)."""
         cfg = self.cfg
         ops = OpList(tc_weight_map(self.blob, self.wbase))
         nlev = cfg.levels
@@ -302,35 +235,32 @@ class UNetCompiler:
         lens = [Lz >> l for l in range(nlev)]
         mc = cfg.model_channels
         G = cfg.gn_groups
-        fuse_ln = fuse_norms and (self.prefix + "input_blocks.0.0.weight") in self.blob.entries and any(k.endswith("qkv_ln.weight") for k in self.blob.entries)
+        if fold_ln is None:
+            fold_ln = rows[0] < 8192
+        fuse_ln = fold_ln and any(k.endswith("qkv_ln.weight") for k in self.blob.entries)
 
-        # ---- statistics block: [live | base] fp64 moments, `live` re-armed from `base` by the first op of every evaluation ----
+        # ---- row-moment block: [live | zeros] fp64, `live` re-armed by the first op of every evaluation ----
         all_blocks = [b for e in self.lay.input + [self.lay.middle] + self.lay.output if not isinstance(e, tuple) for b in e]
-        n_gn = sum({"res": 2, "attn": 1, "s4": 1}.get(b.kind, 0) for b in all_blocks) + 1
         lvl_of_ds = {1 << l: l for l in range(nlev)}
         ln_rows = sum(3 * rows[lvl_of_ds[b.ds]] for b in all_blocks if b.kind == "attn")
-        stat_doubles = (n_gn * Beff * G * 2 + ln_rows * 2 + 64) if fuse_norms else 0
+        stat_doubles = ln_rows * 2 if fuse_ln else 0
         stat_floats = (2 * stat_doubles + 63) // 64 * 64
-        live = arena.alloc(1, stat_floats) if fuse_norms else None
-        base = arena.alloc(1, stat_floats) if fuse_norms else None
+        live = arena.alloc(1, stat_floats) if fuse_ln else None
+        zeros = arena.alloc(1, stat_floats) if fuse_ln else None          # never written: the arena starts zeroed
         stat_top = [0]                        # doubles handed out
 
-        def stat_alloc(n_doubles: int) -> Tuple[int, int]:
+        def stat_alloc(n_doubles: int) -> int:
             o = stat_top[0]
             stat_top[0] += (n_doubles + 1) // 2 * 2
-            assert stat_top[0] <= stat_doubles, "statistics block overflow"
-            return live.ptr + 8 * o, base.ptr + 8 * o
+            assert stat_top[0] <= stat_doubles, "row-moment block overflow"
+            return live.ptr + 8 * o
 
-        if fuse_norms:
-            ops.copy2d(base, live, TAG_IO)
-
-        W = Writers()
-        audio_stats: List[Tuple[View, int, int, int, int]] = []       # (audio columns, base moments, col0, cg, G) per request
+        if fuse_ln:
+            ops.copy2d(zeros, live, TAG_IO)
 
         # ---- persistent buffers --------------------------------------------------------------
         xin = arena.alloc(rows[0], cfg.in_channels)
         eps = arena.alloc(rows[0], cfg.out_channels)
-        W.add(xin, None)
         ctx_tokens = ext["ctx_tokens"]
         # down-path concat buffers [h | audio_l]
         down_cat = []
@@ -372,48 +302,19 @@ class UNetCompiler:
             ch_h, ca, ich = up_parts[bi]
             audio_slots.append((level, up_cat[bi].c(ch_h, ch_h + ca)))
             bi += cfg.num_res_blocks + 1
-        for _, v in audio_slots:
-            W.add(v, "audio")
 
         emb_total = self.blob.meta["emb_total"]
         emb_off = self.blob.meta["emb_offsets"]
         E = ext["emb_table"]
         step = ext["step"]
 
-        # ---- op emitters that keep the writer registry up to date ---------------------------------
-        def gemm(A, Wt, N, K, out, **kw) -> int:
-            i = ops.gemm(A, Wt, N, K, out, **kw)
-            W.add(out, [i])
-            return i
+        gemm = ops.gemm
 
         def copy(src: View, dst: View, tag: int):
-            """copy of a tensor that lives in two concat buffers; the copy inherits the producers of the source"""
             ops.copy2d(src, dst, tag)
-            cov = W.cover(src)
-            who = cov[0][0] if cov is not None and len(cov) == 1 and cov[0][1] == 0 and cov[0][2] == src.cols else None
-            W.add(dst, who)
 
         def groupnorm(x: View, y: View, gamma: int, beta: int, Lr: int, silu: bool, tag: int):
-            """GroupNorm(32, eps 1e-6) [+ SiLU]: single-pass apply when every column of x has a producer that can deliver its moments"""
-            cov = W.cover(x) if fuse_norms else None
-            if cov is not None:
-                for who, lo, hi in cov:
-                    if who != "audio" and not all(ops.sink_capable(i) and ops.group_sink_ok(i) for i in who):
-                        cov = None
-                        break
-            if cov is None:
-                ops.groupnorm(x, y, gamma, beta, Beff, Lr, G, silu, tag)
-            else:
-                cg = x.cols // G
-                lv, bs = stat_alloc(Beff * G * 2)
-                for who, lo, hi in cov:
-                    if who == "audio":
-                        audio_stats.append((x.c(lo, hi), bs, lo, cg, G))
-                    else:
-                        for i in who:
-                            ops.add_sink(i, 1, lv, lo, cg, G)
-                ops.groupnorm(x, y, gamma, beta, Beff, Lr, G, silu, tag, stats=lv, stats_col0=0, stats_cg=cg, stats_G=G)
-            W.add(y, None)
+            ops.groupnorm(x, y, gamma, beta, Beff, Lr, G, silu, tag)
 
         # ---- block emitters ------------------------------------------------------------------
         def emit_res(b: Block, x: View, out: View, lvl: int):
@@ -455,15 +356,14 @@ class UNetCompiler:
             def normed_linear(src: View, i_src: int, norm: str, lin: str, N: int, dst: View, gate: int = L_.GATE_NONE, has_bias: bool = False):
                 """Linear(LayerNorm(src)) (attention.py:147-151).  Folded: the producer of src (op i_src) delivers the row moments,
                 the Linear runs on the raw rows with gamma-scaled weights and corrects in its epilogue; else LayerNorm kernel + Linear."""
-                if fuse_ln and ops.sink_capable(i_src):
-                    lv, _ = stat_alloc(src.rows * 2)
-                    ops.add_sink(i_src, 2, lv)
+                if fuse_ln and ops.can_deliver_row_moments(i_src):
+                    lv = stat_alloc(src.rows * 2)
+                    ops.ops[i_src].u.gemm.row_moments = lv
                     gemm(src, self.w(t + lin + "_ln.weight"), N, Cc, dst, bias=self.w(t + lin + "_ln.bias"), gate=gate, Lout=Lr,
                          ln=(lv, self.w(t + lin + "_ln.colsum"), LN_EPS), tag=TAG_ATTN)
                 else:
                     n = arena.alloc(src.rows, Cc)
                     ops.layernorm(src, n, self.w(t + norm + ".weight"), self.w(t + norm + ".bias"), TAG_ATTN)
-                    W.add(n, None)
                     gemm(n, self.w(t + lin + ".weight"), N, Cc, dst, bias=self.w(t + lin + ".bias") if has_bias else 0, gate=gate,
                          Lout=Lr, tag=TAG_ATTN)
 
@@ -473,7 +373,6 @@ class UNetCompiler:
             ops.attention(qkv.c(0, Cc), qkv.c(Cc, 2 * Cc), qkv.c(2 * Cc, 3 * Cc), ao,
                           self.w(t + "attn1.relative_position_embedding"), self.w(t + "attn1.C_embedding"),
                           Beff, H, Lr, Lr, cfg.pos_max, TAG_ATTN)
-            W.add(ao, None)
             h1 = arena.alloc(x.rows, Cc)
             i_h1 = gemm(ao, self.w(t + "attn1.to_out.0.weight"), Cc, Cc, h1, bias=self.w(t + "attn1.to_out.0.bias"),
                         residual=h0, Lout=Lr, tag=TAG_ATTN)
@@ -482,7 +381,6 @@ class UNetCompiler:
             ops.attention(q2, kv.c(0, Cc), kv.c(Cc, 2 * Cc), ao,
                           self.w(t + "attn2.relative_position_embedding"), self.w(t + "attn2.C_embedding"),
                           Beff, H, Lr, ctx_tokens, cfg.pos_max, TAG_ATTN)
-            W.add(ao, None)
             h2 = h0                                    # h0 is dead after the first residual add
             i_h2 = gemm(ao, self.w(t + "attn2.to_out.0.weight"), Cc, Cc, h2, bias=self.w(t + "attn2.to_out.0.bias"),
                         residual=h1, Lout=Lr, tag=TAG_ATTN)
@@ -502,7 +400,6 @@ class UNetCompiler:
             groupnorm(x, g, self.w(p + "norm.weight"), self.w(p + "norm.bias"), Lr, False, TAG_S4)
             y = arena.alloc(x.rows, Hc)
             ops.s4conv(g, ext["s4_kt"][p].ptr, self.w(s_ + "D"), y, Beff, Lr, TAG_S4)
-            W.add(y, None)
             z = g
             gemm(y, self.w(s_ + "output_linear.0.weight"), 2 * Hc, Hc, z, bias=self.w(s_ + "output_linear.0.bias"),
                  gate=L_.GATE_GLU, Lout=Lr, tag=TAG_S4)
@@ -518,10 +415,7 @@ class UNetCompiler:
                 if b.kind == "up":
                     tgt_rows = rows[lvl - 1]
                     out = final_out if (last and final_out is not None) else arena.alloc(tgt_rows, b.cout)
-                    idx = emit_upsample_conv(ops, self.blob, self.w, b.prefix, cur, out, lens[lvl], b.cin, b.cout, TAG_UPDOWN)
-                    # the two parity GEMMs write the even / odd rows of `out`: together they are its producer.  Their rows are
-                    # indexed on the un-upsampled axis, which keeps row / rows-per-sample = sample for the group moments.
-                    W.add(out, idx if len(idx) == 2 else None)
+                    emit_upsample_conv(ops, self.blob, self.w, b.prefix, cur, out, lens[lvl], b.cin, b.cout, TAG_UPDOWN)
                     lvl -= 1
                     cur = out
                     continue
@@ -593,7 +487,7 @@ class UNetCompiler:
         gemm(t, self.w(ob.prefix + "2.weight"), ob.cout, ob.cin, eps, bias=self.w(ob.prefix + "2.bias"), taps=3,
              mode=L_.CONV_SAME, Lin=lens[0], Lout=lens[0], tag=TAG_IO)
         arena.release(m)
-        return dict(ops=ops, xin=xin, eps=eps, audio_slots=audio_slots, stats_base=base, audio_stats=audio_stats)
+        return dict(ops=ops, xin=xin, eps=eps, audio_slots=audio_slots, ln_folded=fuse_ln)
 
 
 class DecoderCompiler:

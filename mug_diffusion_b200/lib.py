@@ -18,13 +18,9 @@ CONV_NONE, CONV_SAME, CONV_DOWN, CONV_UP, CONV_TAPS = range(5)
 ACT_NONE, ACT_SILU, ACT_GELU = range(3)
 GATE_NONE, GATE_GEGLU, GATE_GLU = range(3)
 GEMM_AUTO, GEMM_SIMT, GEMM_TC = range(3)
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 _f = C.c_void_p  # device pointers travel as integers
-
-
-class StatSink(C.Structure):
-    _fields_ = [("buf", _f), ("kind", C.c_int32), ("col0", C.c_int32), ("cg", C.c_int32), ("G", C.c_int32)]
 
 
 class Gemm(C.Structure):
@@ -37,15 +33,14 @@ class Gemm(C.Structure):
                 ("split_k", C.c_int32), ("n_counters", C.c_int32), ("tap_shift", C.c_int32), ("tap_dilation", C.c_int32),
                 ("workspace", _f), ("workspace_bytes", C.c_int64), ("counters", _f),
                 ("A2", _f), ("lda2", C.c_int64), ("K2", C.c_int32), ("reserved_", C.c_int32),
-                ("sink", StatSink * 2),
+                ("row_moments", _f),
                 ("ln_stats", _f), ("ln_colsum", _f), ("ln_eps", C.c_float), ("reserved2_", C.c_int32)]
 
 
 class GroupNorm(C.Structure):
     _fields_ = [("x", _f), ("ldx", C.c_int64), ("y", _f), ("ldy", C.c_int64), ("gamma", _f), ("beta", _f),
                 ("B", C.c_int32), ("L", C.c_int32), ("C", C.c_int32), ("G", C.c_int32),
-                ("eps", C.c_float), ("silu", C.c_int32),
-                ("stats", _f), ("stats_col0", C.c_int32), ("stats_cg", C.c_int32), ("stats_G", C.c_int32), ("reserved_", C.c_int32)]
+                ("eps", C.c_float), ("silu", C.c_int32)]
 
 
 class LayerNorm(C.Structure):

@@ -65,7 +65,7 @@ class MugEngine:
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], cfg: Optional[ModelConfig] = None,
                  device: Optional[torch.device] = None, gemm_impl: str = "auto", blob: Optional[WeightBlob] = None,
-                 max_sessions: int = 4, fuse_norms: bool = True):
+                 max_sessions: int = 4, fold_ln: Optional[bool] = None):
         if not torch.cuda.is_available():
             raise L_.MugdError("mug_diffusion_b200 needs an sm_100 (B200) GPU; there is no CPU fallback")
         self.cfg = cfg or ModelConfig()
@@ -87,7 +87,7 @@ class MugEngine:
         self.sessions: "OrderedDict[tuple, Session]" = OrderedDict()
         self.dec_sessions: "OrderedDict[tuple, object]" = OrderedDict()
         self.max_sessions = max_sessions
-        self.fuse_norms = fuse_norms          # False: stand-alone GroupNorm / LayerNorm kernels (A/B and referee)
+        self.fold_ln = fold_ln                # LayerNorm folded into the next Linear: None = below 8192 token rows, True / False = forced
         # internal S4 kernel length per layer (SSKernelNPLR's `L` buffer, s4.py:557-584).  It is ENGINE state: lengthening
         # rewrites this engine's device copy of C~, so the length that goes with it must not live in the shared host blob.
         self.s4_L: Dict[str, int] = {k: int(v) for k, v in self.blob.meta.items() if k.endswith("kernel.kernel.L")}
@@ -227,21 +227,20 @@ class Session:
         )
 
     def _build(self, comp: UNetCompiler):
-        # norm fusion (statistics sinks, folded LayerNorm) lives in the tensor-core GEMM epilogues; the exact-fp32 FFMA path keeps
-        # the stand-alone norm kernels and doubles as the referee of the fused plan
-        fuse = self.engine.gemm_impl != "simt" and self.engine.fuse_norms
+        # the LayerNorm fold lives in the tensor-core GEMM epilogues; the exact-fp32 FFMA path keeps the stand-alone LayerNorm
+        # kernels and doubles as the referee of the folded plan.  engine.fold_ln: None = by size, True / False = forced (A/B, tests)
+        fold = False if self.engine.gemm_impl == "simt" else self.engine.fold_ln
         dry = Arena(0)
-        comp.compile(dry, self.Beff, self.Lz, self._ext(self.ctx_tokens), self.per_sample_t, fuse)
+        comp.compile(dry, self.Beff, self.Lz, self._ext(self.ctx_tokens), self.per_sample_t, fold)
         nbytes = dry.high + 1024
         self.arena_t = torch.zeros(nbytes // 4 + 64, device=self.engine.device)
         base = (self.arena_t.data_ptr() + 255) // 256 * 256
         arena = Arena(base, nbytes)
-        res = comp.compile(arena, self.Beff, self.Lz, self._ext(self.ctx_tokens), self.per_sample_t, fuse)
+        res = comp.compile(arena, self.Beff, self.Lz, self._ext(self.ctx_tokens), self.per_sample_t, fold)
         self.xin: View = res["xin"]
         self.eps: View = res["eps"]
         self.audio_slots = res["audio_slots"]
-        self.stats_base: Optional[View] = res["stats_base"]
-        self.audio_stats = res["audio_stats"]
+        self.ln_folded = res["ln_folded"]
         self.plan = Plan(self.engine, res["ops"])
         self.arena_bytes = nbytes
         self._captured_for = None
@@ -319,13 +318,6 @@ class Session:
             ops.transpose(_ptr(a), view.ptr, 0, view.ld, Bh, a.shape[1], a.shape[2], True)
             if dup:
                 ops.transpose(_ptr(a), view.r(Bh * a.shape[2], 2 * Bh * a.shape[2]).ptr, 0, view.ld, Bh, a.shape[1], a.shape[2], True)
-        if self.stats_base is not None:
-            # the audio columns of the concat buffers are step-invariant: their GroupNorm moments are accumulated once per request
-            # into the `base` image that re-arms the live statistics at the start of every evaluation
-            off = (self.stats_base.ptr - self.arena_t.data_ptr()) // 4
-            self.arena_t[off:off + self.stats_base.cols].zero_()
-            for view, buf, col0, cg, G in self.audio_stats:
-                ops.groupnorm(view, None, 0, 0, self.Beff, view.rows // self.Beff, G, False, stats=buf, stats_col0=col0, stats_cg=cg, stats_G=G)
         self.engine.run_ops(ops)
         self._keep_audio = w4
 

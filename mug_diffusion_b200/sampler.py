@@ -133,9 +133,9 @@ class MugDiffusionB200:
     """Drop-in for the reference ``DDPM`` object on the sampler path (attributes of SURVEY §8b)."""
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], cfg: Optional[ModelConfig] = None, z_length: int = 512,
-                 device=None, gemm_impl: str = "auto", blob=None, fuse_norms: bool = True):
+                 device=None, gemm_impl: str = "auto", blob=None, fold_ln: Optional[bool] = None):
         self.cfg = cfg or ModelConfig()
-        self.engine = MugEngine(state_dict, self.cfg, device, gemm_impl=gemm_impl, blob=blob, fuse_norms=fuse_norms)
+        self.engine = MugEngine(state_dict, self.cfg, device, gemm_impl=gemm_impl, blob=blob, fold_ln=fold_ln)
         self.device = self.engine.device
         self.z_channels = self.cfg.z_channels
         self.z_length = z_length

@@ -24,10 +24,10 @@ def signature(op):
     if k == L_.OP_GEMM:
         g = op.u.gemm
         return ("gemm", g.M, g.N, g.K, g.taps, g.conv_mode, g.gate, g.act, int(bool(g.residual)), int(bool(g.rowvec)), f"K2={g.K2}",
-                f"sinks={g.sink[0].kind}{g.sink[1].kind}", f"ln={int(bool(g.ln_stats))}")
+                f"rowmom={int(bool(g.row_moments))}", f"ln={int(bool(g.ln_stats))}")
     if k == L_.OP_GROUPNORM:
         g = op.u.gn
-        return ("groupnorm", g.B, g.L, g.C, g.G, g.silu, f"stats={int(bool(g.stats))}")
+        return ("groupnorm", g.B, g.L, g.C, g.G, g.silu)
     if k == L_.OP_LAYERNORM:
         g = op.u.ln
         return ("layernorm", g.rows, g.C)
@@ -47,11 +47,11 @@ def main():
     ap.add_argument("--nocfg", action="store_true")
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--gemm", default="auto")
-    ap.add_argument("--fuse", type=int, default=1, help="0: stand-alone GroupNorm / LayerNorm kernels")
+    ap.add_argument("--fuse", type=int, default=1, help="0: stand-alone LayerNorm kernels")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     cfg = ModelConfig()
-    model = MugDiffusionB200(synth.synthetic_state_dict(a.L), cfg, z_length=a.L, device=dev, gemm_impl=a.gemm, fuse_norms=bool(a.fuse))
+    model = MugDiffusionB200(synth.synthetic_state_dict(a.L), cfg, z_length=a.L, device=dev, gemm_impl=a.gemm, fold_ln=bool(a.fuse))
     eng = model.engine
     Beff = a.B if a.nocfg else 2 * a.B
     sess = eng.session(Beff, a.L, per_sample_t=False)
