@@ -17,124 +17,123 @@
 namespace mugd {
 
 // =====================================================================================================
-// (1) causal long convolution.  lane = channel (coalesced), each warp owns blocks of 8 consecutive
-// outputs; a 16-deep register window slides over u (smem) while K taps stream from L1/L2.
+// (1) causal long convolution on the FFMA lanes.
+//
+// Why not tensor cores: the Toeplitz matrix is per CHANNEL, so a GEMM formulation has N = batch (8..64 columns) and must build a
+// 128 x 32 operand tile per (channel, k-step) by hand; DFT-as-GEMM shares its matrix across channels but costs 8x the FLOPs at
+// 3xTF32.  A direct kernel that keeps the FMA pipe fed wins: the round-1 kernel ran at ~18 % of the FFMA peak (per-load bounds
+// checks, a register window copied every chunk); this one has no predicate in the inner loop and runs 16 loads per 64 FMAs.
+//
+// One CTA = 16 channels of one sample (x a share of the output blocks when nsplit > 1); u and K tiles live in shared memory with
+// zero padding on both sides, so the inner loop never tests an index.  A warp computes a "super block" of 16 consecutive outputs:
+// lanes 0-15 take outputs l0..l0+7 of channels 0..15, lanes 16-31 take l0+8..l0+15 of the same channels (both halves run the
+// same number of chunks; the row pitch of 18 floats puts the two halves on disjoint banks, the tap loads are broadcasts).
+// Per chunk of 8 taps a lane loads 8 new window values + 8 taps and issues 64 FMAs; the 15-wide window lives in two register
+// arrays whose roles alternate (no copies).
 // =====================================================================================================
 constexpr int S4_WARPS = 8;
-constexpr int S4_R = 8;         // outputs per block
+constexpr int S4_R = 8;          // outputs per lane and taps per chunk
+constexpr int S4_CH = 16;        // channels per CTA
+constexpr int S4_PITCH = 18;     // floats per time step in shared memory (8 * 18 = 144 = 16 mod 32: the halves hit disjoint banks)
+constexpr int S4_PAD = 16;       // zero rows in front of u (the last chunk of the lower half reads u[-16 .. -9])
 
-// CH channels per CTA (32: one lane per channel; 16: the two half-warps share 16 channels and split the taps of every
-// chunk by parity, accumulators are added with one shuffle at the end -- used when two L x 32 tiles do not fit).
-// KS: kernel taps staged in shared memory next to u (2 * L * CH * 4 B); otherwise streamed through L1 (very long L).
-template <bool KS, int CH>
+__device__ __forceinline__ void s4_chunk(float (&acc)[S4_R], const float (&lo)[S4_R], const float (&hi)[S4_R], const float (&kk)[S4_R]) {
+    // window W(t) = t < 8 ? lo[t] : hi[t - 8];  acc[r] += K[jc + i] * W(8 + r - i)
+#pragma unroll
+    for (int i = 0; i < S4_R; ++i) {
+#pragma unroll
+        for (int r = 0; r < S4_R; ++r) {
+            const int t = S4_R + r - i;
+            acc[r] = fmaf(kk[i], t < S4_R ? lo[t] : hi[t - S4_R], acc[r]);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(32 * S4_WARPS)
-s4conv_kernel(const mugd_s4conv s, int nsplit) {
-    constexpr int NSUB = 32 / CH;
-    extern __shared__ float smem_s4[];     // us[L][CH] then ks[L][CH]
-    float* us = smem_s4;
-    float* ks = smem_s4 + (size_t)s.L * CH;
-    pdl_trigger();
+s4conv_kernel(const mugd_s4conv s, int nsplit, int Lpad) {
+    extern __shared__ float smem_s4[];
+    float* us = smem_s4;                                        // [S4_PAD + Lpad][S4_PITCH], row S4_PAD = time 0
+    float* ks = smem_s4 + (size_t)(S4_PAD + Lpad) * S4_PITCH;   // [Lpad + S4_R][S4_PITCH], zero beyond L
     pdl_wait();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int ch = lane % CH, sub = lane / CH;
-    const int h = blockIdx.x * CH + ch;
+    const int ch = lane & (S4_CH - 1), half = lane >> 4;
+    const int c0 = blockIdx.x * S4_CH;
     const int b = blockIdx.y;
     const int L = s.L;
-    const float* ub = s.u + (int64_t)b * L * s.ldu + blockIdx.x * CH;
-    const float* Kc = s.Kt + blockIdx.x * CH;  // tap j of channel c at Kc[j*H + c]
-    for (int i = threadIdx.x; i < L * CH; i += 32 * S4_WARPS) {
-        const int l = i / CH, c = i - l * CH;
-        us[i] = ub[(int64_t)l * s.ldu + c];
-        if (KS) ks[i] = Kc[(int64_t)l * s.H + c];
+    const float* ub = s.u + (int64_t)b * L * s.ldu + c0;
+    const float* Kc = s.Kt + c0;                                // tap j of channel c at Kc[j*H + c]
+    // ---- tiles (zero padded) ----
+    for (int i = threadIdx.x; i < (S4_PAD + Lpad) * S4_CH; i += 32 * S4_WARPS) {
+        const int row = i / S4_CH, c = i % S4_CH;
+        const int l = row - S4_PAD;
+        us[row * S4_PITCH + c] = (l >= 0 && l < L) ? ub[(int64_t)l * s.ldu + c] : 0.f;
+    }
+    for (int i = threadIdx.x; i < (Lpad + S4_R) * S4_CH; i += 32 * S4_WARPS) {
+        const int j = i / S4_CH, c = i % S4_CH;
+        ks[j * S4_PITCH + c] = (j < L) ? Kc[(int64_t)j * s.H + c] : 0.f;
     }
     __syncthreads();
 
-    const float* Kh = s.Kt + h;
+    const int h = c0 + ch;
     const float Dh = s.D[h];
     float* yb = s.y + (int64_t)b * L * s.ldy + h;
-    const int nblk = (L + S4_R - 1) / S4_R;
-    const int npairs = (nblk + 1) / 2;
+    const float* uz = us + S4_PAD * S4_PITCH + ch;              // uz[l * PITCH] = u[l, ch], valid for l >= -16
+    const float* kz = ks + ch;
+    const int nsb = Lpad / (2 * S4_R);                          // super blocks of 16 outputs
+    const int npairs = (nsb + 1) / 2;
     const int worker = blockIdx.z * S4_WARPS + warp;
     const int nworkers = nsplit * S4_WARPS;
-    // the cost of block bi grows linearly with bi (causal): pairing block p with block nblk-1-p gives every
-    // worker the same amount of work
+    // the cost of super block sb grows linearly with sb (causal): pairing sb with nsb-1-sb gives every worker the same work
     for (int p = worker; p < npairs; p += nworkers) {
 #pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
-            const int bi = half == 0 ? (nblk - 1 - p) : p;
-            if (half == 1 && bi == nblk - 1 - p) break;
-            const int l0 = bi * S4_R;
-            float acc[S4_R];
+        for (int which = 0; which < 2; ++which) {
+            const int sb = which == 0 ? (nsb - 1 - p) : p;
+            if (which == 1 && sb == nsb - 1 - p) break;
+            const int l0 = sb * 2 * S4_R + half * S4_R;          // this lane's first output
+            float acc[S4_R], wa[S4_R], wb[S4_R], kk[S4_R];
 #pragma unroll
-            for (int r = 0; r < S4_R; ++r) acc[r] = 0.f;
-            float win[2 * S4_R];               // win[i] = u[l0 - jc - 8 + i]
+            for (int r = 0; r < S4_R; ++r) { acc[r] = 0.f; wb[r] = uz[(l0 + r) * S4_PITCH]; }
+            // both halves run chunks jc = 0, 8, ..., sb*16 + 8 (the lower half's last chunk multiplies zeros)
+            const int nchunks = sb * 2 + 2;
+            const float* up = uz + (l0 - S4_R) * S4_PITCH;       // window rows l0 - jc - 8 + r
+            const float* kp = kz;
+#pragma unroll 1
+            for (int c = 0; c < nchunks; c += 2) {
+#pragma unroll
+                for (int r = 0; r < S4_R; ++r) { wa[r] = up[r * S4_PITCH]; kk[r] = kp[r * S4_PITCH]; }
+                s4_chunk(acc, wa, wb, kk);
+                up -= S4_R * S4_PITCH; kp += S4_R * S4_PITCH;
+#pragma unroll
+                for (int r = 0; r < S4_R; ++r) { wb[r] = up[r * S4_PITCH]; kk[r] = kp[r * S4_PITCH]; }
+                s4_chunk(acc, wb, wa, kk);
+                up -= S4_R * S4_PITCH; kp += S4_R * S4_PITCH;
+            }
 #pragma unroll
             for (int r = 0; r < S4_R; ++r) {
                 const int li = l0 + r;
-                win[S4_R + r] = (li < L) ? us[li * CH + ch] : 0.f;
-            }
-            for (int jc = 0; jc < l0 + S4_R; jc += S4_R) {
-                float kk[S4_R / NSUB];
-#pragma unroll
-                for (int r = 0; r < S4_R; ++r) {
-                    const int li = l0 - jc - S4_R + r;
-                    win[r] = (li >= 0) ? us[li * CH + ch] : 0.f;
-                }
-#pragma unroll
-                for (int i = 0; i < S4_R / NSUB; ++i) {
-                    const int j = jc + sub + NSUB * i;
-                    kk[i] = (j < L) ? (KS ? ks[j * CH + ch] : __ldg(Kh + (int64_t)j * s.H)) : 0.f;
-                }
-#pragma unroll
-                for (int i = 0; i < S4_R / NSUB; ++i) {
-#pragma unroll
-                    for (int r = 0; r < S4_R; ++r) {
-                        // tap jj = sub + NSUB*i : window index S4_R + r - jj.  `sub` is 0 when NSUB == 1, else 0/1: select
-                        const float wv = (NSUB == 1) ? win[S4_R + r - i] : (sub ? win[S4_R + r - 1 - NSUB * i] : win[S4_R + r - NSUB * i]);
-                        acc[r] = fmaf(kk[i], wv, acc[r]);
-                    }
-                }
-#pragma unroll
-                for (int r = 0; r < S4_R; ++r) win[S4_R + r] = win[r];
-            }
-            if (NSUB == 2) {
-#pragma unroll
-                for (int r = 0; r < S4_R; ++r) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], 16);
-            }
-            if (sub == 0) {
-#pragma unroll
-                for (int r = 0; r < S4_R; ++r) {
-                    const int li = l0 + r;
-                    if (li < L) yb[(int64_t)li * s.ldy] = gelu_f(acc[r] + Dh * us[li * CH + ch]);
-                }
+                if (li < L) yb[(int64_t)li * s.ldy] = gelu_f(acc[r] + Dh * uz[li * S4_PITCH]);
             }
         }
     }
 }
 
 int launch_s4conv(const DeviceInfo& dev, const mugd_s4conv& s, cudaStream_t st, int* launches) {
-    MUGD_REQUIRE(s.B > 0 && s.L > 0 && s.H > 0 && s.H % 32 == 0, "s4conv: H=%d must be a positive multiple of 32", s.H);
+    MUGD_REQUIRE(s.B > 0 && s.L > 0 && s.H > 0 && s.H % S4_CH == 0, "s4conv: H=%d must be a positive multiple of %d", s.H, S4_CH);
     MUGD_REQUIRE(s.ldu >= s.H && s.ldy >= s.H, "s4conv: ld < H");
-    const size_t tile32 = (size_t)s.L * 32 * sizeof(float);
-    MUGD_REQUIRE((int)tile32 <= dev.max_smem_optin, "s4conv: L=%d needs %zu B of shared memory (max %d)", s.L, tile32, dev.max_smem_optin);
-    // 0: u+K tiles of 32 channels; 1: u+K tiles of 16 channels; 2: u tile of 32 channels, K through L1
-    const int variant = (2 * tile32 <= (size_t)dev.max_smem_optin) ? 0 : (tile32 <= (size_t)dev.max_smem_optin ? 1 : 2);
+    const int Lpad = (s.L + 2 * S4_R - 1) / (2 * S4_R) * (2 * S4_R);
+    const size_t smem = ((size_t)(S4_PAD + Lpad) + (size_t)(Lpad + S4_R)) * S4_PITCH * sizeof(float);
+    MUGD_REQUIRE((int)smem <= dev.max_smem_optin, "s4conv: L=%d needs %zu B of shared memory (max %d)", s.L, smem, dev.max_smem_optin);
     static bool configured = false;
     if (!configured) {
-        MUGD_CHECK_CUDA(cudaFuncSetAttribute(s4conv_kernel<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.max_smem_optin));
-        MUGD_CHECK_CUDA(cudaFuncSetAttribute(s4conv_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.max_smem_optin));
-        MUGD_CHECK_CUDA(cudaFuncSetAttribute(s4conv_kernel<false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.max_smem_optin));
+        MUGD_CHECK_CUDA(cudaFuncSetAttribute(s4conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.max_smem_optin));
         configured = true;
     }
-    const int ch = variant == 1 ? 16 : 32;
-    const int base = (s.H / ch) * s.B;
-    const int npairs = ((s.L + S4_R - 1) / S4_R + 1) / 2;
+    const int base = (s.H / S4_CH) * s.B;
+    const int npairs = (Lpad / (2 * S4_R) + 1) / 2;
     int nsplit = 1;
     while (base * nsplit < 2 * dev.sm_count && nsplit * 2 * S4_WARPS <= npairs && nsplit < 16) nsplit *= 2;
-    dim3 grid(s.H / ch, s.B, nsplit);
-    if (variant == 0) MUGD_CHECK_CUDA(launch_k(s4conv_kernel<true, 32>, grid, dim3(32 * S4_WARPS), 2 * tile32, st, s, nsplit));
-    else if (variant == 1) MUGD_CHECK_CUDA(launch_k(s4conv_kernel<true, 16>, grid, dim3(32 * S4_WARPS), tile32, st, s, nsplit));
-    else MUGD_CHECK_CUDA(launch_k(s4conv_kernel<false, 32>, grid, dim3(32 * S4_WARPS), tile32, st, s, nsplit));
+    dim3 grid(s.H / S4_CH, s.B, nsplit);
+    MUGD_CHECK_CUDA(launch_k(s4conv_kernel, grid, dim3(32 * S4_WARPS), smem, st, s, nsplit, Lpad));
     if (launches) *launches += 1;
     return MUGD_OK;
 }
