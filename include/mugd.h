@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MUGD_ABI_VERSION 10
+#define MUGD_ABI_VERSION 11
 
 typedef struct mugd_handle mugd_handle;   /* one device + scratch state            */
 typedef struct mugd_plan mugd_plan;       /* validated launch plan (+ CUDA graph)  */
@@ -213,6 +213,24 @@ int  mugd_plan_capture(mugd_plan* p, void* stream);        /* build + instantiat
 int  mugd_plan_replay(mugd_plan* p, int32_t times, void* stream); /* launch the graph `times` times     */
 int  mugd_plan_launch_count(mugd_plan* p);                 /* kernels launched by one run of the plan   */
 void mugd_plan_destroy(mugd_plan* p);
+
+/* ---- the sampler loop from ONE call: DDIMSampler.ddim_sampling's for-loop (ddim.py:136-157) -------------------------------
+ * n_steps x { replay the captured evaluation plan (one CUDA graph = Beff U-Net evaluations) ; run the `tail` ops eagerly on the same
+ * stream: MUGD_OP_DDIM_UPDATE (CFG combine + x_{t-1}) and MUGD_OP_STEP_ADVANCE (device step counter) }.  Nothing synchronises; the
+ * step-dependent rows (time embedding, DDIM coefficients) are selected on the device by the counter.  `eval_plan` must be captured. */
+int  mugd_sample(mugd_plan* eval_plan, const mugd_op* tail, int32_t n_tail, int32_t n_steps, void* stream);
+
+/* ---- plans on disk: a host without Python (examples/host_c) loads what the Python plan compiler produced ---------------------
+ * Every pointer of a plan lies in one of a few device allocations ("regions": weight blob, activation arena, side tables, the
+ * caller's staging buffers).  mugd_plan_save stores each pointer as (region, offset); mugd_plan_load resolves them against the
+ * loader's allocations, matched by name (each at least as large as recorded).  Region contents are the caller's business. */
+typedef struct mugd_region { const char* name; void* base; int64_t bytes; } mugd_region;
+int  mugd_plan_save(mugd_plan* p, const mugd_region* regions, int32_t n_regions, const char* path);
+int  mugd_plan_load(mugd_handle* h, const char* path, const mugd_region* regions, int32_t n_regions, mugd_plan** out);
+/* the (relocated) ops of a plan, e.g. to hand a loaded update/advance plan to mugd_sample as its tail; owned by the plan */
+int  mugd_plan_ops(mugd_plan* p, const mugd_op** ops, int32_t* n_ops);
+/* names and sizes of the regions a plan file refers to (names[i] receives the text, out[i].name points at it); n_regions always set */
+int  mugd_plan_regions(const char* path, mugd_region* out, char (*names)[48], int32_t max_regions, int32_t* n_regions);
 
 /* ---- S4 kernel generation: SSKernelNPLR.forward, s4.py:706-832 (once per model and length) ----- */
 int  mugd_s4_kernel_gen(mugd_handle* h,

@@ -37,6 +37,9 @@ struct mugd_plan {
 
 namespace mugd {
 
+const std::vector<mugd_op>& plan_ops(const mugd_plan* p) { return p->ops; }
+int plan_from_ops(mugd_handle* h, const mugd_op* ops, int32_t n, mugd_plan** out) { return mugd_plan_create(h, ops, n, out); }
+
 static int dispatch(mugd_handle* h, const mugd_op& op, cudaStream_t st, int* launches) {
     switch (op.kind) {
         case MUGD_OP_GEMM: return launch_gemm(h->dev, op.u.gemm, h->default_gemm_impl, st, launches);
@@ -187,12 +190,33 @@ int mugd_plan_replay(mugd_plan* p, int32_t times, void* stream) {
     return MUGD_OK;
 }
 
+int mugd_sample(mugd_plan* eval_plan, const mugd_op* tail, int32_t n_tail, int32_t n_steps, void* stream) {
+    MUGD_REQUIRE(eval_plan && eval_plan->exec, "mugd_sample: the evaluation plan must be captured (mugd_plan_capture)");
+    MUGD_REQUIRE(n_steps >= 0 && n_tail >= 0 && (n_tail == 0 || tail), "mugd_sample: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int i = 0; i < n_steps; ++i) {
+        MUGD_CHECK_CUDA(cudaGraphLaunch(eval_plan->exec, st));
+        for (int k = 0; k < n_tail; ++k) {
+            int rc = dispatch(eval_plan->h, tail[k], st, nullptr);
+            if (rc != MUGD_OK) return rc;
+        }
+    }
+    return MUGD_OK;
+}
+
 int mugd_abi_sizes(int32_t* out, int32_t n) {
     MUGD_REQUIRE(out && n >= 11, "abi_sizes: need room for 11 entries");
     out[0] = sizeof(mugd_op); out[1] = sizeof(mugd_gemm); out[2] = sizeof(mugd_groupnorm);
     out[3] = sizeof(mugd_layernorm); out[4] = sizeof(mugd_attention); out[5] = sizeof(mugd_s4conv);
     out[6] = sizeof(mugd_ddim_update); out[7] = sizeof(mugd_transpose); out[8] = sizeof(mugd_copy2d);
     out[9] = sizeof(mugd_notes); out[10] = sizeof(mugd_embed);
+    return MUGD_OK;
+}
+
+int mugd_plan_ops(mugd_plan* p, const mugd_op** ops, int32_t* n_ops) {
+    MUGD_REQUIRE(p && ops && n_ops, "plan_ops: bad arguments");
+    *ops = p->ops.data();
+    *n_ops = (int32_t)p->ops.size();
     return MUGD_OK;
 }
 

@@ -31,11 +31,11 @@ namespace mugd {
 // Per chunk of 8 taps a lane loads 8 new window values + 8 taps and issues 64 FMAs; the 15-wide window lives in two register
 // arrays whose roles alternate (no copies).
 // =====================================================================================================
-constexpr int S4_WARPS = 8;
+constexpr int S4_WARPS = 16;       // 4 warps per scheduler hide the shared-memory latency of the dependent load -> FMA chains
 constexpr int S4_R = 8;          // outputs per lane and taps per chunk
 constexpr int S4_CH = 16;        // channels per CTA
 constexpr int S4_PITCH = 18;     // floats per time step in shared memory (8 * 18 = 144 = 16 mod 32: the halves hit disjoint banks)
-constexpr int S4_PAD = 16;       // zero rows in front of u (the last chunk of the lower half reads u[-16 .. -9])
+constexpr int S4_PAD = 32;       // zero rows in front of u (last chunk of the lower half: u[-16 .. -9]; the prefetch reaches 16 rows further)
 
 __device__ __forceinline__ void s4_chunk(float (&acc)[S4_R], const float (&lo)[S4_R], const float (&hi)[S4_R], const float (&kk)[S4_R]) {
     // window W(t) = t < 8 ? lo[t] : hi[t - 8];  acc[r] += K[jc + i] * W(8 + r - i)
@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(32 * S4_WARPS)
 s4conv_kernel(const mugd_s4conv s, int nsplit, int Lpad) {
     extern __shared__ float smem_s4[];
     float* us = smem_s4;                                        // [S4_PAD + Lpad][S4_PITCH], row S4_PAD = time 0
-    float* ks = smem_s4 + (size_t)(S4_PAD + Lpad) * S4_PITCH;   // [Lpad + S4_R][S4_PITCH], zero beyond L
+    float* ks = smem_s4 + (size_t)(S4_PAD + Lpad) * S4_PITCH;   // [Lpad + 3 * S4_R][S4_PITCH], zero beyond L
     pdl_wait();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ch = lane & (S4_CH - 1), half = lane >> 4;
@@ -68,7 +68,7 @@ s4conv_kernel(const mugd_s4conv s, int nsplit, int Lpad) {
         const int l = row - S4_PAD;
         us[row * S4_PITCH + c] = (l >= 0 && l < L) ? ub[(int64_t)l * s.ldu + c] : 0.f;
     }
-    for (int i = threadIdx.x; i < (Lpad + S4_R) * S4_CH; i += 32 * S4_WARPS) {
+    for (int i = threadIdx.x; i < (Lpad + 3 * S4_R) * S4_CH; i += 32 * S4_WARPS) {
         const int j = i / S4_CH, c = i % S4_CH;
         ks[j * S4_PITCH + c] = (j < L) ? Kc[(int64_t)j * s.H + c] : 0.f;
     }
@@ -77,7 +77,7 @@ s4conv_kernel(const mugd_s4conv s, int nsplit, int Lpad) {
     const int h = c0 + ch;
     const float Dh = s.D[h];
     float* yb = s.y + (int64_t)b * L * s.ldy + h;
-    const float* uz = us + S4_PAD * S4_PITCH + ch;              // uz[l * PITCH] = u[l, ch], valid for l >= -16
+    const float* uz = us + S4_PAD * S4_PITCH + ch;              // uz[l * PITCH] = u[l, ch], valid for l >= -S4_PAD
     const float* kz = ks + ch;
     const int nsb = Lpad / (2 * S4_R);                          // super blocks of 16 outputs
     const int npairs = (nsb + 1) / 2;
@@ -90,23 +90,27 @@ s4conv_kernel(const mugd_s4conv s, int nsplit, int Lpad) {
             const int sb = which == 0 ? (nsb - 1 - p) : p;
             if (which == 1 && sb == nsb - 1 - p) break;
             const int l0 = sb * 2 * S4_R + half * S4_R;          // this lane's first output
-            float acc[S4_R], wa[S4_R], wb[S4_R], kk[S4_R];
-#pragma unroll
-            for (int r = 0; r < S4_R; ++r) { acc[r] = 0.f; wb[r] = uz[(l0 + r) * S4_PITCH]; }
+            float acc[S4_R], wa[S4_R], wb[S4_R], wc[S4_R], ka[S4_R], kb[S4_R];
             // both halves run chunks jc = 0, 8, ..., sb*16 + 8 (the lower half's last chunk multiplies zeros)
             const int nchunks = sb * 2 + 2;
             const float* up = uz + (l0 - S4_R) * S4_PITCH;       // window rows l0 - jc - 8 + r
             const float* kp = kz;
+#pragma unroll
+            for (int r = 0; r < S4_R; ++r) { acc[r] = 0.f; wb[r] = uz[(l0 + r) * S4_PITCH]; wa[r] = up[r * S4_PITCH]; ka[r] = kp[r * S4_PITCH]; }
+            // software pipeline: the window rows and taps of chunk c+1 are loaded before the 64 FMAs of chunk c are issued (the
+            // rows of the padding in front of u / behind K make the last prefetch harmless)
 #pragma unroll 1
             for (int c = 0; c < nchunks; c += 2) {
-#pragma unroll
-                for (int r = 0; r < S4_R; ++r) { wa[r] = up[r * S4_PITCH]; kk[r] = kp[r * S4_PITCH]; }
-                s4_chunk(acc, wa, wb, kk);
                 up -= S4_R * S4_PITCH; kp += S4_R * S4_PITCH;
 #pragma unroll
-                for (int r = 0; r < S4_R; ++r) { wb[r] = up[r * S4_PITCH]; kk[r] = kp[r * S4_PITCH]; }
-                s4_chunk(acc, wb, wa, kk);
+                for (int r = 0; r < S4_R; ++r) { wc[r] = up[r * S4_PITCH]; kb[r] = kp[r * S4_PITCH]; }
+                s4_chunk(acc, wa, wb, ka);                       // lo = wa, hi = wb
                 up -= S4_R * S4_PITCH; kp += S4_R * S4_PITCH;
+#pragma unroll
+                for (int r = 0; r < S4_R; ++r) { wb[r] = up[r * S4_PITCH]; ka[r] = kp[r * S4_PITCH]; }
+                s4_chunk(acc, wc, wa, kb);                       // lo = wc, hi = wa
+#pragma unroll
+                for (int r = 0; r < S4_R; ++r) { const float t = wa[r]; wa[r] = wb[r]; wb[r] = wc[r]; (void)t; }
             }
 #pragma unroll
             for (int r = 0; r < S4_R; ++r) {
@@ -121,7 +125,7 @@ int launch_s4conv(const DeviceInfo& dev, const mugd_s4conv& s, cudaStream_t st, 
     MUGD_REQUIRE(s.B > 0 && s.L > 0 && s.H > 0 && s.H % S4_CH == 0, "s4conv: H=%d must be a positive multiple of %d", s.H, S4_CH);
     MUGD_REQUIRE(s.ldu >= s.H && s.ldy >= s.H, "s4conv: ld < H");
     const int Lpad = (s.L + 2 * S4_R - 1) / (2 * S4_R) * (2 * S4_R);
-    const size_t smem = ((size_t)(S4_PAD + Lpad) + (size_t)(Lpad + S4_R)) * S4_PITCH * sizeof(float);
+    const size_t smem = ((size_t)(S4_PAD + Lpad) + (size_t)(Lpad + 3 * S4_R)) * S4_PITCH * sizeof(float);
     MUGD_REQUIRE((int)smem <= dev.max_smem_optin, "s4conv: L=%d needs %zu B of shared memory (max %d)", s.L, smem, dev.max_smem_optin);
     static bool configured = false;
     if (!configured) {

@@ -18,7 +18,7 @@ CONV_NONE, CONV_SAME, CONV_DOWN, CONV_UP, CONV_TAPS = range(5)
 ACT_NONE, ACT_SILU, ACT_GELU = range(3)
 GATE_NONE, GATE_GEGLU, GATE_GLU = range(3)
 GEMM_AUTO, GEMM_SIMT, GEMM_TC = range(3)
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 _f = C.c_void_p  # device pointers travel as integers
 
@@ -110,6 +110,10 @@ def make_op(kind: int, desc, tag: int = 0) -> Op:
     return op
 
 
+class Region(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("base", _f), ("bytes", C.c_int64)]
+
+
 class MugdError(RuntimeError):
     pass
 
@@ -155,6 +159,9 @@ def load() -> C.CDLL:
     mine = [C.sizeof(t) for t in (Op, Gemm, GroupNorm, LayerNorm, Attention, S4Conv, DdimUpdate, Transpose, Copy2D, Notes, Embed)]
     if list(sizes) != mine:
         raise MugdError(f"struct layout mismatch: C {list(sizes)} vs ctypes {mine}")
+    lib.mugd_sample.argtypes = [C.c_void_p, C.POINTER(Op), C.c_int32, C.c_int32, C.c_void_p]
+    lib.mugd_plan_save.argtypes = [C.c_void_p, C.POINTER(Region), C.c_int32, C.c_char_p]
+    lib.mugd_plan_load.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(Region), C.c_int32, C.POINTER(C.c_void_p)]
     lib.mugd_set_tc_single_pass_tf32.argtypes = [C.c_void_p, C.c_int]
     lib.mugd_set_attention_impl.argtypes = [C.c_void_p, C.c_int]
     lib.mugd_debug_set_tc_tile_n.argtypes = [C.c_int]
@@ -184,5 +191,5 @@ EXPORTED_SYMBOLS = [
     "mugd_op_run", "mugd_plan_create", "mugd_plan_run", "mugd_plan_capture", "mugd_plan_replay",
     "mugd_plan_launch_count", "mugd_plan_destroy", "mugd_s4_kernel_gen", "mugd_fill_i32", "mugd_abi_sizes", "mugd_gemm_tc_query",
     "mugd_set_pdl", "mugd_set_tc_single_pass_tf32", "mugd_set_attention_impl", "mugd_debug_set_tc_tile_n", "mugd_debug_set_tc_cost",
-    "mugd_debug_set_attention_dump", "mugd_debug_set_tc_timing",
+    "mugd_debug_set_attention_dump", "mugd_debug_set_tc_timing", "mugd_sample", "mugd_plan_save", "mugd_plan_load", "mugd_plan_regions", "mugd_plan_ops",
 ]

@@ -261,6 +261,12 @@ class Session:
         args = t[:, None].float() * freqs[None]
         emb = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
         self.temb[:R].copy_(emb.to(eng.device))
+        eng.run_ops(self.timestep_ops(R))
+
+    def timestep_ops(self, R: int) -> OpList:
+        """the three GEMMs that turn R sinusoid rows (self.temb) into R rows of the fused ResBlock embedding table"""
+        cfg = self.engine.cfg.unet
+        eng = self.engine
         ops = OpList(tc_weight_map(eng.blob, eng.wbase))
         up = self.comp.prefix
         tv = View(_ptr(self.temb), cfg.model_channels, R, cfg.model_channels)
@@ -274,7 +280,7 @@ class Session:
         ops.gemm(h1, w(up + "time_embed.2.weight"), cfg.time_embed_dim, cfg.time_embed_dim, h2, bias=w(up + "time_embed.2.bias"),
                  act=L_.ACT_SILU)
         ops.gemm(h2, w(up + "emb_all.weight"), self.emb_table.shape[1], cfg.time_embed_dim, et, bias=w(up + "emb_all.bias"))
-        eng.run_ops(ops)
+        return ops
 
     def set_context(self, context):
         """context [Beff, ctx_dim, T] (reference layout; or a list of such tensors that follow each other along the batch, e.g.
@@ -290,19 +296,26 @@ class Session:
         if T != self.ctx_tokens:
             self.ctx_tokens = T
             self._build(self.comp)            # Lk is baked into the attention ops
+        eng.run_ops(self.context_ops([(_ptr(c), int(c.shape[0])) for c in parts], T))
+        self._keep = parts
+
+    def context_ops(self, parts: Sequence, T: int) -> OpList:
+        """parts: (device address of a [b, ctx_dim, T] tensor, b) in batch order -> transposes + the 16 K|V projections"""
+        eng = self.engine
+        cfg = eng.cfg.unet
+        Cd = cfg.context_dim
+        Bc = sum(b for _, b in parts)
         ops = OpList(tc_weight_map(eng.blob, eng.wbase))
         row = 0
-        for c in parts:
-            ops.transpose(_ptr(c), _ptr(self.ctx) + 4 * row * cfg.context_dim, 0, cfg.context_dim, int(c.shape[0]), Cd, T, True)
-            row += int(c.shape[0]) * T
-        context = parts
-        cv = View(_ptr(self.ctx), cfg.context_dim, Bc * T, cfg.context_dim)
+        for addr, bpart in parts:
+            ops.transpose(addr, _ptr(self.ctx) + 4 * row * Cd, 0, Cd, bpart, Cd, T, True)
+            row += bpart * T
+        cv = View(_ptr(self.ctx), Cd, Bc * T, Cd)
         blocks = [b for b in _all_blocks(self.comp) if b.kind == "attn"]
         for b, kv in zip(blocks, self.ctx_kv):
             o = View(_ptr(kv), kv.shape[1], Bc * T, kv.shape[1])
-            ops.gemm(cv, self.comp.w(b.prefix + "transformer_blocks.0.attn2.kv.weight"), 2 * b.cin, cfg.context_dim, o, Lout=T)
-        eng.run_ops(ops)
-        self._keep = context
+            ops.gemm(cv, self.comp.w(b.prefix + "transformer_blocks.0.attn2.kv.weight"), 2 * b.cin, Cd, o, Lout=T)
+        return ops
 
     def set_audio(self, audios: Sequence[torch.Tensor], dup: bool = False):
         """The last ``levels`` entries of the wave-encoder output list (unet.py:527-543), NCL layout, written
@@ -311,26 +324,37 @@ class Session:
         cfg = self.engine.cfg.unet
         w4 = [a.to(self.engine.device, torch.float32).contiguous() for a in list(audios)[-cfg.levels:]]
         Bh = self.Beff // 2 if dup else self.Beff
+        for lvl in range(cfg.levels):
+            assert w4[lvl].shape == (Bh, cfg.audio_channels[lvl], self.Lz >> lvl), (w4[lvl].shape, lvl)
+        self.engine.run_ops(self.audio_ops([_ptr(a) for a in w4], dup))
+        self._keep_audio = w4
+
+    def audio_ops(self, addrs: Sequence[int], dup: bool) -> OpList:
+        """addrs[lvl] = device address of the [Beff (or Beff/2 when dup), C_lvl, L_lvl] audio feature map of level lvl"""
+        cfg = self.engine.cfg.unet
+        Bh = self.Beff // 2 if dup else self.Beff
         ops = OpList()
         for lvl, view in self.audio_slots:
-            a = w4[lvl]
-            assert a.shape == (Bh, cfg.audio_channels[lvl], self.Lz >> lvl), (a.shape, lvl)
-            ops.transpose(_ptr(a), view.ptr, 0, view.ld, Bh, a.shape[1], a.shape[2], True)
+            Cc, Lr = cfg.audio_channels[lvl], self.Lz >> lvl
+            ops.transpose(addrs[lvl], view.ptr, 0, view.ld, Bh, Cc, Lr, True)
             if dup:
-                ops.transpose(_ptr(a), view.r(Bh * a.shape[2], 2 * Bh * a.shape[2]).ptr, 0, view.ld, Bh, a.shape[1], a.shape[2], True)
-        self.engine.run_ops(ops)
-        self._keep_audio = w4
+                ops.transpose(addrs[lvl], view.r(Bh * Lr, 2 * Bh * Lr).ptr, 0, view.ld, Bh, Cc, Lr, True)
+        return ops
 
     def load_x(self, x: torch.Tensor, dup: bool):
         """x [B,C,L] -> xin rows (both halves when dup)."""
         x = x.to(self.engine.device, torch.float32).contiguous()
         B, Cc, Lr = x.shape
-        ops = OpList()
-        ops.transpose(_ptr(x), self.xin.ptr, 0, self.xin.ld, B, Cc, Lr, True)
-        if dup:
-            ops.transpose(_ptr(x), self.xin.r(B * Lr, 2 * B * Lr).ptr, 0, self.xin.ld, B, Cc, Lr, True)
-        self.engine.run_ops(ops)
+        self.engine.run_ops(self.loadx_ops(_ptr(x), B, dup))
         self._keep_x = x
+
+    def loadx_ops(self, addr: int, B: int, dup: bool) -> OpList:
+        Cc, Lr = self.engine.cfg.unet.in_channels, self.Lz
+        ops = OpList()
+        ops.transpose(addr, self.xin.ptr, 0, self.xin.ld, B, Cc, Lr, True)
+        if dup:
+            ops.transpose(addr, self.xin.r(B * Lr, 2 * B * Lr).ptr, 0, self.xin.ld, B, Cc, Lr, True)
+        return ops
 
     def read_rows(self, view: View, B: int, Cc: int, Lr: int) -> torch.Tensor:
         out = torch.empty(B, Cc, Lr, device=self.engine.device)
@@ -347,6 +371,15 @@ class Session:
             self.plan.replay(1)
         else:
             self.plan.run()
+
+    def run_steps(self, n: int, tail: OpList):
+        """n DDIM steps from ONE C call (mugd_sample): n x {graph replay of the evaluation ; the tail ops (update, step advance)}"""
+        if not self.plan.captured:
+            self.plan.run()                   # warm-up (lazy module load, cudaFuncSetAttribute) outside capture
+            self.plan.capture()
+        self.engine.attach_workspace(tail)
+        arr = tail.array()
+        L_.check(self.engine.lib.mugd_sample(self.plan.handle, arr, len(tail.ops), n, _stream()), "mugd_sample")
 
     def set_step(self, value: int):
         L_.check(self.engine.lib.mugd_fill_i32(_ptr(self.step), value, _stream()), "fill_i32")

@@ -307,31 +307,50 @@ class DDIMSampler(object):
                 eng.run_ops(ops)
                 return out
 
-            for i, step in enumerate(iterator):
-                index = total - i - 1
-                if mask is not None:
-                    assert x0 is not None
-                    tsb = torch.full((B,), int(step), device=dev, dtype=torch.long)
-                    x_orig = model.q_sample(x0.to(dev), tsb)
-                    xm = x_orig * mask + (1. - mask) * current_x()
-                    sess.load_x(xm, dup=cfg_on)
-                if has_noise or match_rng:
-                    nz = torch.randn(shape, device=dev)                      # ddim.py:192
-                    if noise_dropout > 0.:
-                        # dropout(sigma * n * T) == sigma * T * dropout(n): same Bernoulli draw, same 1/(1-p) scale (:193-194)
-                        nz = torch.nn.functional.dropout(nz, p=noise_dropout)
-                if has_noise:
-                    ops = OpList()
-                    ops.transpose(_ptr(nz), _ptr(noise_nlc), 0, Cz, B, Cz, Lz, True)
-                    eng.run_ops(ops)
-                sess.eval(graph=True)
-                eng.run_ops(tail)
-                if callback:
-                    callback(i)
-                if img_callback:
-                    img_callback(current_pred(), i)
-                if index % log_every_t == 0 or index == total - 1:
+            per_step_host_work = (mask is not None or has_noise or match_rng or callback is not None or img_callback is not None)
+            if not per_step_host_work:
+                # nothing on the host between steps: run the stretches between two recorded intermediates from ONE C call each
+                # (mugd_sample: n x {graph replay, CFG/DDIM update, step advance}, no synchronisation)
+                it = iter(iterator)
+                i = 0
+                while i < total:
+                    j = i
+                    while not ((total - j - 1) % log_every_t == 0 or (total - j - 1) == total - 1):
+                        j += 1
+                    sess.run_steps(j - i + 1, tail)
+                    for _ in range(j - i + 1):
+                        next(it, None)                                          # keeps a progress bar (tqdm_class) moving
                     intermediates['x_inter'].append(current_x())
                     intermediates['pred_x0'].append(current_pred())
+                    i = j + 1
+                for _ in it:
+                    pass
+            else:
+                for i, step in enumerate(iterator):
+                    index = total - i - 1
+                    if mask is not None:
+                        assert x0 is not None
+                        tsb = torch.full((B,), int(step), device=dev, dtype=torch.long)
+                        x_orig = model.q_sample(x0.to(dev), tsb)
+                        xm = x_orig * mask + (1. - mask) * current_x()
+                        sess.load_x(xm, dup=cfg_on)
+                    if has_noise or match_rng:
+                        nz = torch.randn(shape, device=dev)                      # ddim.py:192
+                        if noise_dropout > 0.:
+                            # dropout(sigma * n * T) == sigma * T * dropout(n): same Bernoulli draw, same 1/(1-p) scale (:193-194)
+                            nz = torch.nn.functional.dropout(nz, p=noise_dropout)
+                    if has_noise:
+                        ops = OpList()
+                        ops.transpose(_ptr(nz), _ptr(noise_nlc), 0, Cz, B, Cz, Lz, True)
+                        eng.run_ops(ops)
+                    sess.eval(graph=True)
+                    eng.run_ops(tail)
+                    if callback:
+                        callback(i)
+                    if img_callback:
+                        img_callback(current_pred(), i)
+                    if index % log_every_t == 0 or index == total - 1:
+                        intermediates['x_inter'].append(current_x())
+                        intermediates['pred_x0'].append(current_pred())
             self.last_launches_per_step = sess.plan.launches + 2
             return current_x(), intermediates
