@@ -273,40 +273,48 @@ __device__ __forceinline__ void tc_store_tile(const mugd_gemm& g, uint32_t stage
                                               uint32_t rowstat) {
     constexpr int SP = BN + 4;
     constexpr int C4 = BN / 4;
-    constexpr int U = 8;
+    constexpr int NU = TC_BM * C4 / TC_THREADS;          // float4 per thread: 8 / 16 / 32 for BN = 64 / 128 / 256
+    constexpr int U = NU < 16 ? NU : 16;                 // in flight together
     constexpr int SEG = C4 < 32 ? C4 : 32;
+    static_assert(TC_THREADS % C4 == 0, "a thread keeps its column quad for the whole tile");
+    // this thread's column quad is the same for every row it visits: bias / column sums are loaded once
+    const int c4 = (int)threadIdx.x % C4;
+    const int nn = n0 + c4 * 4;
+    const bool col_ok = nn < g.N;
+    float4 bia = make_float4(0.f, 0.f, 0.f, 0.f), cs = bia;
+    if (col_ok && g.bias) bia = ld_f4(g.bias + nn);
+    if constexpr (MODE == TC_EPI_LN) {
+        if (col_ok) cs = ld_f4(g.ln_colsum + nn);
+    }
+    const bool has_res = GATE == MUGD_GATE_NONE && g.residual != nullptr;
 #pragma unroll 1
-    for (int i0 = 0; i0 < TC_BM * C4; i0 += TC_THREADS * U) {
-        float4 acc[U], bia[U], rvv[U], res[U], cs[U];
-        float2 ln[U];
+    for (int i0 = 0; i0 < NU; i0 += U) {
+        // every global load of this pass is issued before anything is consumed: ONE memory round trip per 16 rows
+        float4 res[U], rvv[U];
         bool ok[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int idx = i0 + u * TC_THREADS + (int)threadIdx.x;
-            const int row = idx / C4, c4 = idx - row * C4;
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(acc[u].x), "=f"(acc[u].y), "=f"(acc[u].z), "=f"(acc[u].w)
-                         : "r"(stage + (uint32_t)(row * SP + c4 * 4) * 4u));
-            const int m = m_base + row, nn = n0 + c4 * 4;
-            ok[u] = row < rows_valid && m < g.M && nn < g.N;
-            bia[u] = rvv[u] = res[u] = cs[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            ln[u] = make_float2(0.f, 1.f);
+            const int row = (int)threadIdx.x / C4 + (i0 + u) * (TC_THREADS / C4);
+            const int m = m_base + row;
+            ok[u] = row < rows_valid && m < g.M && col_ok;
+            res[u] = rvv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (ok[u]) {
-                if (g.bias) bia[u] = ld_f4(g.bias + nn);
+                if (has_res) res[u] = ld_f4(g.residual + (int64_t)m * g.ldr + nn);
                 if (rowvec) rvv[u] = ld_f4(rowvec + (int64_t)(m / g.Lout) * g.rowvec_b_stride + nn);
-                if (GATE == MUGD_GATE_NONE && g.residual) res[u] = ld_f4(g.residual + (int64_t)m * g.ldr + nn);
-                if constexpr (MODE == TC_EPI_LN) {
-                    cs[u] = ld_f4(g.ln_colsum + nn);
-                    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(ln[u].x), "=f"(ln[u].y) : "r"(rowstat + (uint32_t)row * 8u));
-                }
             }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int idx = i0 + u * TC_THREADS + (int)threadIdx.x;
-            const int row = idx / C4, c4 = idx - row * C4;
+            const int row = (int)threadIdx.x / C4 + (i0 + u) * (TC_THREADS / C4);
             const int m = m_base + row;
+            float4 acc;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(acc.x), "=f"(acc.y), "=f"(acc.z), "=f"(acc.w)
+                         : "r"(stage + (uint32_t)(row * SP + c4 * 4) * 4u));
+            float2 ln = make_float2(0.f, 1.f);
+            if constexpr (MODE == TC_EPI_LN)
+                asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(ln.x), "=f"(ln.y) : "r"(rowstat + (uint32_t)row * 8u));
             float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ok[u]) o = tc_finish4<ACT, GATE, MODE == TC_EPI_LN>(g, acc[u], bia[u], rvv[u], res[u], cs[u], ln[u], m, n0 + c4 * 4);
+            if (ok[u]) o = tc_finish4<ACT, GATE, MODE == TC_EPI_LN>(g, acc, bia, rvv[u], res[u], cs, ln, m, nn);
             if constexpr (MODE == TC_EPI_SINK) tc_row_sink<SEG>(g.row_moments, ok[u] ? m : -1, o);
         }
     }

@@ -9,30 +9,14 @@
 
 namespace mugd {
 
-// One CTA per (group, sample).  The (L x cg) slab of a group is read twice (moments, then apply);
-// the second read is served by L1/L2.  cg is a multiple of 4 so every float4 belongs to one group.
+// One CTA per (group, sample).  The (L x cg) slab of a group is read ONCE: every thread pulls its float4s into registers with all
+// loads in flight together (one memory round trip), the block reduces the fp64 moments, and the values are normalised straight from
+// the registers.  Slabs of more than GN_MAXV float4 per thread (L * cg > 32768 elements) take the two-pass form below.
+// cg is a multiple of 4 so every float4 belongs to one group.
 constexpr int GN_THREADS = 256;
+constexpr int GN_MAXV = 32;
 
-__global__ void __launch_bounds__(GN_THREADS)
-groupnorm_silu_kernel(const float* __restrict__ x, int64_t ldx, float* __restrict__ y, int64_t ldy,
-                      const float* __restrict__ gamma, const float* __restrict__ beta,
-                      int L, int C, int G, float eps, int silu) {
-    pdl_trigger();
-    pdl_wait();
-    const int g = blockIdx.x, b = blockIdx.y;
-    const int cg = C / G;
-    const int q = cg >> 2;                 // float4 per row of this group
-    const int total = L * q;
-    const float* xb = x + (int64_t)b * L * ldx + (int64_t)g * cg;
-    float* yb = y + (int64_t)b * L * ldy + (int64_t)g * cg;
-
-    double s = 0.0, ss = 0.0;
-    for (int i = threadIdx.x; i < total; i += GN_THREADS) {
-        const int row = i / q, qq = i - row * q;
-        const float4 v = ld_f4(xb + (int64_t)row * ldx + qq * 4);
-        s += (double)v.x + (double)v.y + (double)v.z + (double)v.w;
-        ss += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
-    }
+__device__ __forceinline__ void gn_block_stats(double s, double ss, double n, float eps, float& mean, float& rstd) {
     __shared__ double red[2][GN_THREADS / 32];
     __shared__ float stats[2];
     s = warp_sum(s);
@@ -44,15 +28,89 @@ groupnorm_silu_kernel(const float* __restrict__ x, int64_t ldx, float* __restric
         double ts = 0.0, tss = 0.0;
 #pragma unroll
         for (int w = 0; w < GN_THREADS / 32; ++w) { ts += red[0][w]; tss += red[1][w]; }
-        const double n = (double)L * cg;
-        const double mean = ts / n;
-        double var = tss / n - mean * mean;
+        const double m = ts / n;
+        double var = tss / n - m * m;
         if (var < 0.0) var = 0.0;
-        stats[0] = (float)mean;
+        stats[0] = (float)m;
         stats[1] = (float)(1.0 / sqrt(var + (double)eps));
     }
     __syncthreads();
-    const float mean = stats[0], rstd = stats[1];
+    mean = stats[0];
+    rstd = stats[1];
+}
+
+template <int NV>
+__global__ void __launch_bounds__(GN_THREADS)
+groupnorm_silu_reg_kernel(const float* __restrict__ x, int64_t ldx, float* __restrict__ y, int64_t ldy,
+                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                          int L, int C, int G, float eps, int silu) {
+    pdl_wait();
+    const int g = blockIdx.x, b = blockIdx.y;
+    const int cg = C / G;
+    const int q = cg >> 2;                 // float4 per row of this group
+    const int total = L * q;
+    const float* xb = x + (int64_t)b * L * ldx + (int64_t)g * cg;
+    float* yb = y + (int64_t)b * L * ldy + (int64_t)g * cg;
+    float4 v[NV];
+#pragma unroll
+    for (int u = 0; u < NV; ++u) {
+        const int i = (int)threadIdx.x + u * GN_THREADS;
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < total) {
+            const int row = i / q, qq = i - row * q;
+            v[u] = ld_f4(xb + (int64_t)row * ldx + qq * 4);
+        }
+    }
+    double s = 0.0, ss = 0.0;
+#pragma unroll
+    for (int u = 0; u < NV; ++u) {          // (slots past `total` hold zeros)
+        s += (double)v[u].x + (double)v[u].y + (double)v[u].z + (double)v[u].w;
+        ss += (double)v[u].x * v[u].x + (double)v[u].y * v[u].y + (double)v[u].z * v[u].z + (double)v[u].w * v[u].w;
+    }
+    float mean, rstd;
+    gn_block_stats(s, ss, (double)L * cg, eps, mean, rstd);
+    const float* gm = gamma + g * cg;
+    const float* bt = beta + g * cg;
+#pragma unroll
+    for (int u = 0; u < NV; ++u) {
+        const int i = (int)threadIdx.x + u * GN_THREADS;
+        if (i < total) {
+            const int row = i / q, qq = i - row * q;
+            const float4 ga = ld_f4(gm + qq * 4);
+            const float4 be = ld_f4(bt + qq * 4);
+            float4 o;
+            o.x = (v[u].x - mean) * rstd * ga.x + be.x;
+            o.y = (v[u].y - mean) * rstd * ga.y + be.y;
+            o.z = (v[u].z - mean) * rstd * ga.z + be.z;
+            o.w = (v[u].w - mean) * rstd * ga.w + be.w;
+            if (silu) { o.x = silu_f(o.x); o.y = silu_f(o.y); o.z = silu_f(o.z); o.w = silu_f(o.w); }
+            st_f4(yb + (int64_t)row * ldy + qq * 4, o);
+        }
+    }
+}
+
+// two-pass form for slabs that do not fit the registers: moments, then apply (the second read is served by L1/L2)
+__global__ void __launch_bounds__(GN_THREADS)
+groupnorm_silu_kernel(const float* __restrict__ x, int64_t ldx, float* __restrict__ y, int64_t ldy,
+                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                      int L, int C, int G, float eps, int silu) {
+    pdl_wait();
+    const int g = blockIdx.x, b = blockIdx.y;
+    const int cg = C / G;
+    const int q = cg >> 2;
+    const int total = L * q;
+    const float* xb = x + (int64_t)b * L * ldx + (int64_t)g * cg;
+    float* yb = y + (int64_t)b * L * ldy + (int64_t)g * cg;
+
+    double s = 0.0, ss = 0.0;
+    for (int i = threadIdx.x; i < total; i += GN_THREADS) {
+        const int row = i / q, qq = i - row * q;
+        const float4 v = ld_f4(xb + (int64_t)row * ldx + qq * 4);
+        s += (double)v.x + (double)v.y + (double)v.z + (double)v.w;
+        ss += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+    }
+    float mean, rstd;
+    gn_block_stats(s, ss, (double)L * cg, eps, mean, rstd);
     const float* gm = gamma + g * cg;
     const float* bt = beta + g * cg;
     for (int i = threadIdx.x; i < total; i += GN_THREADS) {
@@ -77,8 +135,15 @@ int launch_groupnorm(const DeviceInfo&, const mugd_groupnorm& g, cudaStream_t st
                  "groupnorm: operands must be 16-byte aligned with ld %% 4 == 0");
     MUGD_REQUIRE(g.ldx >= g.C && g.ldy >= g.C, "groupnorm: leading dimension smaller than C");
     dim3 grid(g.G, g.B);
-    MUGD_CHECK_CUDA(launch_k(groupnorm_silu_kernel, grid, dim3(GN_THREADS), 0, st, g.x, g.ldx, g.y, g.ldy, g.gamma, g.beta, g.L, g.C, g.G,
-                             g.eps, g.silu));
+    const int per_thread = (g.L * (g.C / g.G / 4) + GN_THREADS - 1) / GN_THREADS;     // float4 per thread
+#define GN_GO(K) MUGD_CHECK_CUDA(launch_k(K, grid, dim3(GN_THREADS), 0, st, g.x, g.ldx, g.y, g.ldy, g.gamma, g.beta, g.L, g.C, g.G, g.eps, g.silu))
+    if (per_thread <= 2) GN_GO(groupnorm_silu_reg_kernel<2>);
+    else if (per_thread <= 4) GN_GO(groupnorm_silu_reg_kernel<4>);
+    else if (per_thread <= 8) GN_GO(groupnorm_silu_reg_kernel<8>);
+    else if (per_thread <= 16) GN_GO(groupnorm_silu_reg_kernel<16>);
+    else if (per_thread <= GN_MAXV) GN_GO(groupnorm_silu_reg_kernel<GN_MAXV>);
+    else GN_GO(groupnorm_silu_kernel);
+#undef GN_GO
     if (launches) *launches += 1;
     return MUGD_OK;
 }

@@ -65,3 +65,51 @@ def gather_batch(local: torch.Tensor, sizes: Sequence[int], dst: int = 0) -> Opt
         return torch.cat([bufs[r][:sizes[r]] for r in range(world)], dim=0)
     dist.gather(padded, None, dst=dst)
     return None
+
+
+def scatter_batch(tensors: Optional[Sequence[torch.Tensor]], shapes: Sequence[Sequence[int]], device: torch.device, src: int = 0) -> List[torch.Tensor]:
+    """Rank ``src`` holds whole-batch tensors (``shapes[i]`` = their shapes, known on every rank); every rank receives its contiguous
+    shard (shard_range).  Shards may differ by one sample, collectives want equal shapes: pad to the largest shard, scatter, trim."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    use_cuda = dist.get_backend() == "nccl"
+    dev = device if use_cuda else torch.device("cpu")
+    out = []
+    for i, shape in enumerate(shapes):
+        total = int(shape[0])
+        spans = [shard_range(total, r, world) for r in range(world)]
+        mx = max(b - a for a, b in spans)
+        recv = torch.empty((mx,) + tuple(shape[1:]), dtype=torch.float32, device=dev)
+        if rank == src:
+            full = tensors[i].to(dev, torch.float32)
+            chunks = []
+            for a, b in spans:
+                c = full[a:b]
+                if b - a < mx:
+                    c = torch.cat([c, torch.zeros((mx - (b - a),) + tuple(shape[1:]), dtype=torch.float32, device=dev)])
+                chunks.append(c.contiguous())
+            dist.scatter(recv, chunks, src=src)
+        else:
+            dist.scatter(recv, None, src=src)
+        a, b = spans[rank]
+        out.append(recv[:b - a].to(device))
+    return out
+
+
+def sample_sharded(sample_fn, request: Optional[Dict[str, object]], shapes: Dict[str, Sequence[int]], device: torch.device, src: int = 0):
+    """One sampling request over all ranks (BASELINE config 4: 256 charts on 8 GPUs): rank ``src`` holds the request
+    (x_T [B,16,L], c / uc [B,128,T], w = the four audio feature maps), every rank receives its contiguous slice of the batch, runs
+    ``sample_fn(x_T, c, uc, w) -> result [b, ...]`` on it -- the samples are independent through the whole DDIM loop and the decode, so
+    there is no collective per step -- and the results are gathered on ``src`` in batch order (None elsewhere).
+    ``shapes``: the whole-batch shapes of ``x_T``, ``c``, ``uc`` and ``w0..w3`` (known to every rank, e.g. from the request header)."""
+    keys = ["x_T", "c", "uc", "w0", "w1", "w2", "w3"]
+    rank, world = dist.get_rank(), dist.get_world_size()
+    tensors = None
+    if rank == src:
+        tensors = [request["x_T"], request["c"], request["uc"]] + list(request["w"])[-4:]
+    parts = scatter_batch(tensors, [shapes[k] for k in keys], device, src)
+    local = sample_fn(parts[0], parts[1], parts[2], parts[3:])
+    total = int(shapes["x_T"][0])
+    sizes = [shard_range(total, r, world)[1] - shard_range(total, r, world)[0] for r in range(world)]
+    if dist.get_backend() != "nccl":
+        local = local.cpu()
+    return gather_batch(local, sizes, dst=src)

@@ -70,3 +70,44 @@ def test_shard_range_partitions_exactly():
             assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
             sizes = [b - a for a, b in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def _worker_sharded(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        B, L = 5, 32
+        shapes = dict(x_T=(B, 16, L), c=(B, 128, 21), uc=(B, 128, 21), w0=(B, 256, L), w1=(B, 512, L // 2), w2=(B, 512, L // 4), w3=(B, 512, L // 8))
+        req = None
+        if rank == 0:
+            gen = torch.Generator().manual_seed(3)
+            req = dict(x_T=torch.randn(shapes["x_T"], generator=gen), c=torch.randn(shapes["c"], generator=gen), uc=torch.randn(shapes["uc"], generator=gen),
+                       w=[torch.randn(shapes[f"w{i}"], generator=gen) for i in range(4)])
+
+        def fake_sampler(x, c, uc, w):          # any per-sample function of all inputs: proves every shard got the right rows
+            return x.sum((1, 2), keepdim=True) + c.mean((1, 2), keepdim=True) - uc.amax((1, 2), keepdim=True) + sum(t.sum((1, 2), keepdim=True) for t in w)
+
+        got = mdist.sample_sharded(fake_sampler, req, shapes, torch.device("cpu"))
+        ok = True
+        if rank == 0:
+            ok = torch.allclose(got, fake_sampler(req["x_T"], req["c"], req["uc"], req["w"]), rtol=1e-6, atol=1e-5) and got.shape[0] == B
+        else:
+            ok = got is None
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sample_sharded_scatter_run_gather_world2():
+    """the public multi-rank request call: rank 0 holds the request, shards are scattered (uneven: 3 + 2), results come back in batch order"""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_sharded, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]

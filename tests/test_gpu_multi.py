@@ -22,7 +22,7 @@ def _worker(rank, world, port, L, B, S, out_path):
     import torch.distributed as dist
     from mug_diffusion_b200 import synth
     from mug_diffusion_b200.config import ModelConfig
-    from mug_diffusion_b200.dist import broadcast_blob, gather_batch, shard_batch, shard_range
+    from mug_diffusion_b200.dist import broadcast_blob, sample_sharded
     from mug_diffusion_b200.sampler import DDIMSampler, MugDiffusionB200
 
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
@@ -33,13 +33,20 @@ def _worker(rank, world, port, L, B, S, out_path):
     sd = synth.synthetic_state_dict(L) if rank == 0 else None
     blob = broadcast_blob(sd, cfg, dev)
     m = MugDiffusionB200(None, cfg, z_length=L, device=dev, blob=blob)
-    inp = synth.synthetic_inputs(B, L, seed=3)                 # the request lives on every rank's host (tiny); each takes its shard
-    c, uc, xT, *w = shard_batch([inp["c"], inp["uc"], inp["x_T"]] + list(inp["w"]), rank, world)
-    z, _ = DDIMSampler(m).sample(S=S, c=c.to(dev), w=[t.to(dev) for t in w], batch_size=c.shape[0], verbose=False, x_T=xT.to(dev), eta=0.0,
-                                 shape=(16, L), unconditional_guidance_scale=5.0, unconditional_conditioning=uc.to(dev))
-    logits = m.model.decode(z)
-    sizes = [shard_range(B, r, world)[1] - shard_range(B, r, world)[0] for r in range(world)]
-    full = gather_batch(logits, sizes, dst=0)
+    # the request lives on rank 0 only; the other ranks know its shapes
+    shapes = dict(x_T=(B, 16, L), c=(B, 128, 21), uc=(B, 128, 21), w0=(B, 256, L), w1=(B, 512, L // 2), w2=(B, 512, L // 4), w3=(B, 512, L // 8))
+    req = None
+    if rank == 0:
+        inp = synth.synthetic_inputs(B, L, seed=3)
+        req = dict(x_T=inp["x_T"], c=inp["c"], uc=inp["uc"], w=list(inp["w"])[-4:])
+    sampler = DDIMSampler(m)
+
+    def run(xT, c, uc, w):
+        z, _ = sampler.sample(S=S, c=c, w=w, batch_size=c.shape[0], verbose=False, x_T=xT, eta=0.0, shape=(16, L),
+                              unconditional_guidance_scale=5.0, unconditional_conditioning=uc)
+        return m.model.decode(z)
+
+    full = sample_sharded(run, req, shapes, dev)
     if rank == 0:
         torch.save(full.cpu(), out_path)
     dist.destroy_process_group()

@@ -1,5 +1,6 @@
 """Per-k-step timeline of CTA (0,0,0) of the tensor-core GEMM (globaltimer stamps written by the kernel's debug hooks).
-usage (GPU box): python tools/gemm_timeline.py"""
+usage: python tools/build_variant.py timeline -DMUGD_TC_TIMELINE   (here), then on the GPU box
+       MUGD_LIB=mug_diffusion_b200/libmugd_timeline.so python tools/gemm_timeline.py"""
 import ctypes as C
 import math
 import os
@@ -52,7 +53,8 @@ def main():
         R.lib.mugd_debug_set_tc_tile_n(0)
         t = buf.cpu().tolist()
         t0 = t[0]
-        print(f"\n== {label}: M={M} N={Cout} K={taps*Cin}  accum ready {t[2]-t0} ns, staged {t[3]-t0}, phase-2 start {t[5]-t0}, done {t[4]-t0}")
+        print(f"\n== {label}: M={M} N={Cout} K={taps*Cin}  [ns after kernel entry] setup done {t[1]-t0}, accum ready {t[2]-t0}, staged {t[3]-t0}, "
+              f"phase-2 start {t[5]-t0}, done {t[4]-t0}")
         print("   k | tma issued  full seen  conv done  mma start  mma commit | empty seen (producer)")
         nk = min(24, taps * Cin // 32)
         for i in range(nk):
