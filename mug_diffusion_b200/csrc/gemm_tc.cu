@@ -21,7 +21,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) p.dbg[0] = gtimer();
 #endif
     // ---- one-time setup: barriers, tensor memory; nothing here touches memory written by the previous kernel ----
-    if (threadIdx.x == 0) B.init(false);
+    if (threadIdx.x < 32) B.init_parallel((int)threadIdx.x);
     if (threadIdx.x >= 32 && threadIdx.x < 38) {
         // warm the TMA descriptor cache while the barriers / tensor memory are set up
         const CUtensorMap* m = threadIdx.x == 32 ? &tmA : threadIdx.x == 33 ? &tmA1 : threadIdx.x == 34 ? &tmA2
@@ -235,6 +235,8 @@ int tc_plan(const DeviceInfo& dev, const mugd_gemm& g, TcPlanned* out) {
     p.single_pass = dev.tc_single_pass ? 1 : 0;
     p.BN = t.BN;
     p.ln_invK = 1.0 / (double)g.K;
+    p.it_base = t.total_it / t.splits;
+    p.it_rem = t.total_it % t.splits;
     p.gx = t.gx;
     p.gy = t.gy;
 #ifdef MUGD_TC_TIMELINE

@@ -47,6 +47,7 @@ struct TcParams {
     int32_t single_pass;      // 1: plain TF32 (a_hi*w_hi only, ~2^-11 relative) -- opt-in speed mode, NOT used for parity/bench
     int32_t BN, gx, gy;       // tile width and tile grid (gx column tiles x gy row tiles x splits)
     double ln_invK;           // 1 / K (folded LayerNorm: moments -> mean / variance)
+    int32_t it_base, it_rem;  // split z owns k-steps [z*it_base + min(z, it_rem), +it_base + (z < it_rem)): no division on the device
 #ifdef MUGD_TC_TIMELINE
     long long* dbg;           // CTA (0,0,0) writes globaltimer stamps (tools/gemm_timeline.py)
 #endif
@@ -270,22 +271,17 @@ __device__ __forceinline__ float4 tc_finish4(const mugd_gemm& g, float4 acc, flo
 // MODE = TC_EPI_LN reads the (mean, rstd) of tile row r from shared memory at rowstat + 8*r (written in phase 1).
 template <int BN, int ACT, int GATE, int MODE>
 __device__ __forceinline__ void tc_store_tile(const mugd_gemm& g, uint32_t stage, int m_base, int n0, int rows_valid, const float* rowvec,
-                                              uint32_t rowstat) {
+                                              uint32_t rowstat, float4 bia, float4 cs) {
     constexpr int SP = BN + 4;
     constexpr int C4 = BN / 4;
     constexpr int NU = TC_BM * C4 / TC_THREADS;          // float4 per thread: 8 / 16 / 32 for BN = 64 / 128 / 256
     constexpr int U = NU < 16 ? NU : 16;                 // in flight together
     constexpr int SEG = C4 < 32 ? C4 : 32;
     static_assert(TC_THREADS % C4 == 0, "a thread keeps its column quad for the whole tile");
-    // this thread's column quad is the same for every row it visits: bias / column sums are loaded once
+    // this thread's column quad is the same for every row it visits: bias / column sums (bia, cs) were loaded once, before the main loop
     const int c4 = (int)threadIdx.x % C4;
     const int nn = n0 + c4 * 4;
     const bool col_ok = nn < g.N;
-    float4 bia = make_float4(0.f, 0.f, 0.f, 0.f), cs = bia;
-    if (col_ok && g.bias) bia = ld_f4(g.bias + nn);
-    if constexpr (MODE == TC_EPI_LN) {
-        if (col_ok) cs = ld_f4(g.ln_colsum + nn);
-    }
     const bool has_res = GATE == MUGD_GATE_NONE && g.residual != nullptr;
 #pragma unroll 1
     for (int i0 = 0; i0 < NU; i0 += U) {
@@ -375,18 +371,13 @@ struct TcBars {
     __device__ __forceinline__ uint32_t wfree(int s) const { return bars + 8u * (2 * S::SAS + 2 * S::SA + S::SW + s); }
     __device__ __forceinline__ uint32_t accum() const { return bars + 8u * (COUNT - 1); }
     __device__ __forceinline__ uint32_t tmem_slot() const { return bars + 8u * COUNT; }
-    // (re-)arm every barrier for one tile; called by ONE thread between two CTA-wide barriers
-    __device__ __forceinline__ void init(bool reinit) const {
-        if (reinit) {
-            for (int i = 0; i < COUNT; ++i) mbar_inval(bars + 8u * i);
-        }
-        for (int s = 0; s < S::SA; ++s) { mbar_init(conv(s), 4); mbar_init(empty(s), 1); }
-        for (int s = 0; s < S::SAS; ++s) mbar_init(full(s), 1);
-        if constexpr (S::DEC) {
-            for (int s = 0; s < S::SAS; ++s) mbar_init(afree(s), 4);
-            for (int s = 0; s < S::SW; ++s) { mbar_init(wfull(s), 1); mbar_init(wfree(s), 1); }
-        }
-        mbar_init(accum(), 1);
+    // arm every barrier for one tile: thread t (t < COUNT) arms barrier t; call from the first warp(s), then sync the CTA
+    __device__ __forceinline__ void init_parallel(int t) const {
+        if (t >= COUNT) return;
+        uint32_t count = 1;
+        if (t >= S::SAS && t < S::SAS + S::SA) count = 4;                                         // conv: one arrival per converter warp
+        if (S::DEC && t >= S::SAS + 2 * S::SA && t < 2 * S::SAS + 2 * S::SA) count = 4;           // afree
+        mbar_init(bars + 8u * t, count);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
 };
@@ -414,9 +405,8 @@ __device__ __forceinline__ void gemm_tc_tile(const CUtensorMap* tmA, const CUten
     int b_base, l_base, rows_valid;
     tc_tile_rows(p, by, b_base, l_base, rows_valid);
     const int m_base = b_base * p.Lrows + l_base;
-    const int it_begin = (int)(((long long)p.total_it * bz) / p.splits);
-    const int it_end = (int)(((long long)p.total_it * (bz + 1)) / p.splits);
-    const int nit = it_end - it_begin;
+    const int it_begin = bz * p.it_base + min(bz, p.it_rem);
+    const int nit = p.it_base + (bz < p.it_rem ? 1 : 0);
 #ifdef MUGD_TC_TIMELINE
     const bool dbg_cta = p.dbg && bx == 0 && by == 0 && bz == 0;
 #define TC_STAMP(cond, slot) do { if (dbg_cta && (cond)) p.dbg[slot] = gtimer(); } while (0)
@@ -424,6 +414,22 @@ __device__ __forceinline__ void gemm_tc_tile(const CUtensorMap* tmA, const CUten
 #define TC_STAMP(cond, slot) do { } while (0)
 #endif
     TC_STAMP(threadIdx.x == 0, 1);
+    // Epilogue operands that do not depend on the accumulator are requested NOW, so that their memory latency hides behind the main
+    // loop: the device step counter (selects the time-embedding row) and this thread's bias / column-sum quad (its column quad is the
+    // same for every row of the tile).  Warps 0-3 have nothing else to do with their registers; for warps 4-7 it is 9 registers.
+    int epi_step = 0;
+    float4 epi_bias = make_float4(0.f, 0.f, 0.f, 0.f), epi_cs = epi_bias;
+    if (p.splits == 1) {
+        const int nn = n0 + ((int)threadIdx.x % (BN / 4)) * 4;
+        if (g.step || (g.bias && nn < g.N)) {
+            if constexpr (PDL) pdl_wait();                       // the step counter is written by the previous kernels
+            if (g.step) epi_step = *g.step;
+            if (g.bias && nn < g.N) epi_bias = ld_f4(g.bias + nn);
+        }
+        if constexpr (TcEpiTraits<EPI>::MODE == TC_EPI_LN) {
+            if (nn < g.N) epi_cs = ld_f4(g.ln_colsum + nn);
+        }
+    }
 
     if (warp == 0) {
         // ===================================== TMA producer =====================================
@@ -596,8 +602,7 @@ __device__ __forceinline__ void gemm_tc_tile(const CUtensorMap* tmA, const CUten
     __syncthreads();
     TC_STAMP(threadIdx.x == 0, 5);
     {
-        const int step = g.step ? *g.step : 0;
-        const float* rowvec = g.rowvec ? g.rowvec + (int64_t)step * g.rowvec_step_stride : nullptr;
+        const float* rowvec = g.rowvec ? g.rowvec + (int64_t)epi_step * g.rowvec_step_stride : nullptr;
         if (p.splits > 1) {
             const int tile_lin = by * p.gx + bx;
             float* wsp = p.ws + ((int64_t)tile_lin * p.splits + bz) * (TC_BM * BN);
@@ -619,7 +624,7 @@ __device__ __forceinline__ void gemm_tc_tile(const CUtensorMap* tmA, const CUten
             }
         } else {
             using E = TcEpiTraits<EPI>;
-            tc_store_tile<BN, E::ACT, E::GATE, E::MODE>(g, base, m_base, n0, rows_valid, rowvec, base + S::TILE_BYTES - 1024u);
+            tc_store_tile<BN, E::ACT, E::GATE, E::MODE>(g, base, m_base, n0, rows_valid, rowvec, base + S::TILE_BYTES - 1024u, epi_bias, epi_cs);
         }
     }
     TC_STAMP(threadIdx.x == 0, 4);
