@@ -60,9 +60,10 @@ gemm_tc_reduce_kernel(const __grid_constant__ TcParams p) {
 #ifdef MUGD_TC_TIMELINE
 static long long* g_tc_dbg = nullptr;
 #endif
-// planner constants from the B200 micro-benchmark (tools/bench_gemm.py): us per k-step of a 128- / 256-wide tile, us per
-// split-K round trip (workspace + reduce launch); mugd_debug_set_tc_cost for sweeps
-static float g_tc_cost[3] = {0.55f, 0.9f, 4.0f};
+// planner constants: us per k-step of a 128- / 256-wide tile (tools/bench_gemm.py), us per split-K round trip (workspace + reduce
+// launch).  The split cost was 4.0 in round 1; with the slimmer kernels of round 2 the sweep (tools/experiments/sweep_cost.sh:
+// 299 / 303 / 312 / 312 steps/s at 5.0 / 4.0 / 3.0 / 2.0) favours splitting a little more.  mugd_debug_set_tc_cost for sweeps
+static float g_tc_cost[3] = {0.55f, 0.9f, 3.0f};
 static int g_tc_force_bn = 0;        // experiments: 0 = cost model, 64 / 128 / 256 = force the tile width where legal
 
 // =====================================================================================================

@@ -67,17 +67,30 @@ groupnorm_silu_reg_kernel(const float* __restrict__ x, int64_t ldx, float* __res
         s += (double)v[u].x + (double)v[u].y + (double)v[u].z + (double)v[u].w;
         ss += (double)v[u].x * v[u].x + (double)v[u].y * v[u].y + (double)v[u].z * v[u].z + (double)v[u].w * v[u].w;
     }
-    float mean, rstd;
-    gn_block_stats(s, ss, (double)L * cg, eps, mean, rstd);
+    // gamma / beta do not depend on the moments: request them before the block reduction (NV <= 8: registers are cheap there)
     const float* gm = gamma + g * cg;
     const float* bt = beta + g * cg;
+    constexpr bool PRE = NV <= 8;
+    float4 gav[PRE ? NV : 1], bev[PRE ? NV : 1];
+    if constexpr (PRE) {
+#pragma unroll
+        for (int u = 0; u < NV; ++u) {
+            const int i = (int)threadIdx.x + u * GN_THREADS;
+            const int qq = i < total ? i % q : 0;
+            gav[u] = ld_f4(gm + qq * 4);
+            bev[u] = ld_f4(bt + qq * 4);
+        }
+    }
+    float mean, rstd;
+    gn_block_stats(s, ss, (double)L * cg, eps, mean, rstd);
 #pragma unroll
     for (int u = 0; u < NV; ++u) {
         const int i = (int)threadIdx.x + u * GN_THREADS;
         if (i < total) {
             const int row = i / q, qq = i - row * q;
-            const float4 ga = ld_f4(gm + qq * 4);
-            const float4 be = ld_f4(bt + qq * 4);
+            float4 ga, be;
+            if constexpr (PRE) { ga = gav[u]; be = bev[u]; }
+            else { ga = ld_f4(gm + qq * 4); be = ld_f4(bt + qq * 4); }
             float4 o;
             o.x = (v[u].x - mean) * rstd * ga.x + be.x;
             o.y = (v[u].y - mean) * rstd * ga.y + be.y;

@@ -48,11 +48,14 @@ def main():
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--gemm", default="auto")
     ap.add_argument("--fuse", type=int, default=1, help="0: stand-alone LayerNorm kernels")
+    ap.add_argument("--attn", type=int, default=1, help="0: exact-fp32 FFMA attention kernel instead of the tcgen05 one")
+    ap.add_argument("--only", default="", help="only ops whose family name contains this")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     cfg = ModelConfig()
     model = MugDiffusionB200(synth.synthetic_state_dict(a.L), cfg, z_length=a.L, device=dev, gemm_impl=a.gemm, fold_ln=bool(a.fuse))
     eng = model.engine
+    eng.lib.mugd_set_attention_impl(eng.handle, a.attn)
     Beff = a.B if a.nocfg else 2 * a.B
     sess = eng.session(Beff, a.L, per_sample_t=False)
     arr, n = sess.plan._arr, sess.plan.n_ops
@@ -61,6 +64,8 @@ def main():
         groups.setdefault(signature(arr[i]), []).append(i)
     rows = []
     for sig, idx in groups.items():
+        if a.only and a.only not in sig[0]:
+            continue
         sub = OpList()
         for _ in range(a.reps):
             sub.ops.append(arr[idx[0]])
