@@ -170,55 +170,24 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
 
 template <int BN>
 struct TcSmem {
-    static constexpr uint32_t B_BYTES = BN * TC_BK * 4;                    // one swizzle atom (32 fp32 of K) of W_hi or W_lo
+    static constexpr uint32_t B_BYTES = BN * TC_BK * 4;
+    static constexpr uint32_t STAGE_BYTES = TC_A_BYTES + 2 * B_BYTES;     // raw A tile + W_hi + W_lo (a_hi / a_lo live in TMEM)
+    static constexpr int STAGES = (BN == 256) ? 2 : (BN == 128 ? 4 : 6);
     // Decoupled rings (256-wide tiles): only two 80 KB coupled stages would fit, and tied to the A tile the weight tile sat idle
     // while the activations were fetched and split.  Decoupled, the A side is a 2-deep smem ring feeding a 4-deep ring of TMEM
     // operand slots and runs ahead, and the freed shared memory holds a THIRD weight stage; a weight stage is occupied only from
     // its TMA to the retirement of its MMAs (k-step 1.10 -> 1.00 us on the Beff=64 convs).
     static constexpr bool DEC = BN == 256;
-    // Narrower tiles run 64-deep stages: NAT = 2 swizzle atoms (2 x 32 fp32 of K) per barrier round trip.  The 12 UMMAs of one
-    // 32-deep k-step of a 128-wide tile take 0.40 us of tensor time, but the producer's three TMA issues and the MMA warp's
-    // wait / fence / elect / commit cost ~0.5 us per round trip: with two atoms per round trip that overhead is paid half as often.
-    // A stage holds one atom when its second k-step would cross a tap / source boundary or the end of the CTA's K range.
-    static constexpr int NAT = DEC ? 1 : 2;
-    static constexpr uint32_t STAGE_BYTES = NAT * (TC_A_BYTES + 2 * B_BYTES);     // raw A atoms | W_hi atoms | W_lo atoms
-    static constexpr int STAGES = (BN == 256) ? 2 : (BN == 128 ? 2 : 3);
     static constexpr int SAS = DEC ? 2 : STAGES;           // raw activation tiles in shared memory
     static constexpr int SA = DEC ? 4 : STAGES;            // split activation tiles in tensor memory
     static constexpr int SW = DEC ? 3 : STAGES;            // weight stages (hi + lo)
     static constexpr uint32_t TILE_BYTES = DEC ? SAS * TC_A_BYTES + SW * 2 * B_BYTES : STAGES * STAGE_BYTES;
     static constexpr uint32_t BAR_BYTES = 256;
     static constexpr uint32_t TOTAL = TILE_BYTES + 1024 /*align slack*/ + BAR_BYTES;
-    static constexpr int SLOT_COLS = NAT * 64;             // per atom 32 columns a_hi + 32 columns a_lo
-    static constexpr int TMEM_NEED = BN + SA * SLOT_COLS;  // accumulator + operand slots
+    static constexpr int TMEM_NEED = BN + SA * 64;         // accumulator + per slot 32 columns a_hi + 32 columns a_lo
     static constexpr int TMEM_COLS = TMEM_NEED <= 64 ? 64 : (TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512));
     static_assert(TMEM_NEED <= 512, "tensor memory budget");
     static_assert(128u * (BN + 4) * 4u + 1024u <= TILE_BYTES, "the staged accumulator tile + row statistics must fit the pipeline buffers");
-};
-
-// The K range [it_begin, it_end) of a CTA (in 32-deep k-steps) cut into pipeline stages of one or two k-steps.  Producer, converter
-// and MMA warp each walk it and must agree: a stage takes two k-steps when the tile runs 64-deep stages and both lie in the same
-// tap (or both in the second source) and inside the range.
-struct TcWalk {
-    int it, kb, t;        // k-step, position inside its tap (or inside the second source), tap
-    int it_end, it_main, kblocks, kb2;
-    __device__ __forceinline__ TcWalk(const TcParams& p, int it_begin, int nit) {
-        it = it_begin; it_end = it_begin + nit; it_main = p.it_main; kblocks = p.kblocks; kb2 = p.total_it - p.it_main;
-        if (it < it_main) { t = it / kblocks; kb = it - t * kblocks; }
-        else { t = 0; kb = it - it_main; }
-    }
-    __device__ __forceinline__ bool done() const { return it >= it_end; }
-    __device__ __forceinline__ bool second() const { return it >= it_main; }
-    template <int NAT>
-    __device__ __forceinline__ int nat() const {
-        if (NAT == 1) return 1;
-        return (it + 1 < it_end && kb + 1 < (it < it_main ? kblocks : kb2)) ? 2 : 1;
-    }
-    __device__ __forceinline__ void advance(int n) {
-        it += n; kb += n;
-        if (it == it_main) { kb = 0; t = 0; }
-        else if (it < it_main && kb >= kblocks) { kb -= kblocks; ++t; }
-    }
 };
 
 // ---- row moments of the OUTPUT for the LayerNorm that follows, accumulated while the tile is written (mugd_gemm.row_moments) ----
@@ -426,13 +395,9 @@ __device__ __forceinline__ void gemm_tc_tile(const CUtensorMap* tmA, const CUten
     constexpr bool DEC = S::DEC;
     constexpr int SAS = S::SAS, SA = S::SA, SW = S::SW;
     const TcBars<BN> B(base);
-    constexpr int NAT = S::NAT;
-    // stage s: raw A atoms | W_hi atoms | W_lo atoms (coupled); decoupled rings keep A and W apart and always hold one atom
-    auto a_raw = [&](int s, int a) { return DEC ? base + s * TC_A_BYTES : base + s * S::STAGE_BYTES + a * TC_A_BYTES; };
-    auto b_hi = [&](int s, int a) {
-        return DEC ? base + SAS * TC_A_BYTES + s * 2 * S::B_BYTES : base + s * S::STAGE_BYTES + NAT * TC_A_BYTES + a * S::B_BYTES;
-    };
-    auto b_lo = [&](int s, int a) { return b_hi(s, a) + (DEC ? 1 : NAT) * S::B_BYTES; };
+    auto a_raw = [&](int s) { return DEC ? base + s * TC_A_BYTES : base + s * S::STAGE_BYTES; };
+    auto b_hi = [&](int s) { return DEC ? base + SAS * TC_A_BYTES + s * 2 * S::B_BYTES : base + s * S::STAGE_BYTES + TC_A_BYTES; };
+    auto b_lo = [&](int s) { return b_hi(s) + S::B_BYTES; };
 
     const mugd_gemm& g = p.g;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -471,40 +436,38 @@ __device__ __forceinline__ void gemm_tc_tile(const CUtensorMap* tmA, const CUten
         // the whole warp walks the loop converged; one elected lane issues the copies
         const uint32_t a_tx = (uint32_t)(p.box_l * p.box_b) * TC_BK * 4;
         const uint32_t w_tx = (p.single_pass ? 1u : 2u) * S::B_BYTES;
-        TcWalk w(p, it_begin, nit);
-        for (int i = 0; !w.done(); ++i) {
-            const int nat = w.template nat<NAT>();
+        for (int i = 0; i < nit; ++i) {
             const int s = i % SAS;
             const uint32_t ph = (uint32_t)(i / SAS) & 1u;
             if constexpr (DEC) mbar_wait(B.afree(s), ph ^ 1u);
             else mbar_wait(B.empty(s), ph ^ 1u);
             if (elect_one()) {
                 TC_STAMP(i < 24, 8 + i * 6 + 5);
-                mbar_expect_tx(B.full(s), (uint32_t)nat * (DEC ? a_tx : a_tx + w_tx));
+                const int it = it_begin + i;
+                mbar_expect_tx(B.full(s), DEC ? a_tx : a_tx + w_tx);
                 if constexpr (!DEC) {
                     // weights first: they do not depend on the previous kernel / op.  W columns are in k-step order.
-                    for (int a = 0; a < nat; ++a) {
-                        tma_load_2d(b_hi(s, a), tmWhi, B.full(s), (w.it + a) * TC_BK, n0);
-                        if (!p.single_pass) tma_load_2d(b_lo(s, a), tmWlo, B.full(s), (w.it + a) * TC_BK, n0);
-                    }
+                    tma_load_2d(b_hi(s), tmWhi, B.full(s), it * TC_BK, n0);
+                    if (!p.single_pass) tma_load_2d(b_lo(s), tmWlo, B.full(s), it * TC_BK, n0);
                 }
                 if (PDL && i == 0) pdl_wait();      // activations written by the previous kernel are touched from here on
-                if (!w.second()) {
+                if (it < p.it_main) {
+                    const int t = it / p.kblocks;
+                    const int kb = it - t * p.kblocks;
                     // row addressing per tap: SAME = l+t-1, TAPS = l+(t+shift)*dilation (zero fill outside the sample by TMA
                     // bounds); DOWN (stride 2, right pad) uses one strided tensor map per tap (row l of map t = source row 2l+t)
                     const CUtensorMap* ma = tmA;
                     int lshift = 0;
-                    if (g.conv_mode == MUGD_CONV_SAME) lshift = w.t - 1;
-                    else if (g.conv_mode == MUGD_CONV_TAPS) lshift = (w.t + g.tap_shift) * (g.tap_dilation > 1 ? g.tap_dilation : 1);
-                    else if (g.conv_mode == MUGD_CONV_DOWN) ma = (w.t == 0) ? tmA : (w.t == 1 ? tmA1 : tmA2);
-                    for (int a = 0; a < nat; ++a) tma_load_3d(a_raw(s, a), ma, B.full(s), (w.kb + a) * TC_BK, l_base + lshift, b_base);
+                    if (g.conv_mode == MUGD_CONV_SAME) lshift = t - 1;
+                    else if (g.conv_mode == MUGD_CONV_TAPS) lshift = (t + g.tap_shift) * (g.tap_dilation > 1 ? g.tap_dilation : 1);
+                    else if (g.conv_mode == MUGD_CONV_DOWN) ma = (t == 0) ? tmA : (t == 1 ? tmA1 : tmA2);
+                    tma_load_3d(a_raw(s), ma, B.full(s), kb * TC_BK, l_base + lshift, b_base);
                 } else {
-                    for (int a = 0; a < nat; ++a) tma_load_3d(a_raw(s, a), tmB, B.full(s), (w.kb + a) * TC_BK, l_base, b_base);   // second source: 1x1 term
+                    tma_load_3d(a_raw(s), tmB, B.full(s), (it - p.it_main) * TC_BK, l_base, b_base);   // second source: 1x1 term
                 }
                 TC_STAMP(i < 24, 8 + i * 6 + 0);
             }
             __syncwarp();
-            w.advance(nat);
         }
     } else if (DEC && warp == 3) {
         // ===================================== weight producer (decoupled rings) ================
@@ -515,8 +478,8 @@ __device__ __forceinline__ void gemm_tc_tile(const CUtensorMap* tmA, const CUten
             if (elect_one()) {
                 const int it = it_begin + i;
                 mbar_expect_tx(B.wfull(s), (p.single_pass ? 1u : 2u) * S::B_BYTES);
-                tma_load_2d(b_hi(s, 0), tmWhi, B.wfull(s), it * TC_BK, n0);
-                if (!p.single_pass) tma_load_2d(b_lo(s, 0), tmWlo, B.wfull(s), it * TC_BK, n0);
+                tma_load_2d(b_hi(s), tmWhi, B.wfull(s), it * TC_BK, n0);
+                if (!p.single_pass) tma_load_2d(b_lo(s), tmWlo, B.wfull(s), it * TC_BK, n0);
             }
             __syncwarp();
         }
@@ -525,10 +488,7 @@ __device__ __forceinline__ void gemm_tc_tile(const CUtensorMap* tmA, const CUten
         // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A=TF32 [7,10)=2, B=TF32 [10,13)=2,
         // A/B K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-        TcWalk w(p, it_begin, nit);
-        int nst = 0;
-        for (int i = 0; !w.done(); ++i) {
-            const int nat = w.template nat<NAT>();
+        for (int i = 0; i < nit; ++i) {
             const int s = i % SA;
             const uint32_t ph = (uint32_t)(i / SA) & 1u;
             const int sw = DEC ? i % SW : s;
@@ -537,20 +497,17 @@ __device__ __forceinline__ void gemm_tc_tile(const CUtensorMap* tmA, const CUten
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (elect_one()) {
                 TC_STAMP(i < 24, 8 + i * 6 + 3);
-                for (int a = 0; a < nat; ++a) {
-                    const uint64_t dbh = umma_desc(b_hi(sw, a)), dbl = umma_desc(b_lo(sw, a));
-                    const uint32_t ta_hi = tmem_base + (uint32_t)(BN + s * S::SLOT_COLS + a * 64), ta_lo = ta_hi + 32u;
+                const uint64_t dbh = umma_desc(b_hi(sw)), dbl = umma_desc(b_lo(sw));
+                const uint32_t ta_hi = tmem_base + (uint32_t)(BN + s * 64), ta_lo = ta_hi + 32u;
 #pragma unroll
-                    for (int kk = 0; kk < TC_BK / 8; ++kk) {
-                        const uint64_t ko = (uint64_t)(kk * 2);     // 8 fp32 = 32 bytes = 2 x 16-byte units
-                        const uint32_t first = (i > 0 || a > 0 || kk > 0) ? 1u : 0u;
-                        if (p.single_pass) {
-                            umma_tf32_ts(tmem_base, ta_hi + kk * 8, dbh + ko, idesc, first);
-                        } else {
-                            umma_tf32_ts(tmem_base, ta_lo + kk * 8, dbh + ko, idesc, first);
-                            umma_tf32_ts(tmem_base, ta_hi + kk * 8, dbl + ko, idesc, 1u);
-                            umma_tf32_ts(tmem_base, ta_hi + kk * 8, dbh + ko, idesc, 1u);
-                        }
+                for (int kk = 0; kk < TC_BK / 8; ++kk) {
+                    const uint64_t ko = (uint64_t)(kk * 2);     // 8 fp32 = 32 bytes = 2 x 16-byte units
+                    if (p.single_pass) {
+                        umma_tf32_ts(tmem_base, ta_hi + kk * 8, dbh + ko, idesc, (i > 0 || kk > 0) ? 1u : 0u);
+                    } else {
+                        umma_tf32_ts(tmem_base, ta_lo + kk * 8, dbh + ko, idesc, (i > 0 || kk > 0) ? 1u : 0u);
+                        umma_tf32_ts(tmem_base, ta_hi + kk * 8, dbl + ko, idesc, 1u);
+                        umma_tf32_ts(tmem_base, ta_hi + kk * 8, dbh + ko, idesc, 1u);
                     }
                 }
                 umma_commit(B.empty(s));                      // stage (decoupled: TMEM operand slot) reusable once these MMAs retire
@@ -558,16 +515,14 @@ __device__ __forceinline__ void gemm_tc_tile(const CUtensorMap* tmA, const CUten
                 TC_STAMP(i < 24, 8 + i * 6 + 4);
             }
             __syncwarp();
-            w.advance(nat);
-            nst = i + 1;
         }
         if (elect_one()) umma_commit(B.accum());
         __syncwarp();
         // drain: observe the release of the last use of every stage, so that no commit is still on its way to a barrier when the
-        // caller re-arms them for the next tile or the CTA exits
-        for (int i = (nst > SA ? nst - SA : 0); i < nst; ++i) mbar_wait(B.empty(i % SA), (uint32_t)(i / SA) & 1u);
+        // caller re-arms them for the next tile (persistent kernel) or the CTA exits
+        for (int i = (nit > SA ? nit - SA : 0); i < nit; ++i) mbar_wait(B.empty(i % SA), (uint32_t)(i / SA) & 1u);
         if constexpr (DEC) {
-            for (int i = (nst > SW ? nst - SW : 0); i < nst; ++i) mbar_wait(B.wfree(i % SW), (uint32_t)(i / SW) & 1u);
+            for (int i = (nit > SW ? nit - SW : 0); i < nit; ++i) mbar_wait(B.wfree(i % SW), (uint32_t)(i / SW) & 1u);
         }
     } else if (warp >= 4) {
         // ===================================== converter ========================================
@@ -581,9 +536,7 @@ __device__ __forceinline__ void gemm_tc_tile(const CUtensorMap* tmA, const CUten
                 ln_s = mo.x; ln_ss = mo.y;
             }
         }
-        TcWalk w(p, it_begin, nit);
-        for (int i = 0; !w.done(); ++i) {
-            const int nat = w.template nat<NAT>();
+        for (int i = 0; i < nit; ++i) {
             const int s = i % SA;                                     // TMEM operand slot
             const int sm = i % SAS;                                   // raw tile in shared memory
             mbar_wait(B.full(sm), (uint32_t)(i / SAS) & 1u);
@@ -592,25 +545,23 @@ __device__ __forceinline__ void gemm_tc_tile(const CUtensorMap* tmA, const CUten
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             }
             TC_STAMP(threadIdx.x == 128 && i < 24, 8 + i * 6 + 1);
-            // thread = tile row (= TMEM lane): read the row's 128 bytes out of each 128B-swizzled atom (16-byte chunk c
+            // thread = tile row (= TMEM lane): read the row's 128 bytes out of the 128B-swizzled tile (16-byte chunk c
             // of row r sits at chunk c ^ (r & 7)), split, and store hi / lo to this slot's TMEM columns
             const int r = (warp & 3) * 32 + lane;
-            for (int a = 0; a < nat; ++a) {
-                const uint32_t rowaddr = a_raw(sm, a) + (uint32_t)r * 128u;
-                float hi[32], lo[32];
+            const uint32_t rowaddr = a_raw(sm) + (uint32_t)r * 128u;
+            float hi[32], lo[32];
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    float4 x;
-                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
-                                 : "r"(rowaddr + (uint32_t)((c ^ (r & 7)) * 16)));
-                    hi[c * 4] = to_tf32(x.x); hi[c * 4 + 1] = to_tf32(x.y); hi[c * 4 + 2] = to_tf32(x.z); hi[c * 4 + 3] = to_tf32(x.w);
-                    lo[c * 4] = to_tf32(x.x - hi[c * 4]); lo[c * 4 + 1] = to_tf32(x.y - hi[c * 4 + 1]);
-                    lo[c * 4 + 2] = to_tf32(x.z - hi[c * 4 + 2]); lo[c * 4 + 3] = to_tf32(x.w - hi[c * 4 + 3]);
-                }
-                const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(BN + s * S::SLOT_COLS + a * 64);
-                tmem_st32(ta, hi);
-                tmem_st32(ta + 32u, lo);
+            for (int c = 0; c < 8; ++c) {
+                float4 x;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
+                             : "r"(rowaddr + (uint32_t)((c ^ (r & 7)) * 16)));
+                hi[c * 4] = to_tf32(x.x); hi[c * 4 + 1] = to_tf32(x.y); hi[c * 4 + 2] = to_tf32(x.z); hi[c * 4 + 3] = to_tf32(x.w);
+                lo[c * 4] = to_tf32(x.x - hi[c * 4]); lo[c * 4 + 1] = to_tf32(x.y - hi[c * 4 + 1]);
+                lo[c * 4 + 2] = to_tf32(x.z - hi[c * 4 + 2]); lo[c * 4 + 3] = to_tf32(x.w - hi[c * 4 + 3]);
             }
+            const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(BN + s * 64);
+            tmem_st32(ta, hi);
+            tmem_st32(ta + 32u, lo);
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
@@ -619,7 +570,6 @@ __device__ __forceinline__ void gemm_tc_tile(const CUtensorMap* tmA, const CUten
                 if constexpr (DEC) mbar_arrive(B.afree(sm));          // the raw tile has been read: its smem slot may be refilled
             }
             TC_STAMP(threadIdx.x == 128 && i < 24, 8 + i * 6 + 2);
-            w.advance(nat);
         }
         // LayerNorm folded into this GEMM: the moments of this thread's row (written by the previous kernels) -> mean / rstd
         float2 lnrow = make_float2(0.f, 1.f);
