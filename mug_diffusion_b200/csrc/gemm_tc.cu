@@ -21,25 +21,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) p.dbg[0] = gtimer();
 #endif
     // ---- one-time setup: barriers, tensor memory; nothing here touches memory written by the previous kernel ----
-    if (threadIdx.x < 32) B.init_parallel((int)threadIdx.x);
-    if (threadIdx.x >= 32 && threadIdx.x < 38) {
-        // warm the TMA descriptor cache while the barriers / tensor memory are set up
-        const CUtensorMap* m = threadIdx.x == 32 ? &tmA : threadIdx.x == 33 ? &tmA1 : threadIdx.x == 34 ? &tmA2
-                             : threadIdx.x == 35 ? &tmB : threadIdx.x == 36 ? &tmWhi : &tmWlo;
-        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+    // The producer warp arms the barriers itself and starts fetching operands at once: it only ARRIVES at the setup rendezvous
+    // (named barrier 1), the other seven warps wait there for it and for the tensor-memory allocation.  The first TMA leaves
+    // ~0.8 us earlier than behind a CTA-wide __syncthreads (tools/gemm_timeline.py: setup took 0.86 us, first TMA at 1.4 us).
+    uint32_t tmem_base = 0;
+    if (warp == 0) {
+        B.init_parallel((int)threadIdx.x);
+        __syncwarp();
+        asm volatile("bar.arrive 1, %0;" ::"n"(TC_THREADS) : "memory");
+    } else {
+        if (threadIdx.x >= 32 && threadIdx.x < 38) {
+            // warm the TMA descriptor cache while the barriers / tensor memory are set up
+            const CUtensorMap* m = threadIdx.x == 32 ? &tmA : threadIdx.x == 33 ? &tmA1 : threadIdx.x == 34 ? &tmA2
+                                 : threadIdx.x == 35 ? &tmB : threadIdx.x == 36 ? &tmWhi : &tmWlo;
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+        }
+        if (warp == 2) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(B.tmem_slot()), "r"((uint32_t)S::TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(TC_THREADS) : "memory");
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(B.tmem_slot()));
+        // the producer warp waits for the previous kernel (griddepcontrol.wait) before its first activation load; every other
+        // global access of this kernel (epilogue) is ordered behind data that went through that load
+        pdl_wait();
     }
-    if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(B.tmem_slot()), "r"((uint32_t)S::TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    uint32_t tmem_base;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(B.tmem_slot()));
-    // the producer warp waits for the previous kernel (griddepcontrol.wait) before its first activation load; every other
-    // global access of this kernel (epilogue) is ordered behind data that went through that load
-    if (warp != 0) pdl_wait();
     gemm_tc_tile<BN, true, EPI>(&tmA, &tmA1, &tmA2, &tmB, &tmWhi, &tmWlo, p, blockIdx.x, blockIdx.y, blockIdx.z, base, tmem_base);
     // ---- teardown (all tcgen05.ld completed before the phase-2 barrier inside the tile function) ----
     __syncthreads();
