@@ -246,6 +246,8 @@ int tc_plan(const DeviceInfo& dev, const mugd_gemm& g, TcPlanned* out) {
     p.ln_invK = 1.0 / (double)g.K;
     p.it_base = t.total_it / t.splits;
     p.it_rem = t.total_it % t.splits;
+    p.hot = {p.Lrows, p.Bs, p.box_l, p.box_b, p.tiles_per_sample, p.it_base, p.it_rem, p.it_main, p.kblocks, p.total_it, p.splits, p.single_pass,
+             g.conv_mode, g.tap_shift, g.tap_dilation, p.gx};
     p.gx = t.gx;
     p.gy = t.gy;
 #ifdef MUGD_TC_TIMELINE

@@ -35,6 +35,13 @@ constexpr int TC_THREADS = 256;
 constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
 
 struct TcParams {
+    // What the tile prologue and the TMA producer read before the first load leaves, packed into the first 64 bytes: kernel
+    // parameters live in constant memory, a fresh launch misses on every line it touches, and those misses are serial on the
+    // producer's critical path (tools/gemm_timeline.py: ~0.4 us between kernel entry and the first TMA were parameter fetches).
+    struct Hot {
+        int32_t Lrows, Bs, box_l, box_b, tiles_per_sample, it_base, it_rem, it_main, kblocks, total_it, splits, single_pass,
+            conv_mode, tap_shift, tap_dilation, gx;
+    } hot;
     mugd_gemm g;
     float* ws;                // split-K partial tiles [tile][split][128][BN]
     int32_t splits;
@@ -342,14 +349,15 @@ inline int tc_epi_of(const mugd_gemm& g) {
 
 // rows of output tile `by`
 __device__ __forceinline__ void tc_tile_rows(const TcParams& p, int by, int& b_base, int& l_base, int& rows_valid) {
-    if (p.Lrows >= TC_BM) {
-        b_base = by / p.tiles_per_sample;
-        l_base = (by % p.tiles_per_sample) * TC_BM;
-        rows_valid = min(TC_BM, p.Lrows - l_base);
+    const TcParams::Hot& h = p.hot;
+    if (h.Lrows >= TC_BM) {
+        b_base = by / h.tiles_per_sample;
+        l_base = (by % h.tiles_per_sample) * TC_BM;
+        rows_valid = min(TC_BM, h.Lrows - l_base);
     } else {
-        b_base = by * p.box_b;
+        b_base = by * h.box_b;
         l_base = 0;
-        rows_valid = min(p.box_b, p.Bs - b_base) * p.Lrows;
+        rows_valid = min(h.box_b, h.Bs - b_base) * h.Lrows;
     }
 }
 
@@ -404,9 +412,9 @@ __device__ __forceinline__ void gemm_tc_tile(const CUtensorMap* tmA, const CUten
     const int n0 = bx * BN;
     int b_base, l_base, rows_valid;
     tc_tile_rows(p, by, b_base, l_base, rows_valid);
-    const int m_base = b_base * p.Lrows + l_base;
-    const int it_begin = bz * p.it_base + min(bz, p.it_rem);
-    const int nit = p.it_base + (bz < p.it_rem ? 1 : 0);
+    const int m_base = b_base * p.hot.Lrows + l_base;
+    const int it_begin = bz * p.hot.it_base + min(bz, p.hot.it_rem);
+    const int nit = p.hot.it_base + (bz < p.hot.it_rem ? 1 : 0);
 #ifdef MUGD_TC_TIMELINE
     const bool dbg_cta = p.dbg && bx == 0 && by == 0 && bz == 0;
 #define TC_STAMP(cond, slot) do { if (dbg_cta && (cond)) p.dbg[slot] = gtimer(); } while (0)
@@ -419,7 +427,8 @@ __device__ __forceinline__ void gemm_tc_tile(const CUtensorMap* tmA, const CUten
     // same for every row of the tile).  Warps 0-3 have nothing else to do with their registers; for warps 4-7 it is 9 registers.
     int epi_step = 0;
     float4 epi_bias = make_float4(0.f, 0.f, 0.f, 0.f), epi_cs = epi_bias;
-    if (p.splits == 1) {
+    auto request_epilogue_operands = [&]() {
+        if (p.hot.splits != 1) return;
         const int nn = n0 + ((int)threadIdx.x % (BN / 4)) * 4;
         if (g.step || (g.bias && nn < g.N)) {
             if constexpr (PDL) pdl_wait();                       // the step counter is written by the previous kernels
@@ -429,13 +438,15 @@ __device__ __forceinline__ void gemm_tc_tile(const CUtensorMap* tmA, const CUten
         if constexpr (TcEpiTraits<EPI>::MODE == TC_EPI_LN) {
             if (nn < g.N) epi_cs = ld_f4(g.ln_colsum + nn);
         }
-    }
+    };
+    if (warp != 0) request_epilogue_operands();      // the producer warp first gets its loads out (it asks after its loop)
 
     if (warp == 0) {
         // ===================================== TMA producer =====================================
         // the whole warp walks the loop converged; one elected lane issues the copies
-        const uint32_t a_tx = (uint32_t)(p.box_l * p.box_b) * TC_BK * 4;
-        const uint32_t w_tx = (p.single_pass ? 1u : 2u) * S::B_BYTES;
+        const TcParams::Hot& h = p.hot;
+        const uint32_t a_tx = (uint32_t)(h.box_l * h.box_b) * TC_BK * 4;
+        const uint32_t w_tx = (h.single_pass ? 1u : 2u) * S::B_BYTES;
         for (int i = 0; i < nit; ++i) {
             const int s = i % SAS;
             const uint32_t ph = (uint32_t)(i / SAS) & 1u;
@@ -448,27 +459,28 @@ __device__ __forceinline__ void gemm_tc_tile(const CUtensorMap* tmA, const CUten
                 if constexpr (!DEC) {
                     // weights first: they do not depend on the previous kernel / op.  W columns are in k-step order.
                     tma_load_2d(b_hi(s), tmWhi, B.full(s), it * TC_BK, n0);
-                    if (!p.single_pass) tma_load_2d(b_lo(s), tmWlo, B.full(s), it * TC_BK, n0);
+                    if (!h.single_pass) tma_load_2d(b_lo(s), tmWlo, B.full(s), it * TC_BK, n0);
                 }
                 if (PDL && i == 0) pdl_wait();      // activations written by the previous kernel are touched from here on
-                if (it < p.it_main) {
-                    const int t = it / p.kblocks;
-                    const int kb = it - t * p.kblocks;
+                if (it < h.it_main) {
+                    const int t = it / h.kblocks;
+                    const int kb = it - t * h.kblocks;
                     // row addressing per tap: SAME = l+t-1, TAPS = l+(t+shift)*dilation (zero fill outside the sample by TMA
                     // bounds); DOWN (stride 2, right pad) uses one strided tensor map per tap (row l of map t = source row 2l+t)
                     const CUtensorMap* ma = tmA;
                     int lshift = 0;
-                    if (g.conv_mode == MUGD_CONV_SAME) lshift = t - 1;
-                    else if (g.conv_mode == MUGD_CONV_TAPS) lshift = (t + g.tap_shift) * (g.tap_dilation > 1 ? g.tap_dilation : 1);
-                    else if (g.conv_mode == MUGD_CONV_DOWN) ma = (t == 0) ? tmA : (t == 1 ? tmA1 : tmA2);
+                    if (h.conv_mode == MUGD_CONV_SAME) lshift = t - 1;
+                    else if (h.conv_mode == MUGD_CONV_TAPS) lshift = (t + h.tap_shift) * (h.tap_dilation > 1 ? h.tap_dilation : 1);
+                    else if (h.conv_mode == MUGD_CONV_DOWN) ma = (t == 0) ? tmA : (t == 1 ? tmA1 : tmA2);
                     tma_load_3d(a_raw(s), ma, B.full(s), kb * TC_BK, l_base + lshift, b_base);
                 } else {
-                    tma_load_3d(a_raw(s), tmB, B.full(s), (it - p.it_main) * TC_BK, l_base, b_base);   // second source: 1x1 term
+                    tma_load_3d(a_raw(s), tmB, B.full(s), (it - h.it_main) * TC_BK, l_base, b_base);   // second source: 1x1 term
                 }
                 TC_STAMP(i < 24, 8 + i * 6 + 0);
             }
             __syncwarp();
         }
+        request_epilogue_operands();
     } else if (DEC && warp == 3) {
         // ===================================== weight producer (decoupled rings) ================
         for (int i = 0; i < nit; ++i) {
