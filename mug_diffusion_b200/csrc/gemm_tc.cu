@@ -39,6 +39,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (warp == 2) {
             asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(B.tmem_slot()), "r"((uint32_t)S::TMEM_COLS) : "memory");
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+            // Kernel parameters live in constant memory and a fresh launch misses on every 64-byte line it touches; the epilogue reads
+            // fields from five of them one after the other (tools/gemm_timeline.py: a bias-free 128x128 tile took 3.2 us to store
+            // against 1.0 us for a split-K partial, which reads two).  This otherwise idle warp touches every line of the block now, so
+            // that the misses overlap the main loop instead of stretching the epilogue.
+            constexpr int LINES = (int)((sizeof(TcParams) + 63) / 64);
+            const int* pw = reinterpret_cast<const int*>(&p);
+#pragma unroll
+            for (int k = 0; k < LINES; ++k) {
+                const int v = pw[k * 16];
+                asm volatile("" ::"r"(v));
+            }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         asm volatile("bar.sync 1, %0;" ::"n"(TC_THREADS) : "memory");
