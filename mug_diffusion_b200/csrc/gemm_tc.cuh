@@ -25,6 +25,8 @@
 #pragma once
 #include <cuda.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace mugd {
@@ -240,7 +242,9 @@ constexpr int TC_EPI_PLAIN = 0, TC_EPI_SINK = 1 /* act == gate == NONE + row mom
 // LNF: acc is A W'^T of the un-normalised rows; (acc - mean*colsum)*rstd is the product with the LayerNorm'd rows.
 // Returns the stored float4 (GATE_NONE) for the row-moment sink.
 template <int ACT, int GATE, bool LNF>
-__device__ __forceinline__ float4 tc_finish4(const mugd_gemm& g, float4 acc, float4 bia, float4 rvv, float4 res, float4 cs, float2 ln, int m, int nn) {
+__device__ __forceinline__ float4 tc_finish4(const mugd_gemm& g, float* dst, float4 acc, float4 bia, float4 rvv, float4 res, float4 cs, float2 ln,
+                                             int m, int no) {
+    // dst = &C[m][no]  (no = output column: the accumulator column, or half of it for gated epilogues)
     float x[4];
     if constexpr (LNF) {
         x[0] = (acc.x - ln.x * cs.x) * ln.y + bia.x + rvv.x; x[1] = (acc.y - ln.x * cs.y) * ln.y + bia.y + rvv.y;
@@ -257,18 +261,17 @@ __device__ __forceinline__ float4 tc_finish4(const mugd_gemm& g, float4 acc, flo
     }
     if constexpr (GATE == MUGD_GATE_NONE) {
         const float4 o = make_float4(x[0] + res.x, x[1] + res.y, x[2] + res.z, x[3] + res.w);
-        st_f4(g.C + (int64_t)m * g.ldc + nn, o);
+        st_f4(dst, o);
         return o;
     } else {
         float o0, o1;
         if constexpr (GATE == MUGD_GATE_GEGLU) { o0 = x[0] * gelu_f(x[1]); o1 = x[2] * gelu_f(x[3]); }
         else { o0 = x[0] * sigmoid_f(x[1]); o1 = x[2] * sigmoid_f(x[3]); }
-        const int no = nn >> 1;
         if (g.residual) {
             const float2 rr = *reinterpret_cast<const float2*>(g.residual + (int64_t)m * g.ldr + no);
             o0 += rr.x; o1 += rr.y;
         }
-        *reinterpret_cast<float2*>(g.C + (int64_t)m * g.ldc + no) = make_float2(o0, o1);
+        *reinterpret_cast<float2*>(dst) = make_float2(o0, o1);
         return make_float4(o0, o1, 0.f, 0.f);
     }
 }
@@ -290,37 +293,58 @@ __device__ __forceinline__ void tc_store_tile(const mugd_gemm& g, uint32_t stage
     const int nn = n0 + c4 * 4;
     const bool col_ok = nn < g.N;
     const bool has_res = GATE == MUGD_GATE_NONE && g.residual != nullptr;
+    // Row bookkeeping is incremental (the SASS of the first version spent ~75 instructions per float4 on it: 64-bit address products,
+    // an integer division per row for the time-embedding row): a thread's rows are row0, row0 + RPP, ... ; pointers advance by
+    // RPP rows; the sample of a row (for the per-sample row vector) is found by ONE division and then by comparison.
+    constexpr int RPP = TC_THREADS / C4;                 // rows between two float4s of a thread
+    const int row0 = (int)threadIdx.x / C4;
+    const int n_rows = min(rows_valid, g.M - m_base);    // rows of this tile that exist
+    const int no = (GATE == MUGD_GATE_NONE) ? nn : (nn >> 1);
+    float* cp = g.C + (int64_t)(m_base + row0) * g.ldc + no;
+    const float* rp = has_res ? g.residual + (int64_t)(m_base + row0) * g.ldr + nn : nullptr;
+    const int64_t c_step = (int64_t)RPP * g.ldc, r_step = (int64_t)RPP * g.ldr;
+    int smp = 0, smp_end = 0;                            // sample of the current row, first row (tile-relative... absolute m) of the next sample
+    if (rowvec) { smp = (m_base + row0) / g.Lout; smp_end = (smp + 1) * g.Lout; }
+    // A tile that lies fully inside the matrix (the common case) runs the loop without any per-element predicate, so that the
+    // compiler can put all shared-memory reads of a pass in flight; edge tiles take the predicated copy.
+    auto pass = [&](auto full_tag) {
+        constexpr bool FULL = decltype(full_tag)::value;
 #pragma unroll 1
-    for (int i0 = 0; i0 < NU; i0 += U) {
-        // every global load of this pass is issued before anything is consumed: ONE memory round trip per 16 rows
-        float4 res[U], rvv[U];
-        bool ok[U];
+        for (int i0 = 0; i0 < NU; i0 += U) {
+            // every global load of this pass is issued before anything is consumed: ONE memory round trip per 16 rows
+            float4 res[U], rvv[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int row = (int)threadIdx.x / C4 + (i0 + u) * (TC_THREADS / C4);
-            const int m = m_base + row;
-            ok[u] = row < rows_valid && m < g.M && col_ok;
-            res[u] = rvv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ok[u]) {
-                if (has_res) res[u] = ld_f4(g.residual + (int64_t)m * g.ldr + nn);
-                if (rowvec) rvv[u] = ld_f4(rowvec + (int64_t)(m / g.Lout) * g.rowvec_b_stride + nn);
+            for (int u = 0; u < U; ++u) {
+                const int row = row0 + (i0 + u) * RPP;
+                res[u] = rvv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (FULL || (row < n_rows && col_ok)) {
+                    if (has_res) res[u] = ld_f4(rp + (int64_t)(i0 + u) * r_step);
+                    if (rowvec) {
+                        const int m = m_base + row;
+                        while (m >= smp_end) { ++smp; smp_end += g.Lout; }
+                        rvv[u] = ld_f4(rowvec + (int64_t)smp * g.rowvec_b_stride + nn);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int row = row0 + (i0 + u) * RPP;
+                const int m = m_base + row;
+                const bool ok = FULL || (row < n_rows && col_ok);
+                float4 acc;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(acc.x), "=f"(acc.y), "=f"(acc.z), "=f"(acc.w)
+                             : "r"(stage + (uint32_t)(row * SP + c4 * 4) * 4u));
+                float2 ln = make_float2(0.f, 1.f);
+                if constexpr (MODE == TC_EPI_LN)
+                    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(ln.x), "=f"(ln.y) : "r"(rowstat + (uint32_t)row * 8u));
+                float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ok) o = tc_finish4<ACT, GATE, MODE == TC_EPI_LN>(g, cp + (int64_t)(i0 + u) * c_step, acc, bia, rvv[u], res[u], cs, ln, m, no);
+                if constexpr (MODE == TC_EPI_SINK) tc_row_sink<SEG>(g.row_moments, ok ? m : -1, o);
             }
         }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int row = (int)threadIdx.x / C4 + (i0 + u) * (TC_THREADS / C4);
-            const int m = m_base + row;
-            float4 acc;
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(acc.x), "=f"(acc.y), "=f"(acc.z), "=f"(acc.w)
-                         : "r"(stage + (uint32_t)(row * SP + c4 * 4) * 4u));
-            float2 ln = make_float2(0.f, 1.f);
-            if constexpr (MODE == TC_EPI_LN)
-                asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(ln.x), "=f"(ln.y) : "r"(rowstat + (uint32_t)row * 8u));
-            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ok[u]) o = tc_finish4<ACT, GATE, MODE == TC_EPI_LN>(g, acc, bia, rvv[u], res[u], cs, ln, m, nn);
-            if constexpr (MODE == TC_EPI_SINK) tc_row_sink<SEG>(g.row_moments, ok[u] ? m : -1, o);
-        }
-    }
+    };
+    if (n_rows >= TC_BM && n0 + BN <= g.N) pass(std::true_type{});
+    else pass(std::false_type{});
 }
 
 // Epilogue variant of a kernel instantiation.  Every variant is its own kernel (template parameter), so a launch only carries the
@@ -704,7 +728,8 @@ __device__ __forceinline__ void tc_reduce_rows(const TcParams& p, int tile_lin, 
                 cs = ld_f4(g.ln_colsum + n);
                 ln = tc_ln_row(g.ln_stats, m, p.ln_invK, g.ln_eps);
             }
-            o = tc_finish4<ACT, GATE, MODE == TC_EPI_LN>(g, acc[j], bia, rvv, res, cs, ln, m, n);
+            const int no = (GATE == MUGD_GATE_NONE) ? n : (n >> 1);
+            o = tc_finish4<ACT, GATE, MODE == TC_EPI_LN>(g, g.C + (int64_t)m * g.ldc + no, acc[j], bia, rvv, res, cs, ln, m, no);
         }
         if constexpr (MODE == TC_EPI_SINK) tc_row_sink<SEG>(g.row_moments, ok[j] ? m : -1, o);
     }
