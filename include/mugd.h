@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MUGD_ABI_VERSION 11
+#define MUGD_ABI_VERSION 12
 
 typedef struct mugd_handle mugd_handle;   /* one device + scratch state            */
 typedef struct mugd_plan mugd_plan;       /* validated launch plan (+ CUDA graph)  */
@@ -52,7 +52,8 @@ enum mugd_op_kind {
     MUGD_OP_COPY2D = 8,        /* strided row copy                                                           */
     MUGD_OP_STEP_ADVANCE = 9,  /* *step += 1                                                                 */
     MUGD_OP_NOTES = 10,        /* decoder logits -> ordered note list (OsuManiaConvertor.array_to_objects)   */
-    MUGD_OP_EMBED = 11         /* prompt ids -> [B, H, F] embedding (BeatmapFeatureEmbedder.forward)         */
+    MUGD_OP_EMBED = 11,        /* prompt ids -> [B, H, F] embedding (BeatmapFeatureEmbedder.forward)         */
+    MUGD_OP_TF32_SPLIT = 12    /* weight preprocessing: w -> (hi in place, lo) for the 3xTF32 tensor-core GEMM */
 };
 
 /* A-operand row addressing of MUGD_OP_GEMM (rows are tokens of B samples, Lout output rows each) */
@@ -184,13 +185,18 @@ typedef struct mugd_embed {
     int32_t B, F, H, n_embed;
 } mugd_embed;
 
+/* hi = rna_tf32(w) written over w, lo = rna_tf32(w - hi): the two TF32 operands whose products reconstruct an fp32 weight.
+ * Run once per engine after the (plain fp32) weight blob has reached the device -- the blob that is packed, stored and broadcast holds
+ * every weight once; the resident copy holds hi + lo of the tensor-core weights and no plain duplicate. */
+typedef struct mugd_tf32_split { float* w_hi; float* lo; int64_t n; } mugd_tf32_split;
+
 typedef struct mugd_op {
     int32_t kind;
     int32_t tag;                           /* free for the host (profiling labels)                          */
     union {
         mugd_gemm gemm; mugd_groupnorm gn; mugd_layernorm ln; mugd_attention attn; mugd_s4conv s4;
         mugd_ddim_update ddim; mugd_transpose tr; mugd_copy2d cp; mugd_step_advance adv; mugd_notes notes;
-        mugd_embed embed;
+        mugd_embed embed; mugd_tf32_split split;
     } u;
 } mugd_op;
 
@@ -281,7 +287,7 @@ int  mugd_debug_set_tc_timing(long long* device_buf);
 /* ---- utility ---------------------------------------------------------------------------------- */
 int  mugd_fill_i32(int32_t* dst, int32_t value, void* stream);
 /* sizeof() of {mugd_op, mugd_gemm, mugd_groupnorm, mugd_layernorm, mugd_attention, mugd_s4conv,
- * mugd_ddim_update, mugd_transpose, mugd_copy2d, mugd_notes, mugd_embed} so a foreign-language mirror can verify its layout */
+ * mugd_ddim_update, mugd_transpose, mugd_copy2d, mugd_notes, mugd_embed, mugd_tf32_split} so a foreign-language mirror can verify its layout */
 int  mugd_abi_sizes(int32_t* out, int32_t n);
 
 #ifdef __cplusplus

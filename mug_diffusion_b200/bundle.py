@@ -6,7 +6,7 @@ The network -> launch-plan compiler is Python (engine.py); what it produces is p
 into a handful of device allocations.  The bundle holds
     manifest.txt        region table (name, bytes, initial contents), the plans in execution order, test inputs, expected outputs
     *.plan              mugd_plan_save files (pointers stored as region + offset)
-    *.bin               region contents: the packed weight blob, the S4 convolution kernels, the per-request tables (timestep
+    *.bin               region contents: the packed weight blob as it is resident (hi in place) + its lo buffer, the S4 convolution kernels, the per-request tables (timestep
                         sinusoids and DDIM coefficients for the chosen S -- host float math, kept out of the C demo), test vectors
 Request flow = DDIMSampler.sample + model.decode (ddim.py:56-196, diffusion.py:49-50):
     emb (time-embedding table) -> ctx (cross-attention K|V) -> audio (concat slots) -> loadx -> S x {eval graph ; update ; advance}
@@ -73,7 +73,7 @@ def export_bundle(model, inp: Dict[str, torch.Tensor], S: int, scale: float, out
         sess.coef[:total].copy_(torch.from_numpy(np.ascontiguousarray(coef)).to(dev))
 
         # ---- regions: every device allocation a plan may point into ----
-        tensors: Dict[str, torch.Tensor] = dict(weights=eng.weights, arena=sess.arena_t, emb_table=sess.emb_table, temb=sess.temb,
+        tensors: Dict[str, torch.Tensor] = dict(weights=eng.weights, weights_lo=eng.weights_lo, arena=sess.arena_t, emb_table=sess.emb_table, temb=sess.temb,
                                                 emb_h1=sess.emb_h1, emb_h2=sess.emb_h2, step=sess.step, coef=sess.coef, ctx=sess.ctx,
                                                 tc_ws=eng.tc_ws, tc_counters=eng.tc_counters, dec_arena=dec.arena_t)
         for i, t in enumerate(sess.ctx_kv):
@@ -81,7 +81,7 @@ def export_bundle(model, inp: Dict[str, torch.Tensor], S: int, scale: float, out
         for i, (_, t) in enumerate(sorted(sess.s4_kt.items())):
             tensors[f"s4_kt{i}"] = t
         tensors.update(st)
-        contents = {"weights", "temb", "coef"} | {k for k in tensors if k.startswith("s4_kt")}       # saved; everything else starts zeroed
+        contents = {"weights", "weights_lo", "temb", "coef"} | {k for k in tensors if k.startswith("s4_kt")}       # saved; everything else starts zeroed
         inputs = {k for k in st if k.startswith("in_")}
         names = list(tensors)
         keep = [n.encode() for n in names]

@@ -120,6 +120,32 @@ int launch_copy2d(const DeviceInfo& dev, const mugd_copy2d& c, cudaStream_t st, 
     return MUGD_OK;
 }
 
+// weight preprocessing for the 3xTF32 GEMM: hi over w, lo beside it (same roundings as the converter warps apply to activations)
+__global__ void __launch_bounds__(256)
+tf32_split_kernel(float* __restrict__ w_hi, float* __restrict__ lo, int64_t n4) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 w = ld_f4(w_hi + i * 4);
+        float4 h, l;
+        uint32_t r;
+#define MUGD_RNA(dst, src) asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(src)); dst = __uint_as_float(r)
+        MUGD_RNA(h.x, w.x); MUGD_RNA(h.y, w.y); MUGD_RNA(h.z, w.z); MUGD_RNA(h.w, w.w);
+        MUGD_RNA(l.x, w.x - h.x); MUGD_RNA(l.y, w.y - h.y); MUGD_RNA(l.z, w.z - h.z); MUGD_RNA(l.w, w.w - h.w);
+#undef MUGD_RNA
+        st_f4(w_hi + i * 4, h);
+        st_f4(lo + i * 4, l);
+    }
+}
+
+int launch_tf32_split(const DeviceInfo& dev, const mugd_tf32_split& s, cudaStream_t st, int* launches) {
+    MUGD_REQUIRE(s.w_hi && s.lo && s.n > 0 && s.n % 4 == 0 && aligned16(s.w_hi) && aligned16(s.lo), "tf32_split: needs 16-byte aligned buffers and n %% 4 == 0");
+    const int64_t n4 = s.n / 4;
+    int blocks = (int)((n4 + 255) / 256);
+    if (blocks > dev.sm_count * 16) blocks = dev.sm_count * 16;
+    MUGD_CHECK_CUDA(launch_k(tf32_split_kernel, dim3(blocks), dim3(256), 0, st, s.w_hi, s.lo, n4));
+    if (launches) *launches += 1;
+    return MUGD_OK;
+}
+
 __global__ void step_advance_kernel(int32_t* step) {
     pdl_trigger();
     pdl_wait();

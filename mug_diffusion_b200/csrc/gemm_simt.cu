@@ -251,6 +251,8 @@ int launch_gemm(const DeviceInfo& dev, const mugd_gemm& g, int default_impl, cud
         if (gemm_tc_supported(g)) return launch_gemm_tc(dev, g, st, launches);
         MUGD_REQUIRE(g.impl != MUGD_GEMM_TC, "gemm: tensor-core path requested but shape unsupported (M=%d N=%d K=%d)", g.M, g.N, g.K);
     }
+    // a weight that was split in place (W_hi == W) no longer holds fp32 values: the FFMA kernel must never read it
+    MUGD_REQUIRE(!(g.W_hi && g.W_hi == g.W), "gemm: W was split into TF32 hi/lo in place, the FFMA kernel needs the plain fp32 weight (M=%d N=%d K=%d)", g.M, g.N, g.K);
     MUGD_REQUIRE(!g.row_moments && !g.ln_stats,
                  "gemm: the row-moment sink / folded LayerNorm exist on the tensor-core path only (M=%d N=%d K=%d fell to the FFMA kernel)", g.M, g.N, g.K);
     GemmParams p;

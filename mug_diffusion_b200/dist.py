@@ -29,13 +29,13 @@ def shard_batch(tensors: Sequence[torch.Tensor], rank: int, world: int) -> List[
 
 
 def broadcast_blob(state_dict: Optional[Dict[str, torch.Tensor]], cfg: ModelConfig, device: torch.device, src: int = 0) -> WeightBlob:
-    """Rank ``src`` packs the state_dict; everybody receives the flat fp32 blob (one broadcast) plus the
+    """Rank ``src`` packs the state_dict; everybody receives the flat fp32 blob (one broadcast of 0.45 GB: plain weights only) plus the
     small layout table (broadcast_object_list).  Works with NCCL (device tensors) and gloo (CPU)."""
     rank = dist.get_rank()
     blob = pack_model(state_dict, cfg.unet, cfg.decoder) if rank == src else None
-    meta = [(blob.entries, blob.meta, blob.numel) if rank == src else None]
+    meta = [(blob.entries, blob.meta, blob.numel, blob.tc, blob.tc_lo_numel) if rank == src else None]
     dist.broadcast_object_list(meta, src=src)
-    entries, bmeta, numel = meta[0]
+    entries, bmeta, numel, tc, tc_lo_numel = meta[0]
     use_cuda = dist.get_backend() == "nccl"
     if rank == src:
         flat = blob.data.to(device) if use_cuda else blob.data
@@ -45,7 +45,8 @@ def broadcast_blob(state_dict: Optional[Dict[str, torch.Tensor]], cfg: ModelConf
     if rank != src:
         blob = WeightBlob()
         blob.entries, blob.meta, blob._size = entries, bmeta, numel
-    blob.data = flat
+        blob.tc, blob.tc_lo_numel = tc, tc_lo_numel
+    blob.data = flat      # plain fp32, every weight once: each rank derives the TF32 hi / lo operands on its own device (MugEngine)
     return blob
 
 

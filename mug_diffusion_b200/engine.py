@@ -195,17 +195,20 @@ def emit_upsample_conv(ops: "OpList", blob: WeightBlob, wfn, prefix: str, x: Vie
 
 
 def tc_weight_map(blob: WeightBlob, wbase: int) -> Dict[int, Tuple[int, int]]:
-    """address of every GEMM weight that has a TF32 hi/lo split in the blob -> (hi address, lo address)"""
-    cached = getattr(blob, "_tc_map", None)
-    if cached is not None and cached[0] == wbase:
-        return cached[1]
-    m = {}
-    for name, e in blob.entries.items():
-        if name.endswith("#hi"):
-            base = name[:-3]
-            m[wbase + 4 * blob.offset(base)] = (wbase + 4 * e.offset, wbase + 4 * blob.offset(base + "#lo"))
-    blob._tc_map = (wbase, m)
-    return m
+    """address of every tensor-core GEMM weight -> (hi address, lo address).  After the engine's device-side split (runtime.MugEngine)
+    hi lives where the plain weight was and lo in the engine's second buffer (``blob.lo_bases[wbase]``; 0 = this engine keeps plain
+    fp32 weights for the exact-fp32 FFMA path: empty map).  A base nobody registered (plan compilation without a device, CPU tests)
+    gets a virtual lo buffer behind the blob."""
+    lo_base = blob.lo_bases.get(wbase, wbase + 4 * blob.numel)
+    if lo_base == 0:
+        return {}
+    cached = getattr(blob, "_tc_maps", None)
+    if cached is None:
+        cached = blob._tc_maps = {}
+    key = (wbase, lo_base)
+    if key not in cached:
+        cached[key] = {wbase + 4 * off: (wbase + 4 * off, lo_base + 4 * lo) for _, off, _, lo in blob.tc}
+    return cached[key]
 
 
 # tags (profiling labels carried in mugd_op.tag)

@@ -39,6 +39,9 @@ class WeightBlob:
         self._size = 0
         self.meta: Dict[str, object] = {}
         self.data: torch.Tensor | None = None      # finalized flat tensor (CPU, then moved)
+        self.tc: List[Tuple[str, int, int, int]] = []   # tensor-core weights: (entry, blob offset, elements, offset in the lo buffer)
+        self.tc_lo_numel = 0
+        self.lo_bases: Dict[int, int] = {}         # device base of an engine's weights -> device base of its lo buffer (0 = not split)
 
     def add(self, name: str, t: torch.Tensor):
         assert name not in self.entries, name
@@ -242,15 +245,18 @@ def pack_model(sd: Dict[str, torch.Tensor], ucfg: UNetConfig, dcfg: DecoderConfi
     if wave_cfg is not None or any(k.startswith("model.wave_model.") for k in sd):
         from .wave import WaveConfig, pack_wave            # the audio encoder, once per request
         pack_wave(blob, sd, wave_cfg or WaveConfig())
-    if tensor_core_split:
-        # pre-split every GEMM weight the tcgen05 kernel can take (K per tap % 32 == 0, N >= 64) into TF32 hi/lo
-        for name in list(blob.entries):
-            e = blob.entries[name]
-            if name.endswith("weight") and len(e.shape) == 2 and e.shape[0] >= 64 and e.shape[1] % 32 == 0:
-                w = _chunk_of(blob, name).view(e.shape)
-                hi, lo = tf32_split(w)
-                blob.add_shaped(name + "#hi", hi)
-                blob.add_shaped(name + "#lo", lo)
+    # Tensor-core weights (K per tap % 32 == 0, N >= 64) get their TF32 hi / lo operands ON THE DEVICE, after the blob has been
+    # uploaded or broadcast (MUGD_OP_TF32_SPLIT: hi over the plain weight, lo in a second buffer).  The host blob -- what is packed,
+    # stored and broadcast -- holds every weight once (0.45 GB; round 1 shipped W + W_hi + W_lo = 1.3 GB).
+    blob.tc = []
+    lo = 0
+    for name in list(blob.entries):
+        e = blob.entries[name]
+        if tensor_core_split and name.endswith("weight") and len(e.shape) == 2 and e.shape[0] >= 64 and e.shape[1] % 32 == 0:
+            n = e.shape[0] * e.shape[1]
+            blob.tc.append((name, e.offset, n, lo))          # (entry, offset in the blob, elements, offset in the lo buffer)
+            lo += (n + ALIGN - 1) // ALIGN * ALIGN
+    blob.tc_lo_numel = lo
     blob.finalize()
     return blob
 

@@ -75,8 +75,10 @@ class MugEngine:
         self.handle = C.c_void_p()
         L_.check(self.lib.mugd_create(self.device.index or 0, C.byref(self.handle)), "mugd_create")
         self.blob = blob if blob is not None else pack_model(state_dict, self.cfg.unet, self.cfg.decoder)
-        self.weights = self.blob.data.to(self.device)          # the ~420 MB HBM-resident blob
+        self.weights = self.blob.data.to(self.device)          # every weight once, fp32 (0.45 GB); tensor-core weights become hi in place
         self.wbase = self.weights.data_ptr()
+        self.weights_lo: Optional[torch.Tensor] = None         # the lo operands of the tensor-core weights (second buffer)
+        self.tc_split_done = False
         self.lock = threading.RLock()
         # split-K scratch of the tensor-core GEMM: all ops run in stream order, so one buffer serves every plan
         # (bound: tiles*splits < 2*SMs tiles of 128x128 fp32)
@@ -98,10 +100,44 @@ class MugEngine:
         # fp32-accurate 3xTF32 split.  Per-handle state; never used by the parity tests or bench.py.
         code = {"auto": L_.GEMM_TC, "simt": L_.GEMM_SIMT, "tc": L_.GEMM_TC, "tc_tf32": L_.GEMM_TC}[impl]
         L_.check(self.lib.mugd_set_gemm_impl(self.handle, code), "set_gemm_impl")
+        if impl == "simt":
+            # the exact-fp32 FFMA path needs the plain weights: restore them if this engine had already split them in place
+            if self.tc_split_done:
+                if self.blob.data.device.type != "cpu":
+                    raise L_.MugdError("this engine's weights were split in place and no host copy exists: build a new engine for gemm_impl='simt'")
+                self.weights.copy_(self.blob.data)
+                self.tc_split_done = False
+            self.blob.lo_bases[self.wbase] = 0
+        else:
+            self._split_tc_weights()
         L_.check(self.lib.mugd_set_tc_single_pass_tf32(self.handle, 1 if impl == "tc_tf32" else 0), "set_tc_single_pass_tf32")
         self.gemm_impl = impl
         self.sessions.clear()
         self.dec_sessions.clear()
+
+    def _split_tc_weights(self):
+        """TF32 hi / lo operands of every tensor-core weight, computed on the device: hi over the plain weight, lo in a second buffer"""
+        shared = getattr(self.blob, "_lo_tensors", None)
+        if shared is None:
+            shared = self.blob._lo_tensors = {}
+        if not self.tc_split_done and self.wbase in shared:
+            # the blob already lives on this device (broadcast_blob over NCCL) and another engine split it in place: share its lo buffer
+            self.weights_lo, self.tc_split_done = shared[self.wbase], True
+        if not self.tc_split_done:
+            if self.weights_lo is None:
+                self.weights_lo = torch.zeros(max(self.blob.tc_lo_numel, 4), device=self.device)
+            if self.weights is self.blob.data:
+                shared[self.wbase] = self.weights_lo
+            ops = OpList()
+            for _, off, n, lo in self.blob.tc:
+                d = L_.Tf32Split()
+                d.w_hi, d.lo, d.n = self.wbase + 4 * off, self.weights_lo.data_ptr() + 4 * lo, n
+                ops.add(L_.OP_TF32_SPLIT, d)
+            st = _stream()
+            for op in ops.ops:
+                L_.check(self.lib.mugd_op_run(self.handle, C.byref(op), st), "tf32_split")
+            self.tc_split_done = True
+        self.blob.lo_bases[self.wbase] = self.weights_lo.data_ptr()
 
     def attach_workspace(self, ops: OpList):
         for op in ops.ops:

@@ -105,3 +105,43 @@ def test_folded_plan_equals_plain_plan():
         assert (kinds.count(L_.OP_LAYERNORM) == 0) == fuse
         del m
     assert rel_err(outs[0], outs[1]) < 2e-5
+
+
+def test_device_side_tf32_split_is_bit_identical_to_the_host_statement(R):
+    """MUGD_OP_TF32_SPLIT: hi over the plain weight, lo beside it -- the same two roundings as packer.tf32_split, bit for bit"""
+    w = g("split_w", (384, 1152), seed=5) * torch.logspace(-6, 3, 1152)[None, :]     # a wide range of exponents
+    hi, lo = tf32_split(w)
+    wc, lc = w.cuda(), torch.full_like(w, 7.0).cuda()
+    ops = OpList()
+    d = L_.Tf32Split()
+    d.w_hi, d.lo, d.n = ptr(wc), ptr(lc), w.numel()
+    ops.add(L_.OP_TF32_SPLIT, d)
+    R.run(ops)
+    assert torch.equal(wc.cpu().view(torch.int32), hi.view(torch.int32))
+    assert torch.equal(lc.cpu().view(torch.int32), lo.view(torch.int32))
+    assert int((wc.view(torch.int32) & 0x1FFF).abs().max()) == 0          # TF32 operands: 13 low mantissa bits clear
+
+
+def test_engine_keeps_every_weight_once_plus_the_lo_halves():
+    """resident weights = the packed fp32 blob (tensor-core weights overwritten by their hi halves) + one lo buffer; the host blob
+    stays plain fp32 and an engine switched to the exact-fp32 FFMA path gets the plain weights back"""
+    from mug_diffusion_b200.config import ModelConfig
+    from mug_diffusion_b200.runtime import MugEngine
+    cfg = ModelConfig()
+    sd = synth.synthetic_state_dict(96, decoder=False)
+    eng = MugEngine(sd, cfg, torch.device("cuda"))
+    blob = eng.blob
+    assert eng.weights.numel() == blob.numel and eng.weights_lo.numel() == blob.tc_lo_numel
+    assert blob.tc_lo_numel < blob.numel                                   # lo exists for the tensor-core weights only
+    assert blob.data.device.type == "cpu"
+    name, off, n, lo = blob.tc[len(blob.tc) // 2]
+    hi_ref, lo_ref = tf32_split(blob.data[off:off + n])
+    assert torch.equal(eng.weights[off:off + n].cpu(), hi_ref) and torch.equal(eng.weights_lo[lo:lo + n].cpu(), lo_ref)
+    in_tc = torch.zeros(blob.numel, dtype=torch.bool)
+    for _, o, m, _ in blob.tc:
+        in_tc[o:o + m] = True
+    assert torch.equal(eng.weights.cpu()[~in_tc], blob.data[~in_tc])       # everything else is untouched
+    eng.set_gemm_impl("simt")
+    assert torch.equal(eng.weights.cpu(), blob.data)
+    eng.set_gemm_impl("auto")
+    assert torch.equal(eng.weights[off:off + n].cpu(), hi_ref)

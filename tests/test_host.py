@@ -175,7 +175,9 @@ def test_tensor_core_planner_invariants(packed, Beff, Lz):
         assert bool(ok.value) == (not small), (g.M, g.N, g.K)
         if not ok.value:
             assert sp.value == 0 and ws.value == 0
+            assert not g.W_hi                                    # FFMA GEMMs must read a weight the device-side TF32 split left alone
             continue
+        assert g.W_hi == g.W                                     # hi lives where the plain weight was: no fp32 duplicate is resident
         n_tc += 1
         ksteps = g.taps * (g.K // 32) + g.K2 // 32
         assert 1 <= sp.value <= ksteps and 1 <= nt.value <= 4096
