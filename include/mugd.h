@@ -270,10 +270,10 @@ int  mugd_set_attention_impl(mugd_handle* h, int impl);
 
 /* ---- measurement aids (process-wide, not needed in production) -------------------------------------
  * planner cost constants of the tensor-core GEMM (us per 32-deep k-step of a 128- and a 256-column tile, us per split-K
- * round trip); values <= 0 keep the current one.  For tuning sweeps (tools/). */
-int  mugd_debug_set_tc_cost(float kstep128_us, float kstep256_us, float split_us);
+ * round trip, fixed us of the two-CTAs-per-SM variant); values <= 0 keep the current one.  For tuning sweeps (tools/). */
+int  mugd_debug_set_tc_cost(float kstep128_us, float kstep256_us, float split_us, float two_cta_fixed_us);
 
-/* force the tensor-core tile width (64, 128 or 256) where legal; 0 = cost model */
+/* force the tensor-core tile variant (64, 128, 256 columns, or 130 = 128 columns built for two CTAs per SM) where legal; 0 = cost model */
 int  mugd_debug_set_tc_tile_n(int bn);
 
 /* CTA (0,0,0) of the tensor-core attention kernel dumps 40 floats per query row of its first key tile

@@ -7,15 +7,15 @@
 
 namespace mugd {
 
-template <int BN, int EPI>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <int BN, int EPI, int OCC = 1>
+__global__ void __launch_bounds__(TC_THREADS, OCC)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmWhi,
                const __grid_constant__ CUtensorMap tmWlo, const __grid_constant__ TcParams p) {
-    using S = TcSmem<BN>;
+    using S = TcSmem<BN, OCC>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // SWIZZLE_128B needs 1024-B alignment
-    const TcBars<BN> B(base);
+    const TcBars<BN, OCC> B(base);
     const int warp = threadIdx.x >> 5;
 #ifdef MUGD_TC_TIMELINE
     if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) p.dbg[0] = gtimer();
@@ -59,7 +59,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // global access of this kernel (epilogue) is ordered behind data that went through that load
         pdl_wait();
     }
-    gemm_tc_tile<BN, true, EPI>(&tmA, &tmA1, &tmA2, &tmB, &tmWhi, &tmWlo, p, blockIdx.x, blockIdx.y, blockIdx.z, base, tmem_base);
+    gemm_tc_tile<BN, true, EPI, OCC>(&tmA, &tmA1, &tmA2, &tmB, &tmWhi, &tmWlo, p, blockIdx.x, blockIdx.y, blockIdx.z, base, tmem_base);
     // ---- teardown (all tcgen05.ld completed before the phase-2 barrier inside the tile function) ----
     __syncthreads();
     if (warp == 2) {
@@ -82,7 +82,13 @@ static long long* g_tc_dbg = nullptr;
 // planner constants: us per k-step of a 128- / 256-wide tile (tools/bench_gemm.py), us per split-K round trip (workspace + reduce
 // launch).  The split cost was 4.0 in round 1; with the slimmer kernels of round 2 the sweep (tools/experiments/sweep_cost.sh:
 // 299 / 303 / 312 / 312 steps/s at 5.0 / 4.0 / 3.0 / 2.0) favours splitting a little more.  mugd_debug_set_tc_cost for sweeps
-static float g_tc_cost[3] = {0.55f, 0.9f, 3.0f};
+// The two-CTAs-per-SM variant (TcSmem<128, 2>) is taken when its estimate -- tiles per SM x k-steps x the 128-wide k-step, two residents
+// sharing one tensor pipe -- beats the best single-resident estimate by more than g_tc_cost[3].  That constant is a CREDIT (negative):
+// the single-resident estimates carry 1.0 us of fill per wave because only their differences matter to the split decision, while a
+// wave really exposes ~7 us of prologue + accumulator drain that two residents hide behind each other's main loop.  Fitted on the
+// per-op tables of Beff = 64 / L = 512 and Beff = 16 / L = 992 (tools/compare_ops.py): every GEMM it picks was measured faster
+// (0.71-0.98x), the ones it leaves alone (fewer tiles than SMs, or long K with < 2 tiles per SM) were slower or even.
+static float g_tc_cost[4] = {0.55f, 0.9f, 3.0f, -6.5f};
 static int g_tc_force_bn = 0;        // experiments: 0 = cost model, 64 / 128 / 256 = force the tile width where legal
 
 // =====================================================================================================
@@ -135,6 +141,7 @@ static int tc_validate_fusions(const mugd_gemm& g) {
 TcGeometry tc_geometry(const mugd_gemm& g, int sm_count, int forced_split) {
     TcGeometry t;
     t.BN = (g.N >= 128) ? 128 : 64;
+    t.occ = 1;
     if (g.conv_mode == MUGD_CONV_NONE) { t.Lrows = g.M; t.Bs = 1; }
     else { t.Lrows = g.Lout; t.Bs = g.M / g.Lout; }
     if (t.Lrows >= TC_BM) {
@@ -155,14 +162,24 @@ TcGeometry tc_geometry(const mugd_gemm& g, int sm_count, int forced_split) {
     // Candidates: tile width 64 for narrow N, 128, 256 when N allows it, each with its best K split.
     int splits = 1;
     float best = 1e30f;
-    static const int cands[3] = {64, 128, 256};
-    for (int cand = 0; cand < 3; ++cand) {
-        const int bn = cands[cand];
-        if (bn > 64 && g.N < bn) break;
+    static const int cands[4] = {64, 128, 256, 130 /* 128 wide, two CTAs per SM */};
+    for (int cand = 0; cand < 4; ++cand) {
+        const int code = cands[cand];
+        const int bn = code == 130 ? 128 : code;
+        const int occ = code == 130 ? 2 : 1;
+        if (bn > 64 && g.N < bn) continue;
         if (bn == 64 && g.N >= 128 && g_tc_force_bn != 64) continue;
-        if (g_tc_force_bn && bn != g_tc_force_bn && !(g_tc_force_bn > g.N && bn == (g.N >= 128 ? 128 : 64))) continue;
+        if (g_tc_force_bn && code != g_tc_force_bn && !((g_tc_force_bn == 256 ? 256 : 128) > g.N && code == (g.N >= 128 ? 128 : 64))) continue;
         const int gx = (g.N + bn - 1) / bn;
         const int tiles = gx * t.gy;
+        if (occ == 2) {
+            // two residents per SM share one tensor pipe: n tiles per SM back to back, one exposed prologue + epilogue
+            if (forced_split > 1 || (tiles <= sm_count && g_tc_force_bn != 130)) continue;
+            const int n = (tiles + sm_count - 1) / sm_count;
+            const float est = g_tc_cost[3] + n * g_tc_cost[0] * t.total_it;
+            if (est < best - 0.25f || g_tc_force_bn == 130) { best = est; splits = 1; t.BN = 128; t.occ = 2; }
+            continue;
+        }
         const float kstep = bn == 256 ? g_tc_cost[1] : (bn == 128 ? g_tc_cost[0] : 0.4f);
         // 256-wide tiles only pay off unsplit (measured: l1/l2 FF1 and the B=64 convs gain 15-25 %, split cases lose)
         const int sp_max = forced_split > 0 ? forced_split : ((tiles < sm_count && bn != 256) ? 16 : 1);
@@ -172,7 +189,7 @@ TcGeometry tc_geometry(const mugd_gemm& g, int sm_count, int forced_split) {
             if (forced_split <= 0 && sp > 1 && tiles * sp > 2 * sm_count) break;   // bounds the workspace: < 2*SMs partial tiles
             const int waves = (tiles * sp + sm_count - 1) / sm_count;
             const float est = waves * (1.0f + kstep * per) + (sp > 1 ? g_tc_cost[2] : 0.0f);
-            if (est < best - 0.25f) { best = est; splits = sp; t.BN = bn; }
+            if (est < best - 0.25f) { best = est; splits = sp; t.BN = bn; t.occ = 1; }
         }
     }
     t.gx = (g.N + t.BN - 1) / t.BN;
@@ -254,13 +271,14 @@ int tc_plan(const DeviceInfo& dev, const mugd_gemm& g, TcPlanned* out) {
     p.tiles_per_sample = t.tiles_per_sample;
     p.single_pass = dev.tc_single_pass ? 1 : 0;
     p.BN = t.BN;
+    p.occ = t.occ;
+    p.gx = t.gx;
+    p.gy = t.gy;
     p.ln_invK = 1.0 / (double)g.K;
     p.it_base = t.total_it / t.splits;
     p.it_rem = t.total_it % t.splits;
     p.hot = {p.Lrows, p.Bs, p.box_l, p.box_b, p.tiles_per_sample, p.it_base, p.it_rem, p.it_main, p.kblocks, p.total_it, p.splits, p.single_pass,
              g.conv_mode, g.tap_shift, g.tap_dilation, p.gx};
-    p.gx = t.gx;
-    p.gy = t.gy;
 #ifdef MUGD_TC_TIMELINE
     p.dbg = g_tc_dbg;
 #endif
@@ -281,6 +299,19 @@ static int tc_launch(const TcPlanned& pl, cudaStream_t st) {
                                  pl.maps[1], pl.maps[2], pl.maps[3], pl.maps[4], pl.maps[5], p));
         MUGD_CHECK_CUDA(launch_k(gemm_tc_reduce_kernel<BN, EPI>, dim3((unsigned)(p.gx * p.gy * TcReduceGeom<BN>::BPT)), dim3(TC_THREADS), 0, st, p));
         return MUGD_OK;
+    }
+    if constexpr (BN == 128) {
+        if (p.occ == 2) {
+            static bool configured2 = false;
+            if (!configured2) {
+                MUGD_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcSmem<BN, 2>::TOTAL));
+                MUGD_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+                configured2 = true;
+            }
+            MUGD_CHECK_CUDA(launch_k(gemm_tc_kernel<BN, EPI, 2>, dim3(p.gx, p.gy, 1), dim3(TC_THREADS), TcSmem<BN, 2>::TOTAL, st, pl.maps[0], pl.maps[1],
+                                     pl.maps[2], pl.maps[3], pl.maps[4], pl.maps[5], p));
+            return MUGD_OK;
+        }
     }
     static bool configured = false;
     if (!configured) {
@@ -320,7 +351,8 @@ int launch_gemm_tc(const DeviceInfo& dev, const mugd_gemm& g, cudaStream_t st, i
 
 }  // namespace mugd
 
-extern "C" int mugd_debug_set_tc_cost(float kstep128_us, float kstep256_us, float split_us) {
+extern "C" int mugd_debug_set_tc_cost(float kstep128_us, float kstep256_us, float split_us, float two_cta_fixed_us) {
+    if (two_cta_fixed_us != 0.f) mugd::g_tc_cost[3] = two_cta_fixed_us;      // may be negative (a credit); 1e9 = never
     if (kstep128_us > 0.f) mugd::g_tc_cost[0] = kstep128_us;
     if (kstep256_us > 0.f) mugd::g_tc_cost[1] = kstep256_us;
     if (split_us > 0.f) mugd::g_tc_cost[2] = split_us;
@@ -328,7 +360,7 @@ extern "C" int mugd_debug_set_tc_cost(float kstep128_us, float kstep256_us, floa
 }
 
 extern "C" int mugd_debug_set_tc_tile_n(int bn) {
-    mugd::g_tc_force_bn = (bn == 64 || bn == 128 || bn == 256) ? bn : 0;
+    mugd::g_tc_force_bn = (bn == 64 || bn == 128 || bn == 256 || bn == 130 /* 128 wide, two CTAs per SM */) ? bn : 0;
     return MUGD_OK;
 }
 

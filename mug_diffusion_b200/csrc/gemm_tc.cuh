@@ -55,6 +55,7 @@ struct TcParams {
     int32_t tiles_per_sample; // when Lrows >= 128
     int32_t single_pass;      // 1: plain TF32 (a_hi*w_hi only, ~2^-11 relative) -- opt-in speed mode, NOT used for parity/bench
     int32_t BN, gx, gy;       // tile width and tile grid (gx column tiles x gy row tiles x splits)
+    int32_t occ;              // CTAs per SM the kernel variant is built for (1; 2 = the two-stage 128-wide variant)
     double ln_invK;           // 1 / K (folded LayerNorm: moments -> mean / variance)
     int32_t it_base, it_rem;  // split z owns k-steps [z*it_base + min(z, it_rem), +it_base + (z < it_rem)): no division on the device
 #ifdef MUGD_TC_TIMELINE
@@ -177,11 +178,16 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
     return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 
-template <int BN>
+// OCC = CTAs resident per SM.  OCC 2 (128-wide tiles only) halves the pipeline to two 48 KB stages and the tensor memory to 256
+// columns so that TWO CTAs share an SM: the same four stages are in flight per SM, but while one CTA drains its accumulator
+// (tcgen05.ld, bias / activation / gate math, global stores: 3-4 us in which its tensor pipe used to idle) the other one's main
+// loop keeps the tensor cores busy.  For GEMMs with more tiles than SMs (big batches).
+template <int BN, int OCC = 1>
 struct TcSmem {
+    static_assert(OCC == 1 || (OCC == 2 && BN == 128), "two CTAs per SM exist for 128-wide tiles");
     static constexpr uint32_t B_BYTES = BN * TC_BK * 4;
     static constexpr uint32_t STAGE_BYTES = TC_A_BYTES + 2 * B_BYTES;     // raw A tile + W_hi + W_lo (a_hi / a_lo live in TMEM)
-    static constexpr int STAGES = (BN == 256) ? 2 : (BN == 128 ? 4 : 6);
+    static constexpr int STAGES = OCC == 2 ? 2 : ((BN == 256) ? 2 : (BN == 128 ? 4 : 6));
     // Decoupled rings (256-wide tiles): only two 80 KB coupled stages would fit, and tied to the A tile the weight tile sat idle
     // while the activations were fetched and split.  Decoupled, the A side is a 2-deep smem ring feeding a 4-deep ring of TMEM
     // operand slots and runs ahead, and the freed shared memory holds a THIRD weight stage; a weight stage is occupied only from
@@ -195,7 +201,8 @@ struct TcSmem {
     static constexpr uint32_t TOTAL = TILE_BYTES + 1024 /*align slack*/ + BAR_BYTES;
     static constexpr int TMEM_NEED = BN + SA * 64;         // accumulator + per slot 32 columns a_hi + 32 columns a_lo
     static constexpr int TMEM_COLS = TMEM_NEED <= 64 ? 64 : (TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512));
-    static_assert(TMEM_NEED <= 512, "tensor memory budget");
+    static_assert(TMEM_NEED <= 512 && TMEM_COLS * OCC <= 512, "tensor memory budget");
+    static_assert((TOTAL + 1024) * OCC <= 227u * 1024u, "shared memory budget");
     static_assert(128u * (BN + 4) * 4u + 1024u <= TILE_BYTES, "the staged accumulator tile + row statistics must fit the pipeline buffers");
 };
 
@@ -279,13 +286,13 @@ __device__ __forceinline__ float4 tc_finish4(const mugd_gemm& g, float* dst, flo
 // phase 2 of the epilogue for one CTA: read the staged accumulator tile from shared memory (row pitch BN+4) and
 // finish it with coalesced global traffic; U float4 per thread in flight, every global load issued before any use.
 // MODE = TC_EPI_LN reads the (mean, rstd) of tile row r from shared memory at rowstat + 8*r (written in phase 1).
-template <int BN, int ACT, int GATE, int MODE>
+template <int BN, int ACT, int GATE, int MODE, int UMAX = 16>
 __device__ __forceinline__ void tc_store_tile(const mugd_gemm& g, uint32_t stage, int m_base, int n0, int rows_valid, const float* rowvec,
                                               uint32_t rowstat, float4 bia, float4 cs) {
     constexpr int SP = BN + 4;
     constexpr int C4 = BN / 4;
     constexpr int NU = TC_BM * C4 / TC_THREADS;          // float4 per thread: 8 / 16 / 32 for BN = 64 / 128 / 256
-    constexpr int U = NU < 16 ? NU : 16;                 // in flight together
+    constexpr int U = NU < UMAX ? NU : UMAX;             // in flight together (two CTAs per SM: 8, the register file is split in two)
     constexpr int SEG = C4 < 32 ? C4 : 32;
     static_assert(TC_THREADS % C4 == 0, "a thread keeps its column quad for the whole tile");
     // this thread's column quad is the same for every row it visits: bias / column sums (bia, cs) were loaded once, before the main loop
@@ -387,9 +394,9 @@ __device__ __forceinline__ void tc_tile_rows(const TcParams& p, int by, int& b_b
 
 // Barrier block of one CTA (at base + TILE_BYTES): full[SAS] conv[SA] empty[SA], decoupled rings add afree[SAS] wfull[SW]
 // wfree[SW]; then accum and the tmem-pointer slot.
-template <int BN>
+template <int BN, int OCC = 1>
 struct TcBars {
-    using S = TcSmem<BN>;
+    using S = TcSmem<BN, OCC>;
     static constexpr int N_DEC = S::DEC ? S::SAS + 2 * S::SW : 0;
     static constexpr int COUNT = S::SAS + 2 * S::SA + N_DEC + 1;
     static_assert(8 * (COUNT + 1) <= (int)S::BAR_BYTES, "barrier block");
@@ -419,14 +426,14 @@ struct TcBars {
 // armed by the caller (TcBars::init) and visible to all threads.  All 256 threads call it; on return every TMA has landed, every
 // MMA has retired and been observed, and the tile (or its partial) is on its way to global memory.
 // PDL: stand-alone launches pass true -- the producer side executes griddepcontrol.wait before touching activations.
-template <int BN, bool PDL, int EPI>
+template <int BN, bool PDL, int EPI, int OCC = 1>
 __device__ __forceinline__ void gemm_tc_tile(const CUtensorMap* tmA, const CUtensorMap* tmA1, const CUtensorMap* tmA2, const CUtensorMap* tmB,
                                              const CUtensorMap* tmWhi, const CUtensorMap* tmWlo, const TcParams& p, int bx, int by, int bz,
                                              uint32_t base, uint32_t tmem_base) {
-    using S = TcSmem<BN>;
+    using S = TcSmem<BN, OCC>;
     constexpr bool DEC = S::DEC;
     constexpr int SAS = S::SAS, SA = S::SA, SW = S::SW;
-    const TcBars<BN> B(base);
+    const TcBars<BN, OCC> B(base);
     auto a_raw = [&](int s) { return DEC ? base + s * TC_A_BYTES : base + s * S::STAGE_BYTES; };
     auto b_hi = [&](int s) { return DEC ? base + SAS * TC_A_BYTES + s * 2 * S::B_BYTES : base + s * S::STAGE_BYTES + TC_A_BYTES; };
     auto b_lo = [&](int s) { return b_hi(s) + S::B_BYTES; };
@@ -660,7 +667,8 @@ __device__ __forceinline__ void gemm_tc_tile(const CUtensorMap* tmA, const CUten
             }
         } else {
             using E = TcEpiTraits<EPI>;
-            tc_store_tile<BN, E::ACT, E::GATE, E::MODE>(g, base, m_base, n0, rows_valid, rowvec, base + S::TILE_BYTES - 1024u, epi_bias, epi_cs);
+            tc_store_tile<BN, E::ACT, E::GATE, E::MODE, OCC == 2 ? 8 : 16>(g, base, m_base, n0, rows_valid, rowvec, base + S::TILE_BYTES - 1024u, epi_bias,
+                                                                           epi_cs);
         }
     }
     TC_STAMP(threadIdx.x == 0, 4);
@@ -748,7 +756,7 @@ __device__ __forceinline__ void tc_reduce_block(const TcParams& p, int blk) {
 
 // ---- host side (gemm_tc.cu) -------------------------------------------------------------------------
 struct TcGeometry {
-    int BN, splits, gx, gy, Lrows, Bs, box_l, box_b, tiles_per_sample, total_it;
+    int BN, occ, splits, gx, gy, Lrows, Bs, box_l, box_b, tiles_per_sample, total_it;
     int64_t ws_floats;
 };
 // one planned tensor-core GEMM: kernel parameters + its six tensor maps (A taps 0..2, second source, W_hi, W_lo)

@@ -171,10 +171,12 @@ def load() -> C.CDLL:
     lib.mugd_set_tc_single_pass_tf32.argtypes = [C.c_void_p, C.c_int]
     lib.mugd_set_attention_impl.argtypes = [C.c_void_p, C.c_int]
     lib.mugd_debug_set_tc_tile_n.argtypes = [C.c_int]
-    lib.mugd_debug_set_tc_cost.argtypes = [C.c_float, C.c_float, C.c_float]
+    lib.mugd_debug_set_tc_cost.argtypes = [C.c_float, C.c_float, C.c_float, C.c_float]
     # measurement switches for tuning sweeps (tools/); none of them changes results
     if os.environ.get("MUGD_TC_COST"):
-        lib.mugd_debug_set_tc_cost(*[float(v) for v in os.environ["MUGD_TC_COST"].split(",")])
+        lib.mugd_debug_set_tc_cost(*([float(v) for v in os.environ["MUGD_TC_COST"].split(",")] + [0.0] * 4)[:4])
+    if os.environ.get("MUGD_TC_TILE"):                       # experiments: force the tile variant (64 / 128 / 256 / 130 = 128 x two CTAs per SM)
+        lib.mugd_debug_set_tc_tile_n(int(os.environ["MUGD_TC_TILE"]))
     if os.environ.get("MUGD_TC_BN"):
         lib.mugd_debug_set_tc_tile_n(int(os.environ["MUGD_TC_BN"]))
     if os.environ.get("MUGD_PDL") in ("0", "1"):

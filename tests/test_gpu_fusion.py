@@ -129,7 +129,7 @@ def test_engine_keeps_every_weight_once_plus_the_lo_halves():
     from mug_diffusion_b200.runtime import MugEngine
     cfg = ModelConfig()
     sd = synth.synthetic_state_dict(96, decoder=False)
-    eng = MugEngine(sd, cfg, torch.device("cuda"))
+    eng = MugEngine(sd, cfg, torch.device("cuda:0"))
     blob = eng.blob
     assert eng.weights.numel() == blob.numel and eng.weights_lo.numel() == blob.tc_lo_numel
     assert blob.tc_lo_numel < blob.numel                                   # lo exists for the tensor-core weights only

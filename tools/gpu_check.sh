@@ -17,6 +17,8 @@ try:
     r = d["roofline"]
     print("steps/s", round(d["value"], 1), "ms/step", round(d["ms_per_step"], 3), "e2e", round(d["e2e"]["value"], 1), "launches/step", d["launches_per_step"])
     print("family ms", r["family_ms_in_graph"], r["family_launches"])
+    for k, w in d.get("secondary", {}).get("workloads", {}).items():
+        print(k, round(w["value"], 1), "e2e", round(w["e2e"]["value"], 1), "frac3xtf32", round(w["roofline"].get("frac_of_3xtf32_ceiling", 0), 3), w["roofline"]["family_ms_in_graph"])
 except Exception as e:
     print("no bench line:", e)
 PY
