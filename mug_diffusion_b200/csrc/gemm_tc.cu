@@ -2,7 +2,7 @@
 // The device code lives in gemm_tc.cuh (shared with other kernels that embed GEMM tiles).
 //
 // Reference call sites are the same as gemm_simt.cu (which remains the exact-fp32 referee and the fallback for
-// shapes this kernel does not take: K % 32 != 0, N < 64, generic upsampling addressing).
+// shapes this kernel does not take: K % 32 != 0, N < 16, generic upsampling addressing).
 #include "gemm_tc.cuh"
 
 namespace mugd {
@@ -114,7 +114,7 @@ static bool tc_shape_ok(const mugd_gemm& g) {
           g.conv_mode == MUGD_CONV_TAPS)) return false;
     if (g.conv_mode == MUGD_CONV_DOWN && g.Lout < 2) return false;
     if (g.K2 % TC_BK != 0 || (g.K2 > 0 && g.conv_mode == MUGD_CONV_DOWN)) return false;
-    return g.K % TC_BK == 0 && g.N >= 64 && g.N % 4 == 0;
+    return g.K % TC_BK == 0 && g.N >= 16 && g.N % 4 == 0;      // narrow outputs (the 16-channel output convs) take a 64-wide tile: the TMA zero-fills the missing weight rows
 }
 
 bool gemm_tc_supported(const mugd_gemm& g) {

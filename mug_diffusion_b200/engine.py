@@ -128,7 +128,7 @@ class OpList:
         if op.kind != L_.OP_GEMM:
             return False
         g = op.u.gemm
-        tc = bool(g.W_hi) and g.K % 32 == 0 and g.K2 % 32 == 0 and g.N >= 64 and g.impl != L_.GEMM_SIMT and g.conv_mode != L_.CONV_UP
+        tc = bool(g.W_hi) and g.K % 32 == 0 and g.K2 % 32 == 0 and g.N >= 16 and g.impl != L_.GEMM_SIMT and g.conv_mode != L_.CONV_UP
         return tc and g.act == L_.ACT_NONE and g.gate == L_.GATE_NONE and not g.ln_stats and not g.row_moments
 
     def groupnorm(self, x: View, y: View, gamma: int, beta: int, B: int, Lrows: int, G: int, silu: bool, tag: int = 0) -> int:

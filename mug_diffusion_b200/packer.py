@@ -245,14 +245,14 @@ def pack_model(sd: Dict[str, torch.Tensor], ucfg: UNetConfig, dcfg: DecoderConfi
     if wave_cfg is not None or any(k.startswith("model.wave_model.") for k in sd):
         from .wave import WaveConfig, pack_wave            # the audio encoder, once per request
         pack_wave(blob, sd, wave_cfg or WaveConfig())
-    # Tensor-core weights (K per tap % 32 == 0, N >= 64) get their TF32 hi / lo operands ON THE DEVICE, after the blob has been
+    # Tensor-core weights (K per tap % 32 == 0, N >= 16) get their TF32 hi / lo operands ON THE DEVICE, after the blob has been
     # uploaded or broadcast (MUGD_OP_TF32_SPLIT: hi over the plain weight, lo in a second buffer).  The host blob -- what is packed,
     # stored and broadcast -- holds every weight once (0.45 GB; round 1 shipped W + W_hi + W_lo = 1.3 GB).
     blob.tc = []
     lo = 0
     for name in list(blob.entries):
         e = blob.entries[name]
-        if tensor_core_split and name.endswith("weight") and len(e.shape) == 2 and e.shape[0] >= 64 and e.shape[1] % 32 == 0:
+        if tensor_core_split and name.endswith("weight") and len(e.shape) == 2 and e.shape[0] >= 16 and e.shape[1] % 32 == 0:
             n = e.shape[0] * e.shape[1]
             blob.tc.append((name, e.offset, n, lo))          # (entry, offset in the blob, elements, offset in the lo buffer)
             lo += (n + ALIGN - 1) // ALIGN * ALIGN

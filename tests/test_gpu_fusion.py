@@ -128,7 +128,7 @@ def test_engine_keeps_every_weight_once_plus_the_lo_halves():
     from mug_diffusion_b200.config import ModelConfig
     from mug_diffusion_b200.runtime import MugEngine
     cfg = ModelConfig()
-    sd = synth.synthetic_state_dict(96, decoder=False)
+    sd = synth.synthetic_state_dict(96)
     eng = MugEngine(sd, cfg, torch.device("cuda:0"))
     blob = eng.blob
     assert eng.weights.numel() == blob.numel and eng.weights_lo.numel() == blob.tc_lo_numel

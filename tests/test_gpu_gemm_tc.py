@@ -44,7 +44,8 @@ def test_tf32_split_is_exact_enough():
     assert int((hi.view(torch.int32) & 0x1FFF).abs().max()) == 0 and int((lo.view(torch.int32) & 0x1FFF).abs().max()) == 0
 
 
-@pytest.mark.parametrize("M,K,N", [(256, 128, 128), (100, 256, 192), (300, 64, 64), (1024, 512, 1536), (4096, 128, 384), (37, 32, 64)])
+@pytest.mark.parametrize("M,K,N", [(256, 128, 128), (100, 256, 192), (300, 64, 64), (1024, 512, 1536), (4096, 128, 384), (37, 32, 64),
+                                   (4096, 128, 16), (700, 256, 40), (16384, 384, 3072)])     # narrow N (zero-filled weight rows), two-CTA variant
 def test_tc_linear(R, M, K, N):
     x, w, b = g("x", (M, K)), g("w", (N, K)) / math.sqrt(K), 0.1 * g("b", (N,))
     ref = F.linear(x.double(), w.double(), b.double())
@@ -56,7 +57,7 @@ def test_tc_linear(R, M, K, N):
 
 
 @pytest.mark.parametrize("B,L,Cin,Cout", [(4, 64, 128, 128), (2, 512, 384, 128), (3, 124, 512, 512), (4, 62, 64, 64), (1, 992, 128, 128),
-                                          (8, 64, 1536, 512), (5, 32, 256, 384), (2, 256, 640, 256)])
+                                          (8, 64, 1536, 512), (5, 32, 256, 384), (2, 256, 640, 256), (8, 512, 128, 16), (64, 512, 128, 256)])
 def test_tc_conv3_same(R, B, L, Cin, Cout):
     x, w, b = g("cx", (B, Cin, L)), g("cw", (Cout, Cin, 3)) / math.sqrt(3 * Cin), 0.1 * g("cb", (Cout,))
     emb, res = g("ce", (B, Cout)), g("cr", (B, Cout, L))

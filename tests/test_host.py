@@ -171,7 +171,7 @@ def test_tensor_core_planner_invariants(packed, Beff, Lz):
         g = o.u.gemm
         ok, sp, nt, ws = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int64()
         assert lib.mugd_gemm_tc_query(None, C.byref(g), 148, C.byref(ok), C.byref(sp), C.byref(ws), C.byref(nt)) == 0
-        small = g.K % 32 != 0 or g.N < 64                       # conv_in (K = 16) and the 16-channel output conv stay on the FFMA kernel
+        small = g.K % 32 != 0 or g.N < 16                       # conv_in (K = 16 per tap) stays on the FFMA kernel
         assert bool(ok.value) == (not small), (g.M, g.N, g.K)
         if not ok.value:
             assert sp.value == 0 and ws.value == 0
