@@ -59,7 +59,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // global access of this kernel (epilogue) is ordered behind data that went through that load
         pdl_wait();
     }
-    gemm_tc_tile<BN, true, EPI, OCC>(&tmA, &tmA1, &tmA2, &tmB, &tmWhi, &tmWlo, p, blockIdx.x, blockIdx.y, blockIdx.z, base, tmem_base);
+    if constexpr (OCC == 2) {
+        // Two residents per SM, launched as at most 2 x SMs CTAs: a CTA walks the tile list with stride gridDim.x (consecutive CTAs
+        // take neighbouring column tiles of one row band: the band's activations are fetched once into L2) and keeps its tensor
+        // memory, its tensor-map cache lines and its warm instruction cache from tile to tile; the barrier rings keep turning
+        // (it0 / acc_phase of gemm_tc_tile), nothing is re-armed.
+        const int n_tiles = p.gx * p.gy;
+        int done = 0;
+        for (int tile = (int)blockIdx.x; tile < n_tiles; tile += (int)gridDim.x, ++done) {
+            gemm_tc_tile<BN, true, EPI, OCC>(&tmA, &tmA1, &tmA2, &tmB, &tmWhi, &tmWlo, p, tile % p.gx, tile / p.gx, 0, base, tmem_base,
+                                             done * p.hot.total_it, (uint32_t)done & 1u);
+            __syncthreads();         // the staged tile has been read: the next tile's TMA may overwrite the pipeline buffers
+        }
+    } else {
+        gemm_tc_tile<BN, true, EPI, OCC>(&tmA, &tmA1, &tmA2, &tmB, &tmWhi, &tmWlo, p, blockIdx.x, blockIdx.y, blockIdx.z, base, tmem_base);
+    }
     // ---- teardown (all tcgen05.ld completed before the phase-2 barrier inside the tile function) ----
     __syncthreads();
     if (warp == 2) {
@@ -272,6 +286,7 @@ int tc_plan(const DeviceInfo& dev, const mugd_gemm& g, TcPlanned* out) {
     p.single_pass = dev.tc_single_pass ? 1 : 0;
     p.BN = t.BN;
     p.occ = t.occ;
+    p.sm_count = dev.sm_count;
     p.gx = t.gx;
     p.gy = t.gy;
     p.ln_invK = 1.0 / (double)g.K;
@@ -308,7 +323,9 @@ static int tc_launch(const TcPlanned& pl, cudaStream_t st) {
                 MUGD_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
                 configured2 = true;
             }
-            MUGD_CHECK_CUDA(launch_k(gemm_tc_kernel<BN, EPI, 2>, dim3(p.gx, p.gy, 1), dim3(TC_THREADS), TcSmem<BN, 2>::TOTAL, st, pl.maps[0], pl.maps[1],
+            const int n_tiles = p.gx * p.gy;
+            const int ctas = n_tiles < 2 * p.sm_count ? n_tiles : 2 * p.sm_count;
+            MUGD_CHECK_CUDA(launch_k(gemm_tc_kernel<BN, EPI, 2>, dim3(ctas, 1, 1), dim3(TC_THREADS), TcSmem<BN, 2>::TOTAL, st, pl.maps[0], pl.maps[1],
                                      pl.maps[2], pl.maps[3], pl.maps[4], pl.maps[5], p));
             return MUGD_OK;
         }

@@ -56,6 +56,7 @@ struct TcParams {
     int32_t single_pass;      // 1: plain TF32 (a_hi*w_hi only, ~2^-11 relative) -- opt-in speed mode, NOT used for parity/bench
     int32_t BN, gx, gy;       // tile width and tile grid (gx column tiles x gy row tiles x splits)
     int32_t occ;              // CTAs per SM the kernel variant is built for (1; 2 = the two-stage 128-wide variant)
+    int32_t sm_count;
     double ln_invK;           // 1 / K (folded LayerNorm: moments -> mean / variance)
     int32_t it_base, it_rem;  // split z owns k-steps [z*it_base + min(z, it_rem), +it_base + (z < it_rem)): no division on the device
 #ifdef MUGD_TC_TIMELINE
@@ -429,7 +430,9 @@ struct TcBars {
 template <int BN, bool PDL, int EPI, int OCC = 1>
 __device__ __forceinline__ void gemm_tc_tile(const CUtensorMap* tmA, const CUtensorMap* tmA1, const CUtensorMap* tmA2, const CUtensorMap* tmB,
                                              const CUtensorMap* tmWhi, const CUtensorMap* tmWlo, const TcParams& p, int bx, int by, int bz,
-                                             uint32_t base, uint32_t tmem_base) {
+                                             uint32_t base, uint32_t tmem_base, int it0 = 0, uint32_t acc_phase = 0) {
+    // it0 / acc_phase: a CTA that runs several tiles one after the other (two-CTAs-per-SM variant) does not re-arm its barriers:
+    // the stage rings simply keep turning -- it0 = k-steps this CTA has already pushed through them, acc_phase = tiles done & 1.
     using S = TcSmem<BN, OCC>;
     constexpr bool DEC = S::DEC;
     constexpr int SAS = S::SAS, SA = S::SA, SW = S::SW;
@@ -479,8 +482,9 @@ __device__ __forceinline__ void gemm_tc_tile(const CUtensorMap* tmA, const CUten
         const uint32_t a_tx = (uint32_t)(h.box_l * h.box_b) * TC_BK * 4;
         const uint32_t w_tx = (h.single_pass ? 1u : 2u) * S::B_BYTES;
         for (int i = 0; i < nit; ++i) {
-            const int s = i % SAS;
-            const uint32_t ph = (uint32_t)(i / SAS) & 1u;
+            const int gi = it0 + i;
+            const int s = gi % SAS;
+            const uint32_t ph = (uint32_t)(gi / SAS) & 1u;
             if constexpr (DEC) mbar_wait(B.afree(s), ph ^ 1u);
             else mbar_wait(B.empty(s), ph ^ 1u);
             if (elect_one()) {
@@ -515,8 +519,9 @@ __device__ __forceinline__ void gemm_tc_tile(const CUtensorMap* tmA, const CUten
     } else if (DEC && warp == 3) {
         // ===================================== weight producer (decoupled rings) ================
         for (int i = 0; i < nit; ++i) {
-            const int s = i % SW;
-            const uint32_t ph = (uint32_t)(i / SW) & 1u;
+            const int gi = it0 + i;
+            const int s = gi % SW;
+            const uint32_t ph = (uint32_t)(gi / SW) & 1u;
             mbar_wait(B.wfree(s), ph ^ 1u);
             if (elect_one()) {
                 const int it = it_begin + i;
@@ -532,11 +537,12 @@ __device__ __forceinline__ void gemm_tc_tile(const CUtensorMap* tmA, const CUten
         // A/B K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
         for (int i = 0; i < nit; ++i) {
-            const int s = i % SA;
-            const uint32_t ph = (uint32_t)(i / SA) & 1u;
-            const int sw = DEC ? i % SW : s;
+            const int gi = it0 + i;
+            const int s = gi % SA;
+            const uint32_t ph = (uint32_t)(gi / SA) & 1u;
+            const int sw = DEC ? gi % SW : s;
             mbar_wait(B.conv(s), ph);
-            if constexpr (DEC) mbar_wait(B.wfull(sw), (uint32_t)(i / SW) & 1u);
+            if constexpr (DEC) mbar_wait(B.wfull(sw), (uint32_t)(gi / SW) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (elect_one()) {
                 TC_STAMP(i < 24, 8 + i * 6 + 3);
@@ -563,9 +569,9 @@ __device__ __forceinline__ void gemm_tc_tile(const CUtensorMap* tmA, const CUten
         __syncwarp();
         // drain: observe the release of the last use of every stage, so that no commit is still on its way to a barrier when the
         // caller re-arms them for the next tile (persistent kernel) or the CTA exits
-        for (int i = (nit > SA ? nit - SA : 0); i < nit; ++i) mbar_wait(B.empty(i % SA), (uint32_t)(i / SA) & 1u);
+        for (int i = (nit > SA ? nit - SA : 0); i < nit; ++i) mbar_wait(B.empty((it0 + i) % SA), (uint32_t)((it0 + i) / SA) & 1u);
         if constexpr (DEC) {
-            for (int i = (nit > SW ? nit - SW : 0); i < nit; ++i) mbar_wait(B.wfree(i % SW), (uint32_t)(i / SW) & 1u);
+            for (int i = (nit > SW ? nit - SW : 0); i < nit; ++i) mbar_wait(B.wfree((it0 + i) % SW), (uint32_t)((it0 + i) / SW) & 1u);
         }
     } else if (warp >= 4) {
         // ===================================== converter ========================================
@@ -580,11 +586,12 @@ __device__ __forceinline__ void gemm_tc_tile(const CUtensorMap* tmA, const CUten
             }
         }
         for (int i = 0; i < nit; ++i) {
-            const int s = i % SA;                                     // TMEM operand slot
-            const int sm = i % SAS;                                   // raw tile in shared memory
-            mbar_wait(B.full(sm), (uint32_t)(i / SAS) & 1u);
+            const int gi = it0 + i;
+            const int s = gi % SA;                                    // TMEM operand slot
+            const int sm = gi % SAS;                                  // raw tile in shared memory
+            mbar_wait(B.full(sm), (uint32_t)(gi / SAS) & 1u);
             if constexpr (DEC) {
-                mbar_wait(B.empty(s), ((uint32_t)(i / SA) & 1u) ^ 1u);   // the MMAs that read TMEM slot s last time have retired
+                mbar_wait(B.empty(s), ((uint32_t)(gi / SA) & 1u) ^ 1u);  // the MMAs that read TMEM slot s last time have retired
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             }
             TC_STAMP(threadIdx.x == 128 && i < 24, 8 + i * 6 + 1);
@@ -618,7 +625,7 @@ __device__ __forceinline__ void gemm_tc_tile(const CUtensorMap* tmA, const CUten
         float2 lnrow = make_float2(0.f, 1.f);
         if constexpr (TcEpiTraits<EPI>::MODE == TC_EPI_LN) lnrow = tc_ln_from_moments(ln_s, ln_ss, p.ln_invK, g.ln_eps);
         // ===================================== epilogue, phase 1 ================================
-        mbar_wait(B.accum(), 0);
+        mbar_wait(B.accum(), acc_phase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         TC_STAMP(threadIdx.x == 128, 2);
         const int q = warp & 3;                                        // TMEM lane quarter this warp may read

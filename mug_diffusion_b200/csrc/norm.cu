@@ -141,6 +141,11 @@ groupnorm_silu_kernel(const float* __restrict__ x, int64_t ldx, float* __restric
     }
 }
 
+// A second form -- one thread-block CLUSTER per sample, CTAs owning bands of whole rows (fully coalesced, gamma / beta per thread,
+// band moments exchanged through distributed shared memory) -- was built and measured in round 2 and lost almost everywhere
+// (profiles/r02_groupnorm_ab.md: 0.30 -> 0.49 ms per step at Beff = 8, 1.29 -> 1.36 at Beff = 64, 0.77 -> 1.03 at L = 992): inside the
+// graph the slabs come out of L2, where the 16..48-byte pieces of this kernel cost little, while two cluster barriers + the DSMEM
+// exchange sit on every launch's critical path.  Removed.
 int launch_groupnorm(const DeviceInfo&, const mugd_groupnorm& g, cudaStream_t st, int* launches) {
     MUGD_REQUIRE(g.B > 0 && g.L > 0 && g.C > 0 && g.G > 0, "groupnorm: empty shape B=%d L=%d C=%d G=%d", g.B, g.L, g.C, g.G);
     MUGD_REQUIRE(g.C % g.G == 0 && (g.C / g.G) % 4 == 0, "groupnorm: C/G must be a multiple of 4 (C=%d G=%d)", g.C, g.G);
