@@ -29,7 +29,7 @@ def shard_batch(tensors: Sequence[torch.Tensor], rank: int, world: int) -> List[
 
 
 def broadcast_blob(state_dict: Optional[Dict[str, torch.Tensor]], cfg: ModelConfig, device: torch.device, src: int = 0) -> WeightBlob:
-    """Rank ``src`` packs the state_dict; everybody receives the flat fp32 blob (one broadcast of 0.45 GB: plain weights only) plus the
+    """Rank ``src`` packs the state_dict; everybody receives the flat fp32 blob (one broadcast of 0.56 GB: plain weights only) plus the
     small layout table (broadcast_object_list).  Works with NCCL (device tensors) and gloo (CPU)."""
     rank = dist.get_rank()
     blob = pack_model(state_dict, cfg.unet, cfg.decoder) if rank == src else None

@@ -75,7 +75,7 @@ class MugEngine:
         self.handle = C.c_void_p()
         L_.check(self.lib.mugd_create(self.device.index or 0, C.byref(self.handle)), "mugd_create")
         self.blob = blob if blob is not None else pack_model(state_dict, self.cfg.unet, self.cfg.decoder)
-        self.weights = self.blob.data.to(self.device)          # every weight once, fp32 (0.45 GB); tensor-core weights become hi in place
+        self.weights = self.blob.data.to(self.device)          # every weight once, fp32 (0.56 GB); tensor-core weights become hi in place
         self.wbase = self.weights.data_ptr()
         self.weights_lo: Optional[torch.Tensor] = None         # the lo operands of the tensor-core weights (second buffer)
         self.tc_split_done = False

@@ -185,10 +185,11 @@ def attn_ref(q, k, v, rel, cg, H, pos_max=64):
 @pytest.mark.parametrize("impl", [1, 0], ids=["tcgen05", "ffma"])
 @pytest.mark.parametrize("B,H,D,Lq,Lk", [(2, 8, 32, 48, 48), (2, 8, 48, 24, 21), (1, 8, 64, 200, 200), (2, 8, 32, 256, 256),
                                          (1, 8, 64, 124, 124), (3, 8, 48, 130, 21), (1, 8, 32, 496, 496), (1, 8, 48, 300, 300),
-                                         (2, 8, 64, 12, 12), (1, 4, 64, 129, 257)])
+                                         (2, 8, 64, 12, 12), (1, 4, 64, 129, 257), (8, 8, 64, 64, 21), (8, 8, 32, 256, 21), (2, 8, 48, 128, 32),
+                                         (1, 8, 32, 70, 1), (2, 8, 64, 33, 33)])
 def test_attention(R, B, H, D, Lq, Lk, impl):
-    """both attention kernels (tensor-core 3xTF32 and the exact FFMA referee) against the fp64 formula; covers several key
-    tiles, ragged last tiles (Lk % 16 != 0), Lq < one tile and the 21-token prompt context"""
+    """the attention kernels (tensor-core 3xTF32, lane-per-key for <= 32 keys, and the exact FFMA referee) against the fp64 formula;
+    covers several key tiles, ragged last tiles (Lk % 16 != 0), Lq < one tile, the 21-token prompt context, 1 / 32 / 33 keys"""
     R.lib.mugd_set_attention_impl(R.handle, impl)
     C = H * D
     q, k, v = g("aq", (B, Lq, C)), g("ak", (B, Lk, C)), g("av", (B, Lk, C))
