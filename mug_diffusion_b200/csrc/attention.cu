@@ -193,36 +193,33 @@ constexpr int ASK_ROWS = ASK_WARPS * ASK_RW;      // query rows per CTA
 
 template <int D>
 __global__ void __launch_bounds__(ASK_WARPS * 32)
-attention_smallk_kernel(const mugd_attention a, int groups) {
+attention_smallk_kernel(const mugd_attention a) {
     constexpr int DV = (D + 31) / 32;                 // output channels per lane
     constexpr int KP = D + 1;                         // K row pitch: lane j reads row j, the odd pitch keeps the lanes on distinct banks
+    constexpr int QD = D / 4;
     extern __shared__ __align__(16) float sm[];
     float* Ks = sm;                                   // [32][KP]
     float* Vs = Ks + 32 * KP;                         // [32][D]
     float* Qs = Vs + 32 * D;                          // [ASK_ROWS][D]
-    float* rel = Qs + ASK_ROWS * D;                   // [2P+1]
-    const int P = a.pos_max, NT = 2 * P + 1;
-    float* cg = rel + NT;
     pdl_wait();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * ASK_ROWS * groups;
-    // the warp's first query rows are requested before anything else: their latency overlaps the K / V / table fill
-    float qpre[ASK_RW][DV];
-    {
-        const int qb0 = q0 + warp * ASK_RW;
+    const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * ASK_ROWS;
+    const int P = a.pos_max;
+    const int qbase = q0 + warp * ASK_RW;             // the warp's ASK_RW query rows go through the kernel together
+    const bool key_ok = lane < a.Lk;
+    // everything this thread needs from global memory is requested up front, in one round trip with the K / V fill: its slice of
+    // the warp's query rows and the bias / gain of (its key, each row) -- 2 x ASK_RW table entries, not the whole 2P+1 table
+    float qpre[ASK_RW][DV], relv[ASK_RW], cgv[ASK_RW];
 #pragma unroll
-        for (int i = 0; i < ASK_RW; ++i) {
-            const int qi = min(qb0 + i, a.Lq - 1);
-            const float* qp = a.q + ((int64_t)b * a.Lq + qi) * a.ldq + h * D;
+    for (int i = 0; i < ASK_RW; ++i) {
+        const int qi = min(qbase + i, a.Lq - 1);      // rows past the end recompute the last row (never stored)
+        const float* qp = a.q + ((int64_t)b * a.Lq + qi) * a.ldq + h * D;
 #pragma unroll
-            for (int c = 0; c < DV; ++c) qpre[i][c] = (lane + c * 32 < D) ? qp[lane + c * 32] : 0.f;
-        }
+        for (int c = 0; c < DV; ++c) qpre[i][c] = (lane + c * 32 < D) ? qp[lane + c * 32] : 0.f;
+        const int idx = max(-P, min(P, lane - (qbase + i))) + P;
+        relv[i] = a.relpos[idx * a.H + h];
+        cgv[i] = a.cgain[idx * a.H + h];
     }
-    for (int t = tid; t < NT; t += ASK_WARPS * 32) {
-        rel[t] = a.relpos[t * a.H + h];
-        cg[t] = a.cgain[t * a.H + h];
-    }
-    constexpr int QD = D / 4;
     const float* kb = a.k + (int64_t)b * a.Lk * a.ldk + h * D;
     const float* vb = a.v + (int64_t)b * a.Lk * a.ldv + h * D;
     for (int t = tid; t < 32 * QD; t += ASK_WARPS * 32) {
@@ -235,94 +232,79 @@ attention_smallk_kernel(const mugd_attention a, int groups) {
         Ks[r * KP + c] = kv.x; Ks[r * KP + c + 1] = kv.y; Ks[r * KP + c + 2] = kv.z; Ks[r * KP + c + 3] = kv.w;
         *reinterpret_cast<float4*>(&Vs[r * D + c]) = vv;
     }
+    float* qrows = Qs + warp * ASK_RW * D;
+#pragma unroll
+    for (int i = 0; i < ASK_RW; ++i)
+#pragma unroll
+        for (int c = 0; c < DV; ++c)
+            if (lane + c * 32 < D) qrows[i * D + lane + c * 32] = qpre[i][c];
     __syncthreads();
+    if (qbase >= a.Lq) return;                        // uniform over the warp; no barrier follows
     float kreg[D];
 #pragma unroll
     for (int d = 0; d < D; ++d) kreg[d] = Ks[lane * KP + d];
-    // the warp's ASK_RW query rows go through the dot products / softmax / PV together: ASK_RW independent dependency chains
-    float* qrows = Qs + warp * ASK_RW * D;
-    const bool key_ok = lane < a.Lk;
-    for (int grp = 0; grp < groups; ++grp) {
-        const int qbase = q0 + grp * ASK_ROWS + warp * ASK_RW;
-        if (qbase >= a.Lq) break;                     // uniform over the warp
-        __syncwarp();                                 // the previous group's broadcast reads are done
+    float s[ASK_RW];
+#pragma unroll
+    for (int i = 0; i < ASK_RW; ++i) s[i] = 0.f;
+#pragma unroll
+    for (int c = 0; c < QD; ++c) {
 #pragma unroll
         for (int i = 0; i < ASK_RW; ++i) {
-            const int qi = min(qbase + i, a.Lq - 1);  // rows past the end recompute the last row (never stored)
-            const float* qp = a.q + ((int64_t)b * a.Lq + qi) * a.ldq + h * D;
+            const float4 qv = *reinterpret_cast<const float4*>(&qrows[i * D + c * 4]);       // broadcast
+            s[i] = fmaf(qv.x, kreg[c * 4], s[i]); s[i] = fmaf(qv.y, kreg[c * 4 + 1], s[i]);
+            s[i] = fmaf(qv.z, kreg[c * 4 + 2], s[i]); s[i] = fmaf(qv.w, kreg[c * 4 + 3], s[i]);
+        }
+    }
+    float mx[ASK_RW], pe[ASK_RW], sum[ASK_RW], pg[ASK_RW];
+#pragma unroll
+    for (int i = 0; i < ASK_RW; ++i) {
+        s[i] = key_ok ? (s[i] + relv[i]) * a.scale : -INFINITY;
+        mx[i] = s[i];
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+        for (int i = 0; i < ASK_RW; ++i) mx[i] = fmaxf(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], off));
+#pragma unroll
+    for (int i = 0; i < ASK_RW; ++i) { pe[i] = expf(s[i] - mx[i]); sum[i] = pe[i]; pg[i] = pe[i] * cgv[i]; }   // pe = 0 for lanes without a key
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+        for (int i = 0; i < ASK_RW; ++i) sum[i] += __shfl_xor_sync(0xffffffffu, sum[i], off);
+    float o[ASK_RW][DV];
+#pragma unroll
+    for (int i = 0; i < ASK_RW; ++i)
+#pragma unroll
+        for (int c = 0; c < DV; ++c) o[i][c] = 0.f;
+    for (int j = 0; j < a.Lk; ++j) {
+        float vj[DV];
+#pragma unroll
+        for (int c = 0; c < DV; ++c) vj[c] = (lane + c * 32 < D) ? Vs[j * D + lane + c * 32] : 0.f;
+#pragma unroll
+        for (int i = 0; i < ASK_RW; ++i) {
+            const float pj = __shfl_sync(0xffffffffu, pg[i], j);
+#pragma unroll
+            for (int c = 0; c < DV; ++c) o[i][c] = fmaf(pj, vj[c], o[i][c]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < ASK_RW; ++i) {
+        const int qi = qbase + i;
+        if (qi < a.Lq) {
+            const float inv = 1.0f / sum[i];
+            float* op = a.o + ((int64_t)b * a.Lq + qi) * a.ldo + h * D;
 #pragma unroll
             for (int c = 0; c < DV; ++c)
-                if (lane + c * 32 < D) qrows[i * D + lane + c * 32] = grp == 0 ? qpre[i][c] : qp[lane + c * 32];
-        }
-        __syncwarp();
-        float s[ASK_RW];
-#pragma unroll
-        for (int i = 0; i < ASK_RW; ++i) s[i] = 0.f;
-#pragma unroll
-        for (int c = 0; c < QD; ++c) {
-#pragma unroll
-            for (int i = 0; i < ASK_RW; ++i) {
-                const float4 qv = *reinterpret_cast<const float4*>(&qrows[i * D + c * 4]);       // broadcast
-                s[i] = fmaf(qv.x, kreg[c * 4], s[i]); s[i] = fmaf(qv.y, kreg[c * 4 + 1], s[i]);
-                s[i] = fmaf(qv.z, kreg[c * 4 + 2], s[i]); s[i] = fmaf(qv.w, kreg[c * 4 + 3], s[i]);
-            }
-        }
-        float mx[ASK_RW], pe[ASK_RW], sum[ASK_RW], pg[ASK_RW];
-#pragma unroll
-        for (int i = 0; i < ASK_RW; ++i) {
-            const int idx = max(-P, min(P, lane - (qbase + i))) + P;
-            s[i] = key_ok ? (s[i] + rel[idx]) * a.scale : -INFINITY;
-            mx[i] = s[i];
-            pg[i] = cg[idx];
-        }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1)
-#pragma unroll
-            for (int i = 0; i < ASK_RW; ++i) mx[i] = fmaxf(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], off));
-#pragma unroll
-        for (int i = 0; i < ASK_RW; ++i) { pe[i] = expf(s[i] - mx[i]); sum[i] = pe[i]; pg[i] *= pe[i]; }   // pe = 0 for lanes without a key
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1)
-#pragma unroll
-            for (int i = 0; i < ASK_RW; ++i) sum[i] += __shfl_xor_sync(0xffffffffu, sum[i], off);
-        float o[ASK_RW][DV];
-#pragma unroll
-        for (int i = 0; i < ASK_RW; ++i)
-#pragma unroll
-            for (int c = 0; c < DV; ++c) o[i][c] = 0.f;
-        for (int j = 0; j < a.Lk; ++j) {
-            float vj[DV];
-#pragma unroll
-            for (int c = 0; c < DV; ++c) vj[c] = (lane + c * 32 < D) ? Vs[j * D + lane + c * 32] : 0.f;
-#pragma unroll
-            for (int i = 0; i < ASK_RW; ++i) {
-                const float pj = __shfl_sync(0xffffffffu, pg[i], j);
-#pragma unroll
-                for (int c = 0; c < DV; ++c) o[i][c] = fmaf(pj, vj[c], o[i][c]);
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < ASK_RW; ++i) {
-            const int qi = qbase + i;
-            if (qi < a.Lq) {
-                const float inv = 1.0f / sum[i];
-                float* op = a.o + ((int64_t)b * a.Lq + qi) * a.ldo + h * D;
-#pragma unroll
-                for (int c = 0; c < DV; ++c)
-                    if (lane + c * 32 < D) op[lane + c * 32] = o[i][c] * inv;
-            }
+                if (lane + c * 32 < D) op[lane + c * 32] = o[i][c] * inv;
         }
     }
 }
 
 template <int D>
-static int attention_smallk_launch(const DeviceInfo&, const mugd_attention& a, cudaStream_t st) {
-    const size_t bytes = sizeof(float) * (32 * (D + 1) + 32 * D + ASK_ROWS * D + 2 * (2 * a.pos_max + 1) + 4);
-    // one 32-row group per CTA: more rows per CTA (fewer re-reads of K / V / tables) measured slower at every batch size
-    const int ngroups = (a.Lq + ASK_ROWS - 1) / ASK_ROWS;
-    const int groups = 1;
-    dim3 grid((ngroups + groups - 1) / groups, a.H, a.B);
-    MUGD_CHECK_CUDA(launch_k(attention_smallk_kernel<D>, grid, dim3(ASK_WARPS * 32), bytes, st, a, groups));
+static int attention_smallk_launch(const mugd_attention& a, cudaStream_t st) {
+    const size_t bytes = sizeof(float) * (32 * (D + 1) + 32 * D + ASK_ROWS * D + 4);
+    dim3 grid((a.Lq + ASK_ROWS - 1) / ASK_ROWS, a.H, a.B);      // (more rows per CTA -- fewer re-reads of K / V -- measured slower)
+    MUGD_CHECK_CUDA(launch_k(attention_smallk_kernel<D>, grid, dim3(ASK_WARPS * 32), bytes, st, a));
     return MUGD_OK;
 }
 
@@ -342,8 +324,7 @@ int launch_attention(const DeviceInfo& dev, const mugd_attention& a, cudaStream_
     // and short and the FFMA lanes saturate (6.9 vs 5.8 us at Beff = 8); with head dim 48 / 64 the lane-per-key kernel wins
     // (5.7 vs 7.6, 4.2 vs 6.5 us at Beff = 8; 26.8 vs 28.0, 17.3 vs 23.9 us at Beff = 64)
     if (dev.attention_impl == 1 && a.Lk <= 32 && a.D >= 48)
-        rc = (a.D == 32) ? attention_smallk_launch<32>(dev, a, st) : (a.D == 48) ? attention_smallk_launch<48>(dev, a, st)
-                         : attention_smallk_launch<64>(dev, a, st);
+        rc = (a.D == 48) ? attention_smallk_launch<48>(a, st) : attention_smallk_launch<64>(a, st);
     else if (dev.attention_impl == 1) rc = launch_attention_tc(dev, a, st);
     else rc = (a.D == 32) ? attention_launch<32>(a, st) : (a.D == 48) ? attention_launch<48>(a, st) : attention_launch<64>(a, st);
     if (rc != MUGD_OK) return rc;

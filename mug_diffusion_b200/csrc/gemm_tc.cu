@@ -86,8 +86,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(TC_THREADS)
 gemm_tc_reduce_kernel(const __grid_constant__ TcParams p) {
-    pdl_wait();
-    tc_reduce_block<BN, EPI>(p, blockIdx.x);
+    tc_reduce_block<BN, EPI>(p, blockIdx.x);           // waits for the GEMM (griddepcontrol.wait) after requesting its weight-side operands
 }
 
 #ifdef MUGD_TC_TIMELINE

@@ -236,10 +236,6 @@ __device__ __forceinline__ float2 tc_ln_from_moments(double s, double ss, double
     r = r * (1.5f - 0.5f * v * r * r);
     return make_float2((float)mean, r);
 }
-__device__ __forceinline__ float2 tc_ln_row(const double* st, int m, double invK, float eps) {
-    const double2 mo = *reinterpret_cast<const double2*>(st + (int64_t)m * 2);
-    return tc_ln_from_moments(mo.x, mo.y, invK, eps);
-}
 
 // epilogue modes of a tile / reduce pass
 constexpr int TC_EPI_PLAIN = 0, TC_EPI_SINK = 1 /* act == gate == NONE + row moments of the output */, TC_EPI_LN = 2 /* LayerNorm folded in */;
@@ -697,67 +693,67 @@ struct TcReduceGeom {
 };
 
 template <int BN, int ACT, int GATE, int MODE>
-__device__ __forceinline__ void tc_reduce_rows(const TcParams& p, int tile_lin, int rb, const float* rowvec) {
+__device__ __forceinline__ void tc_reduce_rows(const TcParams& p, int tile_lin, int rb) {
     using G = TcReduceGeom<BN>;
+    static_assert(TC_RED_R == 1, "one output row per thread");
     constexpr int C4 = G::C4;
     constexpr int SEG = C4 < 32 ? C4 : 32;
+    constexpr int ZU = 8;                              // partial tiles in flight per thread
     const mugd_gemm& g = p.g;
     const int bx = tile_lin % p.gx, by = tile_lin / p.gx;
     int b_base, l_base, rows_valid;
     tc_tile_rows(p, by, b_base, l_base, rows_valid);
     const int m_base = b_base * p.Lrows + l_base;
     const int c4 = (int)threadIdx.x % C4;
-    const int r0 = rb * G::RPB + (int)threadIdx.x / C4;
+    const int r = rb * G::RPB + (int)threadIdx.x / C4;
     const int n = bx * BN + c4 * 4;
-    const float* src = p.ws + ((long long)tile_lin * p.splits) * (TC_BM * BN) + c4 * 4;
-    constexpr int R = TC_RED_R;
-    float4 acc[R];
-    bool ok[R];
-#pragma unroll
-    for (int j = 0; j < R; ++j) {
-        const int r = r0 + j * G::RPP;
-        ok[j] = r < rows_valid && m_base + r < g.M && n < g.N;
-        acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int m = m_base + r;
+    const bool ok = r < rows_valid && m < g.M && n < g.N;
+    // The kernel is one dependent chain of memory round trips; everything that can be asked for early is: bias / column sums are
+    // weights (requested before the wait for the GEMM), then -- behind the wait -- the step counter, the residual quad and the row's
+    // LayerNorm moments go out BEFORE the partial tiles, and up to 8 partial tiles are in flight together.
+    float4 bia = make_float4(0.f, 0.f, 0.f, 0.f), rvv = bia, res = bia, cs = bia;
+    if (ok && g.bias) bia = ld_f4(g.bias + n);
+    if constexpr (MODE == TC_EPI_LN) {
+        if (ok) cs = ld_f4(g.ln_colsum + n);
     }
-#pragma unroll 4
-    for (int z = 0; z < p.splits; ++z) {                                   // fixed order -> deterministic
+    pdl_wait();
+    int step = 0;
+    if (g.step) step = *g.step;
+    if (GATE == MUGD_GATE_NONE && g.residual && ok) res = ld_f4(g.residual + (int64_t)m * g.ldr + n);
+    double2 mo = make_double2(0.0, 1.0);
+    if constexpr (MODE == TC_EPI_LN) {
+        if (ok) mo = *reinterpret_cast<const double2*>(g.ln_stats + (int64_t)m * 2);
+    }
+    const float* src = p.ws + ((long long)tile_lin * p.splits) * (TC_BM * BN) + (long long)r * BN + c4 * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int z0 = 0; z0 < p.splits; z0 += ZU) {                            // fixed order -> deterministic
+        float4 t4[ZU];
 #pragma unroll
-        for (int j = 0; j < R; ++j) {
-            if (ok[j]) {
-                const float4 t4 = __ldcg(reinterpret_cast<const float4*>(src + (long long)z * (TC_BM * BN) + (long long)(r0 + j * G::RPP) * BN));
-                acc[j].x += t4.x; acc[j].y += t4.y; acc[j].z += t4.z; acc[j].w += t4.w;
-            }
+        for (int u = 0; u < ZU; ++u) {
+            t4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok && z0 + u < p.splits) t4[u] = __ldcg(reinterpret_cast<const float4*>(src + (long long)(z0 + u) * (TC_BM * BN)));
         }
-    }
+        if (z0 == 0 && g.rowvec && ok)                                      // needs the step counter: by now it has arrived
+            rvv = ld_f4(g.rowvec + (int64_t)step * g.rowvec_step_stride + (int64_t)(m / g.Lout) * g.rowvec_b_stride + n);
 #pragma unroll
-    for (int j = 0; j < R; ++j) {
-        const int m = m_base + r0 + j * G::RPP;
-        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ok[j]) {
-            float4 bia = make_float4(0.f, 0.f, 0.f, 0.f), rvv = bia, res = bia, cs = bia;
-            float2 ln = make_float2(0.f, 1.f);
-            if (g.bias) bia = ld_f4(g.bias + n);
-            if (rowvec) rvv = ld_f4(rowvec + (int64_t)(m / g.Lout) * g.rowvec_b_stride + n);
-            if (GATE == MUGD_GATE_NONE && g.residual) res = ld_f4(g.residual + (int64_t)m * g.ldr + n);
-            if constexpr (MODE == TC_EPI_LN) {
-                cs = ld_f4(g.ln_colsum + n);
-                ln = tc_ln_row(g.ln_stats, m, p.ln_invK, g.ln_eps);
-            }
-            const int no = (GATE == MUGD_GATE_NONE) ? n : (n >> 1);
-            o = tc_finish4<ACT, GATE, MODE == TC_EPI_LN>(g, g.C + (int64_t)m * g.ldc + no, acc[j], bia, rvv, res, cs, ln, m, no);
-        }
-        if constexpr (MODE == TC_EPI_SINK) tc_row_sink<SEG>(g.row_moments, ok[j] ? m : -1, o);
+        for (int u = 0; u < ZU; ++u) { acc.x += t4[u].x; acc.y += t4[u].y; acc.z += t4[u].z; acc.w += t4[u].w; }
     }
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ok) {
+        float2 ln = make_float2(0.f, 1.f);
+        if constexpr (MODE == TC_EPI_LN) ln = tc_ln_from_moments(mo.x, mo.y, p.ln_invK, g.ln_eps);
+        const int no = (GATE == MUGD_GATE_NONE) ? n : (n >> 1);
+        o = tc_finish4<ACT, GATE, MODE == TC_EPI_LN>(g, g.C + (int64_t)m * g.ldc + no, acc, bia, rvv, res, cs, ln, m, no);
+    }
+    if constexpr (MODE == TC_EPI_SINK) tc_row_sink<SEG>(g.row_moments, ok ? m : -1, o);
 }
 
 template <int BN, int EPI>
 __device__ __forceinline__ void tc_reduce_block(const TcParams& p, int blk) {
     using G = TcReduceGeom<BN>;
     using E = TcEpiTraits<EPI>;
-    const mugd_gemm& g = p.g;
-    const int step = g.step ? *g.step : 0;
-    const float* rowvec = g.rowvec ? g.rowvec + (int64_t)step * g.rowvec_step_stride : nullptr;
-    tc_reduce_rows<BN, E::ACT, E::GATE, E::MODE>(p, blk / G::BPT, blk % G::BPT, rowvec);
+    tc_reduce_rows<BN, E::ACT, E::GATE, E::MODE>(p, blk / G::BPT, blk % G::BPT);
 }
 #endif  // __CUDACC__
 
