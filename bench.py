@@ -552,7 +552,7 @@ def main():
                     ms_per_step=m["ms_per_step"], higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
                     config=config_of(name, wl, world),
                     info=dict(gemm_impl=args.gemm, parallelism=f"replica-sharded batch x{world}",
-                              l2="working set exceeds L2: ~0.8 GB of pre-split fp32 weights are streamed every step",
+                              l2="working set exceeds L2: ~0.8 GB of TF32 hi/lo weight operands are streamed every step",
                               gflop_per_step=Beff * GFLOP_PER_EVAL.get(L, 0.0), outputs_finite=m["finite"]),
                     roofline=m["roofline"], cpu_baseline=cpu, e2e=m["e2e"], secondary=secondary,
                     gpu_launches=m["launches_per_step"] * args.steps, launches_per_step=m["launches_per_step"], clocks=m["clocks"])
