@@ -88,7 +88,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // bounded wait: a protocol bug traps (CUDA error) instead of hanging the GPU
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
-    const long long t0 = clock64();
+    long long t0 = 0;                 // the clock is read only after a probe has failed: the common case costs one try_wait
     while (true) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
@@ -98,7 +98,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "r"(bar), "r"(parity)
             : "memory");
         if (done) break;
-        if (clock64() - t0 > 4000000000LL) __trap();
+        const long long now = clock64();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 4000000000LL) __trap();
     }
 }
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
