@@ -16,7 +16,7 @@ namespace mugd {
 constexpr int GN_THREADS = 256;
 constexpr int GN_MAXV = 32;
 
-__device__ __forceinline__ void gn_block_stats(double s, double ss, double n, float eps, float& mean, float& rstd) {
+__device__ __forceinline__ void gn_block_stats(double s, double ss, double inv_n, float eps, float& mean, float& rstd) {
     __shared__ double red[2][GN_THREADS / 32];
     __shared__ float stats[2];
     s = warp_sum(s);
@@ -28,11 +28,15 @@ __device__ __forceinline__ void gn_block_stats(double s, double ss, double n, fl
         double ts = 0.0, tss = 0.0;
 #pragma unroll
         for (int w = 0; w < GN_THREADS / 32; ++w) { ts += red[0][w]; tss += red[1][w]; }
-        const double m = ts / n;
-        double var = tss / n - m * m;
-        if (var < 0.0) var = 0.0;
+        // the variance is formed in fp64 (E[x^2] - mean^2 cancels); its reciprocal square root in fp32 with one Newton step (~1 ulp)
+        // instead of the ~100-deep fp64 sqrt + divide chain that every thread of the CTA waited for
+        const double m = ts * inv_n;
+        double var = tss * inv_n - m * m;
+        const float v = fmaxf((float)var, 0.f) + eps;
+        float r = rsqrtf(v);
+        r = r * (1.5f - 0.5f * v * r * r);
         stats[0] = (float)m;
-        stats[1] = (float)(1.0 / sqrt(var + (double)eps));
+        stats[1] = r;
     }
     __syncthreads();
     mean = stats[0];
@@ -49,6 +53,7 @@ groupnorm_silu_reg_kernel(const float* __restrict__ x, int64_t ldx, float* __res
     const int cg = C / G;
     const int q = cg >> 2;                 // float4 per row of this group
     const int total = L * q;
+    const double inv_n = 1.0 / ((double)L * cg);       // requested before the loads: off the chain behind the block reduction
     const float* xb = x + (int64_t)b * L * ldx + (int64_t)g * cg;
     float* yb = y + (int64_t)b * L * ldy + (int64_t)g * cg;
     float4 v[NV];
@@ -82,7 +87,7 @@ groupnorm_silu_reg_kernel(const float* __restrict__ x, int64_t ldx, float* __res
         }
     }
     float mean, rstd;
-    gn_block_stats(s, ss, (double)L * cg, eps, mean, rstd);
+    gn_block_stats(s, ss, inv_n, eps, mean, rstd);
 #pragma unroll
     for (int u = 0; u < NV; ++u) {
         const int i = (int)threadIdx.x + u * GN_THREADS;
@@ -112,6 +117,7 @@ groupnorm_silu_kernel(const float* __restrict__ x, int64_t ldx, float* __restric
     const int cg = C / G;
     const int q = cg >> 2;
     const int total = L * q;
+    const double inv_n = 1.0 / ((double)L * cg);       // requested before the loads: off the chain behind the block reduction
     const float* xb = x + (int64_t)b * L * ldx + (int64_t)g * cg;
     float* yb = y + (int64_t)b * L * ldy + (int64_t)g * cg;
 
@@ -123,7 +129,7 @@ groupnorm_silu_kernel(const float* __restrict__ x, int64_t ldx, float* __restric
         ss += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
     }
     float mean, rstd;
-    gn_block_stats(s, ss, (double)L * cg, eps, mean, rstd);
+    gn_block_stats(s, ss, inv_n, eps, mean, rstd);
     const float* gm = gamma + g * cg;
     const float* bt = beta + g * cg;
     for (int i = threadIdx.x; i < total; i += GN_THREADS) {

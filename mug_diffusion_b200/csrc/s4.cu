@@ -81,7 +81,7 @@ s4conv_kernel(const mugd_s4conv s, int nsplit, int Lpad) {
     const float* kz = ks + ch;
     const int nsb = Lpad / (2 * S4_R);                          // super blocks of 16 outputs
     const int npairs = (nsb + 1) / 2;
-    const int worker = blockIdx.z * S4_WARPS + warp;
+    const int worker = warp * nsplit + (int)blockIdx.z;          // interleaved: when there are fewer pairs than workers every CTA of the split keeps some
     const int nworkers = nsplit * S4_WARPS;
     // the cost of super block sb grows linearly with sb (causal): pairing sb with nsb-1-sb gives every worker the same work
     for (int p = worker; p < npairs; p += nworkers) {
@@ -135,7 +135,13 @@ int launch_s4conv(const DeviceInfo& dev, const mugd_s4conv& s, cudaStream_t st, 
     const int base = (s.H / S4_CH) * s.B;
     const int npairs = (Lpad / (2 * S4_R) + 1) / 2;
     int nsplit = 1;
-    while (base * nsplit < 2 * dev.sm_count && nsplit * 2 * S4_WARPS <= npairs && nsplit < 16) nsplit *= 2;
+    // A pair of super blocks is the unit of work (constant cost).  Output blocks are split over more CTAs while every worker (warp) still
+    // gets two pairs -- and, as long as there are fewer CTAs than SMs, even when the doubled CTAs leave half of their warps without
+    // a pair: the busy warps then share a scheduler with fewer others (Beff = 8, L = 512, H = 128: 64 -> 128 CTAs, 20.3 -> 13.6 us;
+    // with the machine already full the same step costs time: Beff = 16, L = 496: 37.2 -> 39.8 us).
+    while (nsplit < 16 && ((base * nsplit < 2 * dev.sm_count && nsplit * 2 * S4_WARPS <= npairs) ||
+                           (base * nsplit < dev.sm_count && nsplit * S4_WARPS <= npairs)))
+        nsplit *= 2;
     dim3 grid(s.H / S4_CH, s.B, nsplit);
     MUGD_CHECK_CUDA(launch_k(s4conv_kernel, grid, dim3(32 * S4_WARPS), smem, st, s, nsplit, Lpad));
     if (launches) *launches += 1;
