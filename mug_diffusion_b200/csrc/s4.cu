@@ -81,8 +81,9 @@ s4conv_kernel(const mugd_s4conv s, int nsplit, int Lpad) {
     const float* kz = ks + ch;
     const int nsb = Lpad / (2 * S4_R);                          // super blocks of 16 outputs
     const int npairs = (nsb + 1) / 2;
-    const int worker = warp * nsplit + (int)blockIdx.z;          // interleaved: when there are fewer pairs than workers every CTA of the split keeps some
     const int nworkers = nsplit * S4_WARPS;
+    // blocked ids normally; interleaved when at most half of the workers get a pair, so that every CTA of the split keeps some
+    const int worker = 2 * npairs > nworkers ? (int)blockIdx.z * S4_WARPS + warp : warp * nsplit + (int)blockIdx.z;
     // the cost of super block sb grows linearly with sb (causal): pairing sb with nsb-1-sb gives every worker the same work
     for (int p = worker; p < npairs; p += nworkers) {
 #pragma unroll 1
