@@ -49,6 +49,7 @@ __device__ __forceinline__ void s4_chunk(float (&acc)[S4_R], const float (&lo)[S
     }
 }
 
+template <bool INTERLEAVE>
 __global__ void __launch_bounds__(32 * S4_WARPS)
 s4conv_kernel(const mugd_s4conv s, int nsplit, int Lpad) {
     extern __shared__ float smem_s4[];
@@ -81,9 +82,9 @@ s4conv_kernel(const mugd_s4conv s, int nsplit, int Lpad) {
     const float* kz = ks + ch;
     const int nsb = Lpad / (2 * S4_R);                          // super blocks of 16 outputs
     const int npairs = (nsb + 1) / 2;
+    // blocked worker ids normally; interleaved (host's choice) when at most half of the workers get a pair, so that every CTA of the split keeps some
+    const int worker = INTERLEAVE ? warp * nsplit + (int)blockIdx.z : (int)blockIdx.z * S4_WARPS + warp;
     const int nworkers = nsplit * S4_WARPS;
-    // blocked ids normally; interleaved when at most half of the workers get a pair, so that every CTA of the split keeps some
-    const int worker = 2 * npairs > nworkers ? (int)blockIdx.z * S4_WARPS + warp : warp * nsplit + (int)blockIdx.z;
     // the cost of super block sb grows linearly with sb (causal): pairing sb with nsb-1-sb gives every worker the same work
     for (int p = worker; p < npairs; p += nworkers) {
 #pragma unroll 1
@@ -130,7 +131,8 @@ int launch_s4conv(const DeviceInfo& dev, const mugd_s4conv& s, cudaStream_t st, 
     MUGD_REQUIRE((int)smem <= dev.max_smem_optin, "s4conv: L=%d needs %zu B of shared memory (max %d)", s.L, smem, dev.max_smem_optin);
     static bool configured = false;
     if (!configured) {
-        MUGD_CHECK_CUDA(cudaFuncSetAttribute(s4conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.max_smem_optin));
+        MUGD_CHECK_CUDA(cudaFuncSetAttribute(s4conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.max_smem_optin));
+        MUGD_CHECK_CUDA(cudaFuncSetAttribute(s4conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.max_smem_optin));
         configured = true;
     }
     const int base = (s.H / S4_CH) * s.B;
@@ -144,7 +146,8 @@ int launch_s4conv(const DeviceInfo& dev, const mugd_s4conv& s, cudaStream_t st, 
                            (base * nsplit < dev.sm_count && nsplit * S4_WARPS <= npairs)))
         nsplit *= 2;
     dim3 grid(s.H / S4_CH, s.B, nsplit);
-    MUGD_CHECK_CUDA(launch_k(s4conv_kernel, grid, dim3(32 * S4_WARPS), smem, st, s, nsplit, Lpad));
+    if (2 * npairs <= nsplit * S4_WARPS) MUGD_CHECK_CUDA(launch_k(s4conv_kernel<true>, grid, dim3(32 * S4_WARPS), smem, st, s, nsplit, Lpad));
+    else MUGD_CHECK_CUDA(launch_k(s4conv_kernel<false>, grid, dim3(32 * S4_WARPS), smem, st, s, nsplit, Lpad));
     if (launches) *launches += 1;
     return MUGD_OK;
 }
