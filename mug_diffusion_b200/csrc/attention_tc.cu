@@ -247,27 +247,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
             sts_f4(k_hi(s) + (uint32_t)f * 16u, hi);
             sts_f4(k_lo + (uint32_t)f * 16u, lo);
         }
-        // ---- value tile: split + transpose into V^T (row = channel, 32-key slabs).  One warp step = 32 keys x one
-        // 16-byte channel chunk: the reads hit 8 distinct swizzled chunks per quarter warp and the 32 lanes of each scalar
-        // store fill one 128-byte row, so both sides are bank-conflict free.
-        for (int it = warp; it < D; it += THREADS / 32) {
-            const int kg = it / (D / 4), c = it - kg * (D / 4);
-            const int key = kg * 32 + (tid & 31);
-            if (key >= NK) continue;
-            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (key < nk) x = lds_f4(v_raw(s) + (uint32_t)(c >> 3) * SLAB + (uint32_t)key * 128u + (uint32_t)(((c & 7) ^ (key & 7)) << 4));
-            const float xs[4] = {x.x, x.y, x.z, x.w};
-            const uint32_t col = (uint32_t)kg * S::VT_SLAB + (uint32_t)((key & 3) << 2);
-            const int kc = (key & 31) >> 2;                 // 16-byte chunk of this key inside its 32-key slab row
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int d = c * 4 + j;
-                const float hi = to_tf32(xs[j]), lo = to_tf32(xs[j] - hi);
-                const uint32_t off = col + (uint32_t)d * 128u + (uint32_t)((kc ^ (d & 7)) << 4);
-                sts_f1(vt_hi + off, hi);
-                sts_f1(vt_lo + off, lo);
-            }
-        }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the MMA / TMA
         fence_before();
         __syncthreads();
@@ -289,6 +268,29 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
             }
             __syncwarp();
         }
+        // ---- value tile (needed by the SECOND contraction only, so it is prepared while the tensor cores work on S): split + transpose
+        // into V^T (row = channel, 32-key slabs).  One warp step = 32 keys x one 16-byte channel chunk: the reads hit 8 distinct
+        // swizzled chunks per quarter warp and the 32 lanes of each scalar store fill one 128-byte row, so both sides are
+        // bank-conflict free.
+        for (int it = warp; it < D; it += THREADS / 32) {
+            const int kg = it / (D / 4), c = it - kg * (D / 4);
+            const int key = kg * 32 + (tid & 31);
+            if (key >= NK) continue;
+            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (key < nk) x = lds_f4(v_raw(s) + (uint32_t)(c >> 3) * SLAB + (uint32_t)key * 128u + (uint32_t)(((c & 7) ^ (key & 7)) << 4));
+            const float xs[4] = {x.x, x.y, x.z, x.w};
+            const uint32_t col = (uint32_t)kg * S::VT_SLAB + (uint32_t)((key & 3) << 2);
+            const int kc = (key & 31) >> 2;                 // 16-byte chunk of this key inside its 32-key slab row
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int d = c * 4 + j;
+                const float hi = to_tf32(xs[j]), lo = to_tf32(xs[j] - hi);
+                const uint32_t off = col + (uint32_t)d * 128u + (uint32_t)((kc ^ (d & 7)) << 4);
+                sts_f1(vt_hi + off, hi);
+                sts_f1(vt_lo + off, lo);
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // V^T writes -> visible to the PV MMAs (issued behind the next barriers)
         mbar_wait(bar_s, ph);
         fence_after();
         // ---- bias, scale, mask, online softmax on this thread's half of the row (logits stay in registers) -------

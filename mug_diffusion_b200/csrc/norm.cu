@@ -18,29 +18,25 @@ constexpr int GN_MAXV = 32;
 
 __device__ __forceinline__ void gn_block_stats(double s, double ss, double inv_n, float eps, float& mean, float& rstd) {
     __shared__ double red[2][GN_THREADS / 32];
-    __shared__ float stats[2];
     s = warp_sum(s);
     ss = warp_sum(ss);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (lane == 0) { red[0][warp] = s; red[1][warp] = ss; }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        double ts = 0.0, tss = 0.0;
+    // every thread adds the eight warp partials itself (broadcast reads, same order everywhere): one barrier instead of
+    // barrier -> thread 0 -> barrier on the critical path of a 3 us kernel
+    double ts = 0.0, tss = 0.0;
 #pragma unroll
-        for (int w = 0; w < GN_THREADS / 32; ++w) { ts += red[0][w]; tss += red[1][w]; }
-        // the variance is formed in fp64 (E[x^2] - mean^2 cancels); its reciprocal square root in fp32 with one Newton step (~1 ulp)
-        // instead of the ~100-deep fp64 sqrt + divide chain that every thread of the CTA waited for
-        const double m = ts * inv_n;
-        double var = tss * inv_n - m * m;
-        const float v = fmaxf((float)var, 0.f) + eps;
-        float r = rsqrtf(v);
-        r = r * (1.5f - 0.5f * v * r * r);
-        stats[0] = (float)m;
-        stats[1] = r;
-    }
-    __syncthreads();
-    mean = stats[0];
-    rstd = stats[1];
+    for (int w = 0; w < GN_THREADS / 32; ++w) { ts += red[0][w]; tss += red[1][w]; }
+    // the variance is formed in fp64 (E[x^2] - mean^2 cancels); its reciprocal square root in fp32 with one Newton step (~1 ulp)
+    // instead of the ~100-deep fp64 sqrt + divide chain
+    const double m = ts * inv_n;
+    const double var = tss * inv_n - m * m;
+    const float v = fmaxf((float)var, 0.f) + eps;
+    float r = rsqrtf(v);
+    r = r * (1.5f - 0.5f * v * r * r);
+    mean = (float)m;
+    rstd = r;
 }
 
 template <int NV>
