@@ -257,6 +257,9 @@ int  mugd_s4_kernel_gen(mugd_handle* h,
  * split-K workspace / how many tile counters does it need (the host allocates them once per plan) ------ */
 int  mugd_gemm_tc_query(mugd_handle* h, const mugd_gemm* g, int32_t sm_count, int32_t* supported, int32_t* splits,
                         int64_t* workspace_bytes, int32_t* n_tiles);
+/* which kernel variant the planner picks for this GEMM on a machine with sm_count SMs: tile width (64 / 128 / 256; 0 = not taken by the
+ * tensor-core kernel), CTAs per SM it is built for (1, or 2 = the 128-wide variant whose CTAs walk a tile list), CTAs launched */
+int  mugd_gemm_tc_variant(const mugd_gemm* g, int32_t sm_count, int32_t* tile_n, int32_t* ctas_per_sm, int32_t* grid_ctas);
 
 /* ---- per-handle switches -------------------------------------------------------------------------
  * OPT-IN speed mode of the tensor-core GEMM: 1 = plain TF32 products (a_hi*w_hi only, ~2^-11 relative error per product, like

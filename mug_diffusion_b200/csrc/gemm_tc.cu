@@ -391,6 +391,24 @@ extern "C" int mugd_debug_set_tc_timing(long long* device_buf) {
 #endif
 }
 
+extern "C" int mugd_gemm_tc_variant(const mugd_gemm* g, int32_t sm_count, int32_t* tile_n, int32_t* ctas_per_sm, int32_t* grid_ctas) {
+    using namespace mugd;
+    MUGD_REQUIRE(g, "gemm_tc_variant: null");
+    if (!tc_shape_ok(*g)) {
+        if (tile_n) *tile_n = 0;
+        if (ctas_per_sm) *ctas_per_sm = 0;
+        if (grid_ctas) *grid_ctas = 0;
+        return MUGD_OK;
+    }
+    const int sms = sm_count > 0 ? sm_count : 148;
+    const TcGeometry t = tc_geometry(*g, sms, g->split_k);
+    const int tiles = t.gx * t.gy;
+    if (tile_n) *tile_n = t.BN;
+    if (ctas_per_sm) *ctas_per_sm = t.occ;
+    if (grid_ctas) *grid_ctas = t.occ == 2 ? (tiles < 2 * sms ? tiles : 2 * sms) : tiles * t.splits;
+    return MUGD_OK;
+}
+
 extern "C" int mugd_gemm_tc_query(mugd_handle*, const mugd_gemm* g, int32_t sm_count, int32_t* supported, int32_t* splits,
                                   int64_t* workspace_bytes, int32_t* n_tiles) {
     using namespace mugd;

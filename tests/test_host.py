@@ -198,3 +198,38 @@ def test_tensor_core_planner_invariants(packed, Beff, Lz):
         assert n_split > 100                                     # small batches underfill 148 SMs: most GEMMs are split
     if Beff == 64:
         assert n_split < n_tc // 2
+
+
+@pytest.mark.parametrize("Beff,Lz", [(8, 512), (64, 512), (16, 992)])
+def test_tensor_core_variant_rule(packed, Beff, Lz):
+    """which GEMM kernel variant the planner picks (pure host code): the two-CTAs-per-SM variant only for unsplit GEMMs with more
+    128-wide tiles than SMs, never more than 2 x SMs CTAs; small batches never see it except for their widest GEMMs"""
+    import ctypes as C
+    cfg, sd, blob = packed
+    lib = L_.load()
+    comp = UNetCompiler(cfg.unet, blob, 1 << 30)
+    res = comp.compile(Arena(1 << 32), Beff, Lz, _fake_ext(comp, Beff, Lz), False)
+    n_two = n_tc = 0
+    for o in res["ops"].ops:
+        if o.kind != L_.OP_GEMM:
+            continue
+        g = o.u.gemm
+        bn, occ, ctas = C.c_int32(), C.c_int32(), C.c_int32()
+        assert lib.mugd_gemm_tc_variant(C.byref(g), 148, C.byref(bn), C.byref(occ), C.byref(ctas)) == 0
+        if bn.value == 0:
+            assert g.K % 32 != 0                                  # only conv_in stays on the FFMA kernel
+            continue
+        n_tc += 1
+        sp, nt = C.c_int32(), C.c_int32()
+        lib.mugd_gemm_tc_query(None, C.byref(g), 148, None, C.byref(sp), None, C.byref(nt))
+        assert bn.value in (64, 128, 256) and occ.value in (1, 2)
+        if occ.value == 2:
+            n_two += 1
+            assert bn.value == 128 and sp.value == 1 and nt.value > 148 and ctas.value == min(nt.value, 296)
+        else:
+            assert ctas.value == nt.value * sp.value
+    assert n_tc >= 190
+    if Beff == 64:
+        assert n_two >= 60                                        # the big batch runs most of its GEMM time on the two-CTA variant
+    if Beff == 8:
+        assert n_two <= 20                                        # only the widest feed-forward GEMMs have more tiles than SMs
