@@ -88,7 +88,10 @@ def main():
             g = arr[idx[0]].u.gemm
             try:
                 eng.lib.mugd_gemm_tc_query(eng.handle, C.byref(g), 148, C.byref(ok), C.byref(sp), None, C.byref(nt))
-                extra = f"tc={ok.value} tiles={nt.value} split={sp.value} TF/s={2.0*g.M*g.N*(g.K*g.taps+g.K2)/us/1e6:.0f}"
+                bn, occ = C.c_int32(), C.c_int32()
+                eng.lib.mugd_gemm_tc_variant(C.byref(g), 148, C.byref(bn), C.byref(occ), None)
+                extra = (f"tc={ok.value} tiles={nt.value} split={sp.value} bn={bn.value}x{occ.value} "
+                         f"TF/s={2.0*g.M*g.N*(g.K*g.taps+g.K2)/us/1e6:.0f}")
             except Exception as e:       # noqa: BLE001
                 extra = str(e)
         rows.append((us * len(idx), len(idx), us, launches, sig, extra))
